@@ -1,0 +1,112 @@
+/*
+ * ohp_schedule.h -- C ABI of the host-side ramp-schedule runner: turns per-stream ramp events
+ * into the chunk descriptors (ohp_chunk_desc) the GPU hot path consumes.
+ *
+ * It replaces, for a batch of independent streams, the control-plane idiom every ramp-setting
+ * pipeline element uses
+ *     if (msg->Jiffies() > remaining) split = msg->Split(remaining);
+ *     current = msg->SetRamp(current, remaining, direction, split);
+ * (Ramper.cpp:114-134, Muter.cpp:210-262, StarvationRamper.cpp:579-603,791-832) followed by
+ * MsgAudioPcm::CreatePlayable (Msg.cpp:2234-2262), MsgSilence::CreatePlayable (Msg.cpp:2472-2492)
+ * and, when a driver block size is given, MsgPlayable::Split (Msg.cpp:2591-2624).
+ *
+ * The message model underneath (Ramp::Set/Split, MsgAudio::SetRamp/Split, Jiffies rounding) is
+ * the C++ mirror in ohpipeline_b200/host/; this header is its plain-C surface.
+ */
+#ifndef OHP_SCHEDULE_H
+#define OHP_SCHEDULE_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "ohp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Jiffies::kPerSecond (Msg.h:193) */
+#define OHP_JIFFIES_PER_SECOND 56448000u
+#define OHP_JIFFIES_PER_MS     56448u
+#define OHP_MAX_STAGES 4u
+
+/* Ramp::EDirection (Msg.h:259-265) */
+#define OHP_DIR_NONE 0u
+#define OHP_DIR_UP   1u
+#define OHP_DIR_DOWN 2u
+#define OHP_DIR_MUTE 3u
+
+typedef enum ohp_event_op {
+    OHP_EV_RAMP_DOWN = 1,       /* arg = duration in jiffies; stage ramps down from its current value,
+                                   then mutes (Muter.cpp:210-262 / StarvationRamper.cpp:579-603)      */
+    OHP_EV_RAMP_UP = 2,         /* arg = duration in jiffies; ramps up from the current value, then runs */
+    OHP_EV_MUTE = 3,            /* stage calls SetMuted on every following message (Muter eMuted)     */
+    OHP_EV_UNMUTE = 4,          /* stage returns to running at Ramp::kMax                            */
+    OHP_EV_SET_ATTENUATION = 5, /* arg = MsgAudioPcm::SetAttenuation value for following PCM msgs (Attenuator.cpp:55-58) */
+    OHP_EV_INSERT_SILENCE = 6,  /* arg = jiffies; a MsgSilence enters the chain ahead of the next PCM msg */
+    OHP_EV_MAX_MSG_JIFFIES = 7  /* arg = jiffies; stage splits larger msgs first (StarvationRamper kMaxAudioOutJiffies,
+                                   StarvationRamper.cpp:802-805); 0 disables                          */
+} ohp_event_op;
+
+typedef struct ohp_ramp_event {
+    uint64_t at_jiffies; /* stream position (jiffies of audio that passed the stage) at which it fires;
+                            a message straddling it is Split() there first                           */
+    uint32_t stage;      /* 0..OHP_MAX_STAGES-1; stages run in index order like pipeline elements    */
+    uint32_t op;         /* ohp_event_op                                                             */
+    uint32_t arg;
+    uint32_t reserved;
+} ohp_ramp_event;
+
+typedef struct ohp_stream_spec {
+    uint32_t sample_rate;       /* one of the 18 PCM rates Jiffies::PerSample accepts (Msg.cpp:424-470) */
+    uint32_t bit_depth;         /* 8/16/24/32                                                          */
+    uint32_t channels;
+    uint32_t in_little_endian;  /* wire format of the stream's PCM (AudioDataEndian)                   */
+    uint32_t chunk_frames;      /* frames per MsgAudioPcm fed into the chain; chunk bytes <= 9216      */
+    uint32_t out_fmt;           /* OHP_OUT_PACKED_BE or OHP_OUT_PACKED_LE                              */
+    uint64_t total_frames;
+    uint64_t src_base;          /* byte offset of the stream's PCM in the input arena                  */
+    uint64_t dst_base;          /* byte offset of the stream's output in the output arena              */
+    uint32_t first_event;       /* slice [first_event, first_event+num_events) of the events array,   */
+    uint32_t num_events;        /*   sorted by at_jiffies                                              */
+    uint32_t driver_block_frames; /* 0: one playable per message; else the driver pulls blocks of this
+                                   many frames and MsgPlayable::Split()s playables to fit              */
+    uint32_t reserved;
+} ohp_stream_spec;
+
+/* Per-chunk facts that are not needed on the device but pin descriptor parity. */
+typedef struct ohp_chunk_info {
+    uint32_t direction; /* Ramp::Direction() of the playable's ramp  */
+    uint32_t jiffies;   /* MsgPlayable::Jiffies()                    */
+} ohp_chunk_info;
+
+typedef struct ohp_schedule ohp_schedule;
+
+/* Run every stream's events through the stage chain (threaded over streams; threads<=0 = all cores). */
+int    ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams,
+                          const ohp_ramp_event* events, size_t n_events,
+                          int threads, ohp_schedule** out);
+size_t ohp_schedule_num_chunks(const ohp_schedule* s);
+const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s);
+const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s);
+/* n_streams+1 prefix offsets into the chunk array */
+const uint64_t* ohp_schedule_stream_chunk_begin(const ohp_schedule* s);
+/* output bytes each stream produces (its chunks' dst ranges tile [dst_base, dst_base+out_bytes)) */
+const uint64_t* ohp_schedule_stream_out_bytes(const ohp_schedule* s);
+const char* ohp_schedule_last_error(void);
+void   ohp_schedule_free(ohp_schedule* s);
+
+/* Scalar helpers mirroring the reference (exported for binding-level tests) ------------------- */
+/* Jiffies::PerSample (Msg.cpp:424-470); 0 for an unsupported rate (the reference throws SampleRateInvalid). */
+uint32_t ohp_jiffies_per_sample(uint32_t sample_rate);
+/* Ramp::Set (Msg.cpp:590-712) on {start,end,direction,enabled}; returns 1 iff a split ramp was produced,
+ * 0 if not, <0 where the reference would ASSERT. */
+typedef struct ohp_ramp { uint32_t start, end, direction, enabled; } ohp_ramp;
+int      ohp_ramp_set(ohp_ramp* ramp, uint32_t start, uint32_t fragment_size, uint32_t remaining_duration,
+                      uint32_t direction, ohp_ramp* split, uint32_t* split_pos);
+/* Ramp::Split (Msg.cpp:784-807): *ramp becomes the first part, returns the remainder in *remaining. */
+int      ohp_ramp_split(ohp_ramp* ramp, uint32_t new_size, uint32_t current_size, ohp_ramp* remaining);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OHP_SCHEDULE_H */

@@ -1,0 +1,90 @@
+"""Plain-data mirror of include/ohp_b200.h and include/ohp_schedule.h (numpy dtypes + constants).
+
+No library is loaded here; see capi.py for the ctypes binding.  Field order and sizes must match the C
+headers exactly -- tests/test_abi.py checks sizeof/offsetof against the built library.
+"""
+import numpy as np
+
+ABI_VERSION = 1
+
+RAMP_MAX = 16384          # Ramp::kMax, OpenHome/Media/Pipeline/Msg.h:257
+RAMP_MIN = 0
+UNITY_ATTENUATION = 256   # MsgAudioPcm::kUnityAttenuation, Msg.cpp:2219
+MAX_PCM_CHUNK_BYTES = 9216  # AudioData::kMaxBytes, Msg.h:117
+JIFFIES_PER_SECOND = 56448000  # Jiffies::kPerSecond, Msg.h:193
+JIFFIES_PER_MS = 56448
+MAX_STAGES = 4
+
+# ohp_status
+OK, E_INVALID_ARG, E_INVALID_DESC, E_NO_DEVICE, E_CUDA, E_OUT_OF_RANGE, E_NO_MEMORY = range(7)
+
+# chunk flags
+F_RAMP_ENABLED = 0x01
+F_SILENCE = 0x02
+F_IN_LITTLE_ENDIAN = 0x04
+
+# ohp_out_fmt
+OUT_PACKED_BE = 0
+OUT_PACKED_LE = 1
+OUT_PLANAR32_BE = 2
+OUT_FROM32_BE = 3
+OUT_SONGCAST = 4
+
+# Ramp::EDirection
+DIR_NONE, DIR_UP, DIR_DOWN, DIR_MUTE = range(4)
+
+# ohp_event_op
+EV_RAMP_DOWN = 1
+EV_RAMP_UP = 2
+EV_MUTE = 3
+EV_UNMUTE = 4
+EV_SET_ATTENUATION = 5
+EV_INSERT_SILENCE = 6
+EV_MAX_MSG_JIFFIES = 7
+
+CHUNK_DESC = np.dtype([
+    ("src_off", "<u8"), ("dst_off", "<u8"), ("bytes", "<u4"),
+    ("ramp_start", "<u2"), ("ramp_end", "<u2"), ("attenuation", "<u2"),
+    ("bit_depth", "u1"), ("channels", "u1"), ("flags", "u1"), ("out_fmt", "u1"),
+    ("aux", "<u2"),
+])
+assert CHUNK_DESC.itemsize == 32
+
+CHUNK_INFO = np.dtype([("direction", "<u4"), ("jiffies", "<u4")])
+
+RAMP_EVENT = np.dtype([
+    ("at_jiffies", "<u8"), ("stage", "<u4"), ("op", "<u4"), ("arg", "<u4"), ("reserved", "<u4"),
+])
+assert RAMP_EVENT.itemsize == 24
+
+STREAM_SPEC = np.dtype([
+    ("sample_rate", "<u4"), ("bit_depth", "<u4"), ("channels", "<u4"), ("in_little_endian", "<u4"),
+    ("chunk_frames", "<u4"), ("out_fmt", "<u4"),
+    ("total_frames", "<u8"), ("src_base", "<u8"), ("dst_base", "<u8"),
+    ("first_event", "<u4"), ("num_events", "<u4"), ("driver_block_frames", "<u4"), ("reserved", "<u4"),
+])
+assert STREAM_SPEC.itemsize == 64
+
+RAMP = np.dtype([("start", "<u4"), ("end", "<u4"), ("direction", "<u4"), ("enabled", "<u4")])
+
+PCM_SAMPLE_RATES = (7350, 8000, 11025, 12000, 14700, 16000, 22050, 24000, 29400, 32000,
+                    44100, 48000, 88200, 96000, 176400, 192000, 352800, 384000)
+
+
+def jiffies_per_sample(rate: int) -> int:
+    """Jiffies::PerSample (Msg.cpp:424-470) for PCM rates; 0 if unsupported."""
+    return JIFFIES_PER_SECOND // rate if rate in PCM_SAMPLE_RATES else 0
+
+
+def chunk_out_bytes(descs: np.ndarray) -> np.ndarray:
+    """Vectorised ohp_chunk_out_bytes."""
+    b = (descs["bit_depth"] // 8).astype(np.uint64)
+    ch = descs["channels"].astype(np.uint64)
+    nbytes = descs["bytes"].astype(np.uint64)
+    frames = nbytes // np.maximum(b * ch, 1)
+    out = nbytes.copy()
+    fmt = descs["out_fmt"]
+    out = np.where(fmt == OUT_PLANAR32_BE, frames * ch * 4, out)
+    out = np.where(fmt == OUT_FROM32_BE, (nbytes // 4) * (descs["aux"].astype(np.uint64) // 8), out)
+    out = np.where(fmt == OUT_SONGCAST, frames * np.minimum(ch, 2) * np.minimum(b, 3), out)
+    return out

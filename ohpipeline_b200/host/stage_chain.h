@@ -1,0 +1,242 @@
+// stage_chain.h -- drives a stream's audio messages through a chain of ramp-setting stages, then
+// through CreatePlayable and a block-pulling driver, exactly as ohPipeline's elements do:
+//
+//     if (msg->Jiffies() > remaining) split = msg->Split(remaining);        // requeued at the head
+//     current = msg->SetRamp(current, remaining, direction, split);         // split requeued too
+//
+// (Ramper.cpp:114-134, Muter.cpp:210-262, StarvationRamper.cpp:579-603, 791-832), then
+// PreDriver -> CreatePlayable (PreDriver.cpp:115-133) and a driver that Split()s playables into
+// fixed blocks (Av/Utils/DriverSongcastSender.cpp:176-199).
+//
+// It is a template over the message API so that ONE statement of the stage logic runs against
+//   * this repo's host mirror (ohpipeline_b200/host/msg_model.h)  -> chunk descriptors for the GPU, and
+//   * the reference's own classes (OpenHome::Media::MsgAudio ...) -> the linked-reference oracle
+//     (oracle/ref_harness.cpp), which is how descriptor parity is checked.
+// The message API must offer the reference's names: Jiffies(), Split(), SetRamp(), SetMuted(),
+// SetAttenuation(), CreatePlayable(), RemoveRef(), MsgPlayable::Split()/Bytes().
+#pragma once
+
+#include <cstdint>
+#include <deque>
+
+#include "../../include/ohp_schedule.h"
+
+namespace ohp {
+
+// Api must provide:
+//   types   MsgAudio, MsgAudioPcm, MsgSilence, MsgPlayable, Factory
+//   consts  kRampMax, kRampMin, kDirUp, kDirDown (of the type SetRamp takes)
+//   static  MsgAudioPcm* CreatePcm(Factory&, const ohp_stream_spec&, uint64_t first_frame, uint32_t frames);
+//   static  MsgSilence*  CreateSilence(Factory&, const ohp_stream_spec&, uint32_t& jiffies);
+//   static  uint32_t     JiffiesPerSample(uint32_t rate);
+//   static  void         Assert(bool) -- raises the API's AssertionFailed
+template <class Api, class Sink>
+class StageChain
+{
+    using MsgAudio = typename Api::MsgAudio;
+    using MsgPlayable = typename Api::MsgPlayable;
+
+    struct Item
+    {
+        MsgAudio* msg;
+        bool silence;
+    };
+    enum Mode { Running = 0, RampingDown = 1, RampingUp = 2, Muted = 3 };
+    struct Stage
+    {
+        std::deque<Item> queue;
+        Mode mode = Running;
+        uint32_t current = Api::kRampMax;
+        uint32_t remaining = 0;
+        uint32_t maxMsg = 0;
+        uint32_t attenuation = OHP_UNITY_ATTENUATION;
+        uint64_t pos = 0;
+        uint32_t nextEv = 0;
+    };
+
+public:
+    StageChain(typename Api::Factory& aFactory, const ohp_stream_spec& aSpec,
+               const ohp_ramp_event* aEvents, Sink& aSink)
+        : iFactory(aFactory), iSpec(aSpec), iEvents(aEvents), iNumEvents(aSpec.num_events), iSink(aSink)
+        , iJps(Api::JiffiesPerSample(aSpec.sample_rate))
+        , iFrameBytes(aSpec.channels * (aSpec.bit_depth / 8u))
+        , iBlockFill(0)
+    {
+    }
+    ~StageChain()
+    {
+        // only non-empty after an assertion unwound Run()
+        for (auto& st : iStages) {
+            for (auto& it : st.queue) {
+                it.msg->RemoveRef();
+            }
+        }
+    }
+    // Returns 0, or -2 for a spec the message model cannot represent.  The API's AssertionFailed propagates.
+    int Run()
+    {
+        if (iJps == 0 || iFrameBytes == 0) return -2;
+        if (iSpec.chunk_frames == 0 || iSpec.chunk_frames * iFrameBytes > OHP_MAX_PCM_CHUNK_BYTES) return -2;
+        uint64_t frame = 0;
+        uint64_t srcJiffies = 0;
+        uint32_t silEv = 0;
+        while (frame < iSpec.total_frames) {
+            for (; silEv < iNumEvents; silEv++) {
+                const ohp_ramp_event& e = iEvents[silEv];
+                if (e.op != OHP_EV_INSERT_SILENCE) continue;
+                if (e.at_jiffies > srcJiffies) break;
+                uint32_t jiffies = e.arg;
+                Item it{Api::CreateSilence(iFactory, iSpec, jiffies), true};
+                Feed(0, it);
+            }
+            const uint64_t left = iSpec.total_frames - frame;
+            const uint32_t frames = (uint32_t)(left < iSpec.chunk_frames ? left : iSpec.chunk_frames);
+            Item it{Api::CreatePcm(iFactory, iSpec, frame, frames), false};
+            Feed(0, it);
+            frame += frames;
+            srcJiffies += (uint64_t)frames * iJps;
+        }
+        return iErr;
+    }
+
+private:
+    bool NextStageEvent(unsigned aStage, uint32_t& aIndex)
+    {
+        Stage& s = iStages[aStage];
+        while (s.nextEv < iNumEvents) {
+            const ohp_ramp_event& e = iEvents[s.nextEv];
+            if (e.stage == aStage && e.op != OHP_EV_INSERT_SILENCE) {
+                aIndex = s.nextEv;
+                return true;
+            }
+            s.nextEv++;
+        }
+        return false;
+    }
+    static void ApplyEvent(Stage& s, const ohp_ramp_event& e)
+    {
+        switch (e.op) {
+        case OHP_EV_RAMP_DOWN:
+            if (s.mode == Muted || s.current == Api::kRampMin) { s.mode = Muted; s.current = Api::kRampMin; s.remaining = 0; }
+            else { s.mode = RampingDown; s.remaining = e.arg; }
+            break;
+        case OHP_EV_RAMP_UP:
+            if (s.mode == Running && s.current == Api::kRampMax) { /* already at full level */ }
+            else { s.mode = RampingUp; s.remaining = e.arg; }
+            break;
+        case OHP_EV_MUTE: s.mode = Muted; s.current = Api::kRampMin; s.remaining = 0; break;
+        case OHP_EV_UNMUTE: s.mode = Running; s.current = Api::kRampMax; s.remaining = 0; break;
+        case OHP_EV_SET_ATTENUATION: s.attenuation = e.arg; break;
+        case OHP_EV_MAX_MSG_JIFFIES: s.maxMsg = e.arg; break;
+        default: break;
+        }
+    }
+    void Process(unsigned aStage, Item& aItem)
+    {
+        Stage& s = iStages[aStage];
+        MsgAudio* msg = aItem.msg;
+        uint32_t ei;
+        while (NextStageEvent(aStage, ei) && iEvents[ei].at_jiffies <= s.pos) {
+            ApplyEvent(s, iEvents[ei]);
+            s.nextEv = ei + 1;
+        }
+        if (NextStageEvent(aStage, ei) && iEvents[ei].at_jiffies < s.pos + msg->Jiffies()) {
+            uint32_t at = (uint32_t)(iEvents[ei].at_jiffies - s.pos);
+            if (aItem.silence) at -= at % iJps; // silence only splits on sample blocks
+            if (at == 0) {
+                ApplyEvent(s, iEvents[ei]);
+                s.nextEv = ei + 1;
+            }
+            else {
+                s.queue.push_front(Item{msg->Split(at), aItem.silence});
+            }
+        }
+        if (s.maxMsg != 0 && msg->Jiffies() > s.maxMsg) {
+            if (s.maxMsg < iJps) { iErr = -2; return; }
+            s.queue.push_front(Item{msg->Split(s.maxMsg), aItem.silence});
+        }
+        if (!aItem.silence && s.attenuation != OHP_UNITY_ATTENUATION) {
+            static_cast<typename Api::MsgAudioPcm*>(msg)->SetAttenuation(s.attenuation);
+        }
+        if (s.mode == RampingDown || s.mode == RampingUp) {
+            if (s.remaining > 0) {
+                if (msg->Jiffies() > s.remaining) {
+                    s.queue.push_front(Item{msg->Split(s.remaining), aItem.silence});
+                    Api::Assert(msg->Jiffies() != 0); // see oracle/ohp_oracle.c stage_process
+                }
+                MsgAudio* split = nullptr;
+                s.current = msg->SetRamp(s.current, s.remaining, s.mode == RampingDown ? Api::kDirDown : Api::kDirUp, split);
+                if (split != nullptr) {
+                    s.queue.push_front(Item{split, aItem.silence});
+                }
+            }
+            if (s.remaining == 0) {
+                if (s.mode == RampingUp) { s.mode = Running; s.current = Api::kRampMax; }
+                else { s.mode = Muted; s.current = Api::kRampMin; }
+            }
+        }
+        else if (s.mode == Muted) {
+            msg->SetMuted();
+        }
+        s.pos += msg->Jiffies();
+    }
+    void Feed(unsigned aStage, Item aItem)
+    {
+        if (iErr) { aItem.msg->RemoveRef(); return; }
+        if (aStage == OHP_MAX_STAGES) { Drive(aItem); return; }
+        Stage& s = iStages[aStage];
+        s.queue.push_back(aItem);
+        while (!s.queue.empty() && !iErr) {
+            Item it = s.queue.front();
+            s.queue.pop_front();
+            try {
+                Process(aStage, it);
+            }
+            catch (...) {
+                it.msg->RemoveRef();
+                throw;
+            }
+            if (iErr) { it.msg->RemoveRef(); return; }
+            Feed(aStage + 1, it);
+        }
+    }
+    void Drive(Item& aItem)
+    {
+        MsgPlayable* playable = aItem.msg->CreatePlayable(); // consumes the msg's reference
+        const uint32_t block = iSpec.driver_block_frames * iFrameBytes;
+        if (block == 0 || playable->Bytes() == 0) {
+            iSink.OnPlayable(playable);
+            return;
+        }
+        for (;;) {
+            const uint32_t room = block - iBlockFill;
+            if (playable->Bytes() > room) {
+                MsgPlayable* remaining = playable->Split(room);
+                iSink.OnPlayable(playable);
+                iBlockFill = 0;
+                playable = remaining;
+            }
+            else {
+                const uint32_t bytes = playable->Bytes();
+                iSink.OnPlayable(playable);
+                iBlockFill += bytes;
+                if (iBlockFill == block) iBlockFill = 0;
+                return;
+            }
+        }
+    }
+
+private:
+    typename Api::Factory& iFactory;
+    const ohp_stream_spec& iSpec;
+    const ohp_ramp_event* iEvents;
+    uint32_t iNumEvents;
+    Sink& iSink;
+    uint32_t iJps;
+    uint32_t iFrameBytes;
+    uint32_t iBlockFill;
+    int iErr = 0;
+    Stage iStages[OHP_MAX_STAGES];
+};
+
+} // namespace ohp

@@ -1,0 +1,215 @@
+"""Synthetic workloads: stream specs + ramp events for BASELINE.json's configs and for randomized parity tests.
+
+Pure host logic (numpy only).  Everything is a function of explicit seeds so that every arm -- the CUDA path,
+the C oracle and the linked reference -- sees identical inputs.
+"""
+import numpy as np
+
+from . import abi
+
+MS = abi.JIFFIES_PER_MS
+
+
+class Workload:
+    """streams: STREAM_SPEC array; events: RAMP_EVENT array; in_bytes/out_bytes: arena sizes; name; seed."""
+
+    def __init__(self, name, streams, events, in_bytes, out_bytes, seed):
+        self.name = name
+        self.streams = streams
+        self.events = events
+        self.in_bytes = int(in_bytes)
+        self.out_bytes = int(out_bytes)
+        self.seed = int(seed)
+
+    @property
+    def total_frames(self):
+        return int(self.streams["total_frames"].sum())
+
+    @property
+    def total_subsamples(self):
+        return int((self.streams["total_frames"] * self.streams["channels"]).sum())
+
+
+def _align(x, a):
+    return (x + a - 1) // a * a
+
+
+def layout(streams, align=16, slack_bytes=None):
+    """Assign src_base/dst_base so streams tile the arenas (each stream `align`-byte aligned).
+
+    Output can exceed input only through inserted silence, which callers account for via slack_bytes
+    (per-stream extra output bytes)."""
+    src = 0
+    dst = 0
+    for i in range(len(streams)):
+        s = streams[i]
+        fb = int(s["channels"]) * int(s["bit_depth"]) // 8
+        nbytes = int(s["total_frames"]) * fb
+        streams[i]["src_base"] = src
+        streams[i]["dst_base"] = dst
+        src = _align(src + nbytes, align)
+        extra = 0 if slack_bytes is None else int(slack_bytes[i])
+        dst = _align(dst + nbytes + extra, align)
+    return src, dst
+
+
+def _spec(rate, bits, ch, le, chunk_frames, total_frames, out_fmt=abi.OUT_PACKED_BE, driver_block_frames=0):
+    s = np.zeros(1, dtype=abi.STREAM_SPEC)[0]
+    s["sample_rate"] = rate
+    s["bit_depth"] = bits
+    s["channels"] = ch
+    s["in_little_endian"] = int(le)
+    s["chunk_frames"] = chunk_frames
+    s["out_fmt"] = out_fmt
+    s["total_frames"] = total_frames
+    s["driver_block_frames"] = driver_block_frames
+    return s
+
+
+def _events(lst):
+    ev = np.zeros(len(lst), dtype=abi.RAMP_EVENT)
+    for i, (at, stage, op, arg) in enumerate(lst):
+        ev[i] = (at, stage, op, arg, 0)
+    return ev
+
+
+def _finish(name, specs, per_stream_events, seed, slack=None):
+    streams = np.array(specs, dtype=abi.STREAM_SPEC)
+    evs = []
+    first = 0
+    for i, lst in enumerate(per_stream_events):
+        lst = sorted(lst, key=lambda e: e[0])
+        streams[i]["first_event"] = first
+        streams[i]["num_events"] = len(lst)
+        first += len(lst)
+        evs.extend(lst)
+    events = _events(evs)
+    in_bytes, out_bytes = layout(streams, slack_bytes=slack)
+    return Workload(name, streams, events, in_bytes, out_bytes, seed)
+
+
+def max_chunk_frames(rate, bits, ch, ms=5):
+    """min(5 ms, 9216 B rounded down to whole frames) -- SURVEY 8d config 4."""
+    fb = ch * bits // 8
+    return max(1, min(rate * ms // 1000, abi.MAX_PCM_CHUNK_BYTES // fb))
+
+
+def config1(seconds=10.0):
+    """BASELINE configs[0]: one stereo 16-bit 44.1 kHz stream, 220-frame chunks; at 3 s a 20 ms ramp down
+    (then muted), at 5 s a 20 ms ramp up."""
+    rate = 44100
+    jps = abi.jiffies_per_sample(rate)
+    total = int(rate * seconds)
+    spec = _spec(rate, 16, 2, False, 220, total)
+    ev = []
+    if seconds >= 6:
+        ev = [(3 * rate * jps, 0, abi.EV_RAMP_DOWN, 20 * MS), (5 * rate * jps, 0, abi.EV_RAMP_UP, 20 * MS)]
+    return _finish("config1: 1 x 2ch/16/44.1k %.3gs, 20 ms down + up" % seconds, [spec], [ev], seed=1 << 32)
+
+
+def config2(n_streams=1024, seconds=10.0):
+    """BASELINE configs[1]: n streams stereo 24-bit 192 kHz, 960-frame (5 ms) chunks, EVERY chunk ramped:
+    a ramp down over the first half of the stream and a ramp up over the second half; packed 24-bit BE out."""
+    rate = 192000
+    jps = abi.jiffies_per_sample(rate)
+    total = int(rate * seconds)
+    total -= total % 2
+    half_j = (total // 2) * jps
+    specs, evs = [], []
+    for _ in range(n_streams):
+        specs.append(_spec(rate, 24, 2, False, 960, total))
+        evs.append([(0, 0, abi.EV_RAMP_DOWN, half_j), (half_j, 0, abi.EV_RAMP_UP, half_j)])
+    return _finish("config2: %d x 2ch/24/192k %.3gs, full-length ramps, packed 24-bit BE" % (n_streams, seconds),
+                   specs, evs, seed=2 << 32)
+
+
+def config3(n_streams=4096, seconds=1.0, rate=48000, n_events=8, seed=3):
+    """BASELINE configs[2]: n streams 8-channel 32-bit LE input, StarvationRamper pattern: K events at random
+    jiffy positions (not aligned to chunks or samples): 20 ms down, mute, 50 ms up; a following event may land
+    inside the ramp up.  Messages are capped at 5 ms like StarvationRamper's output."""
+    jps = abi.jiffies_per_sample(rate)
+    total = int(rate * seconds)
+    chunk = max_chunk_frames(rate, 32, 8)
+    rng = np.random.default_rng(seed)
+    specs, evs = [], []
+    total_j = total * jps
+    for _ in range(n_streams):
+        specs.append(_spec(rate, 32, 8, True, chunk, total))
+        lst = [(0, 1, abi.EV_MAX_MSG_JIFFIES, 5 * MS)]
+        pos = rng.integers(0, max(1, total_j // (n_events + 1)), n_events, dtype=np.int64)
+        t = 0
+        for k in range(n_events):
+            t += int(pos[k]) + 1
+            if t >= total_j:
+                break
+            lst.append((t, 1, abi.EV_RAMP_DOWN, 20 * MS))
+            # next audio after the Halt: ramp up 50 ms; sometimes the next starvation lands mid ramp-up
+            up_at = t + 20 * MS + int(rng.integers(0, 10 * MS))
+            lst.append((up_at, 1, abi.EV_RAMP_UP, 50 * MS))
+            t = up_at + (int(rng.integers(1, 50 * MS)) if rng.random() < 0.4 else 50 * MS)
+        specs[-1]["reserved"] = 0
+        evs.append(lst)
+    return _finish("config3: %d x 8ch/32LE/%dk %.3gs, random starvation ramps" % (n_streams, rate // 1000, seconds),
+                   specs, evs, seed=3 << 32)
+
+
+def config5(n_streams=65536, seconds=1.0):
+    """BASELINE configs[4]: n streams stereo 24-bit 96 kHz, 480-frame chunks; same full-length ramps as config 2."""
+    rate = 96000
+    jps = abi.jiffies_per_sample(rate)
+    total = int(rate * seconds)
+    total -= total % 2
+    half_j = (total // 2) * jps
+    specs, evs = [], []
+    for _ in range(n_streams):
+        specs.append(_spec(rate, 24, 2, False, 480, total))
+        evs.append([(0, 0, abi.EV_RAMP_DOWN, half_j), (half_j, 0, abi.EV_RAMP_UP, half_j)])
+    return _finish("config5: %d x 2ch/24/96k %.3gs, full-length ramps" % (n_streams, seconds), specs, evs, seed=5 << 32)
+
+
+def mixed(n_streams=64, seed=4, max_frames=6000, with_silence=True, p2=True):
+    """BASELINE configs[3] in miniature: random formats (8/16/24/32-bit, 1-8 ch, 44.1-384 kHz, BE/LE, P1/P2),
+    partial ramps, stacked ramps on several stages (-> Ramp::Set merge / intersect / split), muted stretches,
+    MsgSilence, attenuation on 16-bit streams, driver-block MsgPlayable::Split, tiny chunks."""
+    rng = np.random.default_rng(seed)
+    rates = (44100, 48000, 88200, 96000, 176400, 192000, 352800, 384000)
+    specs, evs, slack = [], [], []
+    for i in range(n_streams):
+        bits = int(rng.choice((8, 16, 24, 32)))
+        ch = int(rng.integers(1, 9))
+        rate = int(rng.choice(rates))
+        le = bool(rng.integers(0, 2))
+        jps = abi.jiffies_per_sample(rate)
+        fb = ch * bits // 8
+        cmax = max_chunk_frames(rate, bits, ch)
+        chunk = int(rng.integers(1, cmax + 1)) if rng.random() < 0.3 else cmax
+        total = int(rng.integers(1, max_frames + 1))
+        use_silence = with_silence and rng.random() < 0.3
+        out_fmt = abi.OUT_PACKED_LE if (p2 and bits != 32 and not use_silence and rng.random() < 0.3) else abi.OUT_PACKED_BE
+        block = int(rng.integers(1, 2 * cmax)) if rng.random() < 0.4 else 0
+        spec = _spec(rate, bits, ch, le, chunk, total, out_fmt, block)
+        total_j = total * jps
+        lst = []
+        extra = 0
+        # sample-aligned event grid when silence is in play (a MsgSilence cannot be split inside a sample)
+        q = jps if use_silence else 1
+        n_ev = int(rng.integers(0, 7))
+        for _ in range(n_ev):
+            stage = int(rng.integers(0, 3))
+            at = int(rng.integers(0, total_j + 1)) // q * q
+            dur = int(rng.integers(1, max(2, 2 * total_j))) // q * q + q
+            op = int(rng.choice((abi.EV_RAMP_DOWN, abi.EV_RAMP_UP, abi.EV_RAMP_DOWN, abi.EV_RAMP_UP, abi.EV_MUTE, abi.EV_UNMUTE)))
+            lst.append((at, stage, op, dur if op in (abi.EV_RAMP_DOWN, abi.EV_RAMP_UP) else 0))
+        if rng.random() < 0.3:
+            lst.append((0, int(rng.integers(0, 3)), abi.EV_MAX_MSG_JIFFIES, max(jps, int(rng.integers(jps, 5 * MS)) // q * q)))
+        if bits == 16 and rng.random() < 0.5:
+            lst.append((int(rng.integers(0, total_j + 1)) // q * q, 3, abi.EV_SET_ATTENUATION, int(rng.integers(0, 512))))
+        if use_silence:
+            for _ in range(int(rng.integers(1, 3))):
+                sj = int(rng.integers(1, 200)) * jps
+                lst.append((int(rng.integers(0, total_j)) // jps * jps, 0, abi.EV_INSERT_SILENCE, sj))
+                extra += (sj // jps) * fb
+        specs.append(spec)
+        evs.append(lst)
+        slack.append(extra)
+    return _finish("mixed: %d streams, seed %d" % (n_streams, seed), specs, evs, seed=(4 << 32) + seed, slack=slack)
