@@ -1,0 +1,276 @@
+"""ctypes binding of the C ABI (include/ohp_b200.h, include/ohp_schedule.h).
+
+This is the Python stand-in for the cgo/JNI/ctypes stub a host application would write.
+The libraries are built in-tree by __graft_entry__.build():
+    ohpipeline_b200/libohp_b200.so   CUDA kernels + C ABI (nvcc, sm_100a)
+    ohpipeline_b200/libohp_host.so   host message model + schedule runner (g++)
+There is NO fallback: a missing library raises ImportError-like OhpError at first use, and every compute
+entry point fails with a non-zero status when no sm_100 GPU is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_CUDA = os.path.join(_HERE, "libohp_b200.so")
+LIB_HOST = os.path.join(_HERE, "libohp_host.so")
+
+
+class OhpError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("ohp status %d: %s" % (status, message))
+        self.status = status
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_cuda = None
+_host = None
+
+
+def cuda_lib():
+    """Load libohp_b200.so (raises if it was not built -- there is nothing to fall back to)."""
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(LIB_CUDA):
+            raise OhpError(-1, "%s not built; run __graft_entry__.build()" % LIB_CUDA)
+        L = C.CDLL(LIB_CUDA)
+        L.ohp_abi_version.restype = C.c_uint32
+        L.ohp_device_count.restype = C.c_int
+        L.ohp_create.restype = C.c_int
+        L.ohp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.ohp_destroy.restype = C.c_int
+        L.ohp_destroy.argtypes = [C.c_void_p]
+        L.ohp_last_error.restype = C.c_char_p
+        L.ohp_last_error.argtypes = [C.c_void_p]
+        L.ohp_ramp_table.restype = C.POINTER(C.c_uint16)
+        L.ohp_median_multiplier.restype = C.c_uint32
+        L.ohp_median_multiplier.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.ohp_chunk_out_bytes.restype = C.c_uint32
+        L.ohp_chunk_out_bytes.argtypes = [C.c_void_p]
+        L.ohp_validate.restype = C.c_int
+        L.ohp_validate.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.POINTER(C.c_size_t)]
+        L.ohp_process_device.restype = C.c_int
+        L.ohp_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ohp_process_host.restype = C.c_int
+        L.ohp_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.ohp_sync.restype = C.c_int
+        L.ohp_sync.argtypes = [C.c_void_p, C.c_void_p]
+        L.ohp_checksums_device.restype = C.c_int
+        L.ohp_checksums_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        for name in ("ohp_device_alloc", "ohp_host_alloc"):
+            f = getattr(L, name); f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        for name in ("ohp_device_free", "ohp_host_free"):
+            f = getattr(L, name); f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("ohp_memcpy_h2d", "ohp_memcpy_d2h"):
+            f = getattr(L, name); f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ohp_launch_count.restype = C.c_uint64
+        L.ohp_launch_count.argtypes = [C.c_void_p]
+        L.ohp_set_timing.restype = C.c_int
+        L.ohp_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.ohp_last_kernel_ms.restype = C.c_double
+        L.ohp_last_kernel_ms.argtypes = [C.c_void_p]
+        _cuda = L
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        if not os.path.exists(LIB_HOST):
+            raise OhpError(-1, "%s not built; run __graft_entry__.build()" % LIB_HOST)
+        L = C.CDLL(LIB_HOST)
+        L.ohp_schedule_build.restype = C.c_int
+        L.ohp_schedule_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        L.ohp_schedule_num_chunks.restype = C.c_size_t
+        L.ohp_schedule_num_chunks.argtypes = [C.c_void_p]
+        for name in ("ohp_schedule_chunks", "ohp_schedule_chunk_info", "ohp_schedule_stream_chunk_begin",
+                     "ohp_schedule_stream_out_bytes"):
+            f = getattr(L, name); f.restype = C.c_void_p; f.argtypes = [C.c_void_p]
+        L.ohp_schedule_last_error.restype = C.c_char_p
+        L.ohp_schedule_free.argtypes = [C.c_void_p]
+        L.ohp_jiffies_per_sample.restype = C.c_uint32
+        L.ohp_jiffies_per_sample.argtypes = [C.c_uint32]
+        L.ohp_ramp_set.restype = C.c_int
+        L.ohp_ramp_set.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                   C.POINTER(C.c_uint32)]
+        L.ohp_ramp_split.restype = C.c_int
+        L.ohp_ramp_split.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        _host = L
+    return _host
+
+
+# ---------------------------------------------------------------------------------------------------
+# host message model / schedule runner
+
+def jiffies_per_sample(rate):
+    return int(host_lib().ohp_jiffies_per_sample(rate))
+
+
+def ramp_set(ramp, start, fragment_size, remaining_duration, direction):
+    """Ramp::Set.  ramp = (start, end, direction, enabled).  Returns (rc, ramp, split, split_pos)."""
+    r = np.array([tuple(ramp)], dtype=abi.RAMP)
+    s = np.zeros(1, dtype=abi.RAMP)
+    pos = C.c_uint32(0)
+    rc = host_lib().ohp_ramp_set(_ptr(r), start, fragment_size, remaining_duration, direction, _ptr(s), C.byref(pos))
+    return rc, tuple(int(x) for x in r[0]), tuple(int(x) for x in s[0]), pos.value
+
+
+def ramp_split(ramp, new_size, current_size):
+    r = np.array([tuple(ramp)], dtype=abi.RAMP)
+    rem = np.zeros(1, dtype=abi.RAMP)
+    rc = host_lib().ohp_ramp_split(_ptr(r), new_size, current_size, _ptr(rem))
+    return rc, tuple(int(x) for x in r[0]), tuple(int(x) for x in rem[0])
+
+
+class Schedule:
+    """Result of ohp_schedule_build: chunk descriptors for a batch of streams."""
+
+    def __init__(self, chunks, info, chunk_begin, out_bytes):
+        self.chunks = chunks
+        self.info = info
+        self.stream_chunk_begin = chunk_begin
+        self.stream_out_bytes = out_bytes
+
+
+def schedule_build(streams, events, threads=0):
+    """Run the ramp events of every stream through the stage chain; returns a Schedule.
+    Raises OhpError(E_INVALID_DESC) where the reference would ASSERT."""
+    L = host_lib()
+    streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+    events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+    h = C.c_void_p()
+    rc = L.ohp_schedule_build(_ptr(streams), len(streams), _ptr(events), len(events), threads, C.byref(h))
+    if rc != 0:
+        raise OhpError(rc, L.ohp_schedule_last_error().decode())
+    try:
+        n = L.ohp_schedule_num_chunks(h)
+        chunks = np.zeros(n, dtype=abi.CHUNK_DESC)
+        info = np.zeros(n, dtype=abi.CHUNK_INFO)
+        if n:
+            C.memmove(_ptr(chunks), L.ohp_schedule_chunks(h), n * abi.CHUNK_DESC.itemsize)
+            C.memmove(_ptr(info), L.ohp_schedule_chunk_info(h), n * abi.CHUNK_INFO.itemsize)
+        ns = len(streams)
+        begin = np.zeros(ns + 1, dtype=np.uint64)
+        outb = np.zeros(ns, dtype=np.uint64)
+        C.memmove(_ptr(begin), L.ohp_schedule_stream_chunk_begin(h), (ns + 1) * 8)
+        if ns:
+            C.memmove(_ptr(outb), L.ohp_schedule_stream_out_bytes(h), ns * 8)
+    finally:
+        L.ohp_schedule_free(h)
+    return Schedule(chunks, info, begin, outb)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU context
+
+def device_count():
+    return int(cuda_lib().ohp_device_count())
+
+
+def ramp_table():
+    p = cuda_lib().ohp_ramp_table()
+    return np.array([p[i] for i in range(512)], dtype=np.uint16)
+
+
+def median_multiplier(start, end, direction, enabled):
+    return int(cuda_lib().ohp_median_multiplier(start, end, direction, int(bool(enabled))))
+
+
+def validate(descs, in_bytes, out_bytes):
+    """ohp_validate; returns (status, bad_index)."""
+    descs = np.ascontiguousarray(descs, dtype=abi.CHUNK_DESC)
+    bad = C.c_size_t(0)
+    rc = cuda_lib().ohp_validate(_ptr(descs), len(descs), in_bytes, out_bytes, C.byref(bad))
+    return int(rc), int(bad.value)
+
+
+class Context:
+    """One ohp_context (one GPU).  All pointer arguments are raw addresses (int) or numpy arrays."""
+
+    def __init__(self, device=0):
+        self._L = cuda_lib()
+        h = C.c_void_p()
+        rc = self._L.ohp_create(device, C.byref(h))
+        if rc != 0:
+            raise OhpError(rc, self._L.ohp_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._L.ohp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OhpError(rc, self._L.ohp_last_error(self._h).decode())
+
+    def process_device(self, d_descs, n, d_in, in_bytes, d_out, out_bytes, stream=None):
+        """Asynchronous: device pointers (ints).  stream = raw cudaStream_t or None."""
+        self._check(self._L.ohp_process_device(self._h, C.c_void_p(d_descs), n, C.c_void_p(d_in), in_bytes,
+                                               C.c_void_p(d_out), out_bytes, C.c_void_p(stream or 0)))
+
+    def process_host(self, descs, inp, out):
+        """Synchronous, host numpy buffers: H2D + kernel + D2H inside the call."""
+        descs = np.ascontiguousarray(descs, dtype=abi.CHUNK_DESC)
+        assert inp.dtype == np.uint8 and out.dtype == np.uint8 and inp.flags.c_contiguous and out.flags.c_contiguous
+        self._check(self._L.ohp_process_host(self._h, _ptr(descs), len(descs), _ptr(inp), inp.size, _ptr(out), out.size))
+
+    def process_host_ptr(self, descs_ptr, n, in_ptr, in_bytes, out_ptr, out_bytes):
+        self._check(self._L.ohp_process_host(self._h, C.c_void_p(descs_ptr), n, C.c_void_p(in_ptr), in_bytes,
+                                             C.c_void_p(out_ptr), out_bytes))
+
+    def sync(self, stream=None):
+        self._check(self._L.ohp_sync(self._h, C.c_void_p(stream or 0)))
+
+    def checksums_device(self, d_out, d_stream_off, n_streams, d_sums, stream=None):
+        self._check(self._L.ohp_checksums_device(self._h, C.c_void_p(d_out), C.c_void_p(d_stream_off), n_streams,
+                                                 C.c_void_p(d_sums), C.c_void_p(stream or 0)))
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._L.ohp_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self._L.ohp_device_free(self._h, C.c_void_p(ptr)))
+
+    def host_alloc(self, nbytes):
+        """Pinned host memory as a numpy uint8 array (freed with host_free(arr))."""
+        p = C.c_void_p()
+        self._check(self._L.ohp_host_alloc(self._h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        return arr, p.value
+
+    def host_free(self, ptr):
+        self._check(self._L.ohp_host_free(self._h, C.c_void_p(ptr)))
+
+    def memcpy_h2d(self, dptr, harr, stream=None):
+        self._check(self._L.ohp_memcpy_h2d(self._h, C.c_void_p(dptr), _ptr(harr), harr.nbytes, C.c_void_p(stream or 0)))
+
+    def memcpy_d2h(self, harr, dptr, stream=None):
+        self._check(self._L.ohp_memcpy_d2h(self._h, _ptr(harr), C.c_void_p(dptr), harr.nbytes, C.c_void_p(stream or 0)))
+
+    def launch_count(self):
+        return int(self._L.ohp_launch_count(self._h))
+
+    def set_timing(self, enabled):
+        self._check(self._L.ohp_set_timing(self._h, int(bool(enabled))))
+
+    def last_kernel_ms(self):
+        return float(self._L.ohp_last_kernel_ms(self._h))

@@ -1,0 +1,626 @@
+// ohp_capi.cu -- kernels' __global__ entry points and the C ABI declared in include/ohp_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU fallback anywhere in this file: without a usable sm_100 device every compute entry
+// point returns OHP_E_NO_DEVICE / OHP_E_CUDA.
+#include "ohp_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace ohp {
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+
+__constant__ uint32_t c_ch_magic[33]; // ceil(2^32 / ch); [0],[1] = 0 (mono divides by one)
+
+__device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uint64_t chunk)
+{
+    if (threadIdx.x == 0) {
+        atomicOr(&p.status[0], bits);
+        atomicCAS(&p.status[1], 0u, (uint32_t)(chunk + 1 > 0xffffffffull ? 0xffffffffull : chunk + 1));
+    }
+}
+
+// Persistent CTAs: CTA b handles chunks b, b+grid, b+2*grid, ...  The ramp table is loaded to shared
+// memory once per CTA.  Every branch on descriptor fields is uniform across the CTA.
+__global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
+{
+    __shared__ __align__(16) uint8_t s_in[kSinBytes];
+    __shared__ __align__(16) uint8_t s_out[kSoutBytes];
+    __shared__ uint16_t s_table2[OHP_RAMP_TABLE_ENTRIES];
+    __shared__ RampConst s_rc;
+
+    for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) s_table2[i] = p.table2[i];
+
+    for (uint64_t c = blockIdx.x; c < p.n; c += gridDim.x) {
+        const uint4* dp = reinterpret_cast<const uint4*>(p.descs + c);
+        const uint4 d0 = __ldg(dp);
+        const uint4 d1 = __ldg(dp + 1);
+        const uint64_t src_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
+        const uint64_t dst_off = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+        const uint32_t bytes = d1.x;
+        const uint32_t ramp_start = d1.y & 0xffffu;
+        const uint32_t ramp_end = d1.y >> 16;
+        const uint32_t attenuation = d1.z & 0xffffu;
+        const uint32_t bit_depth = (d1.z >> 16) & 0xffu;
+        const uint32_t channels = d1.z >> 24;
+        const uint32_t flags = d1.w & 0xffu;
+        const uint32_t out_fmt = (d1.w >> 8) & 0xffu;
+
+        const bool silence = (flags & OHP_F_SILENCE) != 0;
+        const uint32_t B = bit_depth >> 3;
+        // the reference's ASSERTs, restated (a chunk that fails is skipped and reported)
+        bool ok = (bit_depth == 8 || bit_depth == 16 || bit_depth == 24 || bit_depth == 32)
+               && channels >= 1 && channels <= 32
+               && ramp_start <= OHP_RAMP_MAX && ramp_end <= OHP_RAMP_MAX
+               && (out_fmt == OHP_OUT_PACKED_BE || out_fmt == OHP_OUT_PACKED_LE);
+        if (ok) {
+            ok = (bytes % (B * channels)) == 0
+              && (silence || bytes <= kMaxChunk)
+              && (silence || attenuation == OHP_UNITY_ATTENUATION || bit_depth == 16)  // Msg.cpp:2741
+              && (out_fmt != OHP_OUT_PACKED_LE || (!silence && B <= 3));                // TestCodecInteractiveMain.cpp:546-567
+        }
+        if (!ok) {
+            report(p, kErrInvalidDesc, c);
+            continue;
+        }
+        if (dst_off > p.out_bytes || bytes > p.out_bytes - dst_off
+            || (!silence && (src_off > p.in_bytes || bytes > p.in_bytes - src_off))) {
+            report(p, kErrOutOfRange, c);
+            continue;
+        }
+        if (bytes == 0) continue; // MsgPlayable::Read only calls ReadBlock when iSize > 0 (Msg.cpp:2649)
+
+        uint8_t* dst = p.out + dst_off;
+        if (silence) {
+            write_silence(dst, bytes, channels, B);
+            continue;
+        }
+
+        ChunkCtx cx;
+        cx.bytes = bytes;
+        cx.channels = channels;
+        cx.ch_magic = c_ch_magic[channels];
+        cx.attenuation = attenuation;
+        cx.ramped = (flags & OHP_F_RAMP_ENABLED) != 0;
+        cx.in_le = (flags & OHP_F_IN_LITTLE_ENDIAN) != 0 && B > 1;
+        cx.out_le = (out_fmt == OHP_OUT_PACKED_LE) && B > 1;
+        cx.tag6 = (channels == 6);
+
+        const uint32_t head = stage_in(p.in, p.in_bytes, src_off, bytes, s_in);
+        if (cx.ramped && threadIdx.x == 0) s_rc = make_ramp_const(ramp_start, ramp_end, bytes / (B * channels));
+        __syncthreads();
+
+        const bool transform = cx.ramped || (cx.in_le != cx.out_le) || attenuation != OHP_UNITY_ATTENUATION;
+        if (transform) {
+            RampConst rc = s_rc; // broadcast read; meaningful only when ramped
+            switch (B) {
+            case 1: transform_chunk<1>(cx, rc, s_table2, s_in, head, s_out); break;
+            case 2: transform_chunk<2>(cx, rc, s_table2, s_in, head, s_out); break;
+            case 3: transform_chunk<3>(cx, rc, s_table2, s_in, head, s_out); break;
+            default: transform_chunk<4>(cx, rc, s_table2, s_in, head, s_out); break;
+            }
+            __syncthreads();
+            stage_out(s_out, 0, dst, bytes);
+        } else {
+            // verbatim pass-through (Msg.cpp:2782-2784)
+            stage_out(s_in, head, dst, bytes);
+        }
+        __syncthreads(); // the next chunk overwrites the staging buffers
+    }
+}
+
+// Per-stream checksum: sum_i (byte_i + 1) * (i + 1) mod 2^64 over [off[s], off[s+1]).  One CTA per stream.
+__global__ void __launch_bounds__(256) checksum_kernel(const uint8_t* __restrict__ out, const uint64_t* __restrict__ off,
+                                                       uint64_t n_streams, uint64_t* __restrict__ sums)
+{
+    __shared__ uint64_t s_part[8];
+    for (uint64_t s = blockIdx.x; s < n_streams; s += gridDim.x) {
+        const uint64_t lo = off[s], hi = off[s + 1];
+        const uint8_t* base = out + lo;
+        const uint64_t n = hi - lo;
+        uint64_t acc = 0;
+        // 16-byte aligned middle with 128-bit loads, ragged edges bytewise
+        const uint64_t lead0 = (16u - (reinterpret_cast<uint64_t>(base) & 15u)) & 15u;
+        const uint64_t lead = lead0 < n ? lead0 : n;
+        const uint64_t words = (n - lead) >> 4;
+        const uint64_t tail_at = lead + (words << 4);
+        if (threadIdx.x < lead) acc += ((uint64_t)base[threadIdx.x] + 1u) * (threadIdx.x + 1u);
+        if (threadIdx.x < n - tail_at) acc += ((uint64_t)base[tail_at + threadIdx.x] + 1u) * (tail_at + threadIdx.x + 1u);
+        const uint4* b4 = reinterpret_cast<const uint4*>(base + lead);
+        for (uint64_t w = threadIdx.x; w < words; w += blockDim.x) {
+            const uint4 v = b4[w];
+            const uint32_t t[4] = {v.x, v.y, v.z, v.w};
+            const uint64_t i0 = lead + (w << 4) + 1u; // 1-based index of the word's first byte
+            uint32_t sum = 0, wsum = 0;               // sum of (byte+1), sum of k*(byte+1) for k=0..15
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t b = ((t[k >> 2] >> (8 * (k & 3))) & 0xffu) + 1u;
+                sum += b;
+                wsum += b * (uint32_t)k;
+            }
+            acc += i0 * sum + wsum;
+        }
+        // block reduce
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t total = 0;
+            for (unsigned i = 0; i < (blockDim.x >> 5); i++) total += s_part[i];
+            sums[s] = total;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+
+static const uint16_t kRampTable[OHP_RAMP_TABLE_ENTRIES] = {
+#include "ramp_table.inc"
+};
+
+static thread_local std::string g_create_error;
+
+} // namespace ohp
+
+struct ohp_context
+{
+    int device = -1;
+    int sm_count = 0;
+    int ctas_per_sm = 0;
+    cudaStream_t stream = nullptr;     // compute
+    cudaStream_t copy_in = nullptr;    // H2D
+    cudaStream_t copy_out = nullptr;   // D2H
+    uint16_t* d_table2 = nullptr;
+    uint32_t* d_status = nullptr;
+    uint32_t* h_status = nullptr;      // pinned
+    // ohp_process_host staging (grown on demand)
+    uint8_t* d_in = nullptr;  uint64_t d_in_cap = 0;
+    uint8_t* d_out = nullptr; uint64_t d_out_cap = 0;
+    ohp_chunk_desc* d_descs = nullptr; uint64_t d_descs_cap = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timing = false;
+    bool timed = false;
+    uint64_t launches = 0;
+    std::vector<cudaEvent_t> slice_events; // ohp_process_host pipeline, reused across calls
+    std::string error;
+};
+
+namespace ohp {
+
+static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess)
+{
+    std::string msg = what;
+    if (e != cudaSuccess) {
+        msg += ": ";
+        msg += cudaGetErrorString(e);
+    }
+    if (ctx) ctx->error = msg; else g_create_error = msg;
+    return status;
+}
+
+#define OHP_CUDA(ctx, call)                                                     \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) return fail((ctx), OHP_E_CUDA, #call, e_);       \
+    } while (0)
+
+static int check_desc(const ohp_chunk_desc& d, uint64_t in_bytes, uint64_t out_bytes)
+{
+    const uint32_t bd = d.bit_depth;
+    if (!(bd == 8 || bd == 16 || bd == 24 || bd == 32)) return OHP_E_INVALID_DESC;
+    if (d.channels < 1 || d.channels > 32) return OHP_E_INVALID_DESC;
+    if (d.ramp_start > OHP_RAMP_MAX || d.ramp_end > OHP_RAMP_MAX) return OHP_E_INVALID_DESC;
+    if (!(d.out_fmt == OHP_OUT_PACKED_BE || d.out_fmt == OHP_OUT_PACKED_LE)) return OHP_E_INVALID_DESC;
+    const uint32_t B = bd / 8;
+    const bool silence = (d.flags & OHP_F_SILENCE) != 0;
+    if (d.bytes % (B * d.channels) != 0) return OHP_E_INVALID_DESC;
+    if (!silence && d.bytes > OHP_MAX_PCM_CHUNK_BYTES) return OHP_E_INVALID_DESC;
+    if (!silence && d.attenuation != OHP_UNITY_ATTENUATION && bd != 16) return OHP_E_INVALID_DESC;
+    if (d.out_fmt == OHP_OUT_PACKED_LE && (silence || B > 3)) return OHP_E_INVALID_DESC;
+    if (d.dst_off > out_bytes || d.bytes > out_bytes - d.dst_off) return OHP_E_OUT_OF_RANGE;
+    if (!silence && (d.src_off > in_bytes || d.bytes > in_bytes - d.src_off)) return OHP_E_OUT_OF_RANGE;
+    return OHP_OK;
+}
+
+static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, const uint8_t* d_in, uint64_t in_bytes,
+                  uint8_t* d_out, uint64_t out_bytes, cudaStream_t st)
+{
+    if (n == 0) return OHP_OK;
+    if ((reinterpret_cast<uint64_t>(d_in) & 15u) || (reinterpret_cast<uint64_t>(d_descs) & 15u)) {
+        return fail(ctx, OHP_E_INVALID_ARG, "input arena and descriptor array must be 16-byte aligned");
+    }
+    KernelParams p;
+    p.descs = d_descs;
+    p.n = n;
+    p.in = d_in;
+    p.in_bytes = in_bytes;
+    p.out = d_out;
+    p.out_bytes = out_bytes;
+    p.table2 = ctx->d_table2;
+    p.status = ctx->d_status;
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctx->ctas_per_sm;
+    if (grid > n) grid = n;
+    if (ctx->timing) OHP_CUDA(ctx, cudaEventRecord(ctx->ev_start, st));
+    ramp_convert_kernel<<<(unsigned)grid, kThreads, 0, st>>>(p);
+    OHP_CUDA(ctx, cudaGetLastError());
+    if (ctx->timing) {
+        OHP_CUDA(ctx, cudaEventRecord(ctx->ev_stop, st));
+        ctx->timed = true;
+    }
+    ctx->launches++;
+    return OHP_OK;
+}
+
+template <class T>
+static int grow(ohp_context* ctx, T*& ptr, uint64_t& cap, uint64_t need)
+{
+    if (need <= cap) return OHP_OK;
+    if (ptr) OHP_CUDA(ctx, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    const uint64_t want = need + need / 8 + 256;
+    OHP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ptr), want));
+    cap = want;
+    return OHP_OK;
+}
+
+static int read_status(ohp_context* ctx, cudaStream_t st)
+{
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t bits = ctx->h_status[0];
+    if (bits == 0) return OHP_OK;
+    const uint32_t first = ctx->h_status[1];
+    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, 2 * sizeof(uint32_t), st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    char buf[128];
+    std::snprintf(buf, sizeof buf, "device rejected chunk descriptor %u (%s)", first - 1,
+                  (bits & kErrInvalidDesc) ? "invalid" : "out of range");
+    return fail(ctx, (bits & kErrInvalidDesc) ? OHP_E_INVALID_DESC : OHP_E_OUT_OF_RANGE, buf);
+}
+
+} // namespace ohp
+
+using namespace ohp;
+
+extern "C" {
+
+uint32_t ohp_abi_version(void) { return OHP_ABI_VERSION; }
+
+int ohp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const uint16_t* ohp_ramp_table(void) { return kRampTable; }
+
+uint32_t ohp_median_multiplier(uint32_t ramp_start, uint32_t ramp_end, uint32_t direction, int enabled)
+{
+    if (!enabled) return 0x8000u;           // MsgAudio::MedianRampMultiplier, Msg.cpp:2065-2067
+    if (direction == 3u) return 0;          // EMute, Msg.cpp:2068-2070 / 912-913
+    uint32_t med;
+    if (direction == 1u) med = ramp_start + ((ramp_end - ramp_start) / 2);       // EUp,   Msg.cpp:906-908
+    else if (direction == 2u) med = ramp_start - ((ramp_start - ramp_end) / 2);  // EDown, Msg.cpp:909-911
+    else med = ramp_start;
+    const uint32_t idx = (OHP_RAMP_MAX - OHP_RAMP_MIN - med + (1u << 4)) >> 5;
+    return idx < OHP_RAMP_TABLE_ENTRIES ? kRampTable[idx] : 0u;
+}
+
+uint32_t ohp_chunk_out_bytes(const ohp_chunk_desc* d)
+{
+    if (!d) return 0;
+    const uint32_t B = d->bit_depth / 8u;
+    if (B == 0 || d->channels == 0) return 0;
+    const uint32_t frames = d->bytes / (B * d->channels);
+    switch (d->out_fmt) {
+    case OHP_OUT_PACKED_BE:
+    case OHP_OUT_PACKED_LE: return d->bytes;
+    case OHP_OUT_PLANAR32_BE: return frames * d->channels * 4u;
+    case OHP_OUT_FROM32_BE: return (d->bytes / 4u) * (d->aux / 8u);
+    case OHP_OUT_SONGCAST: return frames * (d->channels < 2 ? d->channels : 2u) * (B < 3 ? B : 3u);
+    default: return 0;
+    }
+}
+
+int ohp_validate(const ohp_chunk_desc* descs, size_t n, uint64_t in_bytes, uint64_t out_bytes, size_t* bad_index)
+{
+    if (!descs && n) return OHP_E_INVALID_ARG;
+    for (size_t i = 0; i < n; i++) {
+        const int rc = check_desc(descs[i], in_bytes, out_bytes);
+        if (rc != OHP_OK) {
+            if (bad_index) *bad_index = i;
+            return rc;
+        }
+    }
+    return OHP_OK;
+}
+
+int ohp_create(int device, ohp_context** out_ctx)
+{
+    if (!out_ctx) return OHP_E_INVALID_ARG;
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, OHP_E_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)", e);
+    }
+    if (device < 0 || device >= n) return fail(nullptr, OHP_E_INVALID_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, OHP_E_CUDA, "cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        return fail(nullptr, OHP_E_NO_DEVICE, "device is not an sm_100 (Blackwell B200) part; kernels are built for sm_100a only");
+    }
+    ohp_context* ctx = new (std::nothrow) ohp_context();
+    if (!ctx) return fail(nullptr, OHP_E_NO_MEMORY, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+#define OHP_CREATE(call)                                                          \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) {                                                  \
+            fail(nullptr, OHP_E_CUDA, #call, e_);                                 \
+            ohp_destroy(ctx);                                                     \
+            return OHP_E_CUDA;                                                    \
+        }                                                                         \
+    } while (0)
+    OHP_CREATE(cudaSetDevice(device));
+    OHP_CREATE(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    OHP_CREATE(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    OHP_CREATE(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    OHP_CREATE(cudaEventCreate(&ctx->ev_start));
+    OHP_CREATE(cudaEventCreate(&ctx->ev_stop));
+    OHP_CREATE(cudaMalloc(reinterpret_cast<void**>(&ctx->d_table2), sizeof(uint16_t) * OHP_RAMP_TABLE_ENTRIES));
+    OHP_CREATE(cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), 2 * sizeof(uint32_t)));
+    OHP_CREATE(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), 2 * sizeof(uint32_t)));
+    OHP_CREATE(cudaMemset(ctx->d_status, 0, 2 * sizeof(uint32_t)));
+    {
+        uint16_t t2[OHP_RAMP_TABLE_ENTRIES];
+        for (unsigned i = 0; i < OHP_RAMP_TABLE_ENTRIES; i++) t2[i] = (uint16_t)(2u * kRampTable[i]);
+        OHP_CREATE(cudaMemcpy(ctx->d_table2, t2, sizeof t2, cudaMemcpyHostToDevice));
+        uint32_t magic[33];
+        magic[0] = magic[1] = 0;
+        for (uint32_t ch = 2; ch <= 32; ch++) magic[ch] = (uint32_t)((((uint64_t)1 << 32) + ch - 1) / ch);
+        OHP_CREATE(cudaMemcpyToSymbol(c_ch_magic, magic, sizeof magic));
+    }
+    {
+        int per_sm = 0;
+        OHP_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ramp_convert_kernel, kThreads, 0));
+        ctx->ctas_per_sm = per_sm > 0 ? per_sm : 1;
+    }
+#undef OHP_CREATE
+    *out_ctx = ctx;
+    return OHP_OK;
+}
+
+int ohp_destroy(ohp_context* ctx)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (ctx->device >= 0) (void)cudaSetDevice(ctx->device);
+    if (ctx->stream) { (void)cudaStreamSynchronize(ctx->stream); }
+    if (ctx->d_in) (void)cudaFree(ctx->d_in);
+    if (ctx->d_out) (void)cudaFree(ctx->d_out);
+    if (ctx->d_descs) (void)cudaFree(ctx->d_descs);
+    if (ctx->d_table2) (void)cudaFree(ctx->d_table2);
+    if (ctx->d_status) (void)cudaFree(ctx->d_status);
+    if (ctx->h_status) (void)cudaFreeHost(ctx->h_status);
+    if (ctx->ev_start) (void)cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) (void)cudaEventDestroy(ctx->ev_stop);
+    for (cudaEvent_t e : ctx->slice_events) (void)cudaEventDestroy(e);
+    if (ctx->stream) (void)cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_in) (void)cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) (void)cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+    return OHP_OK;
+}
+
+const char* ohp_last_error(const ohp_context* ctx)
+{
+    return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+int ohp_process_device(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, const uint8_t* d_in, uint64_t in_bytes,
+                       uint8_t* d_out, uint64_t out_bytes, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (n && (!d_descs || !d_out || (!d_in && in_bytes))) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch(ctx, d_descs, n, d_in, in_bytes, d_out, out_bytes, st);
+}
+
+int ohp_sync(ohp_context* ctx, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    return read_status(ctx, st);
+}
+
+int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, const uint8_t* h_in, uint64_t in_bytes,
+                     uint8_t* h_out, uint64_t out_bytes)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (n == 0) return OHP_OK;
+    if (!h_descs || !h_out || (!h_in && in_bytes)) return fail(ctx, OHP_E_INVALID_ARG, "null host pointer");
+    size_t bad = 0;
+    const int vrc = ohp_validate(h_descs, n, in_bytes, out_bytes, &bad);
+    if (vrc != OHP_OK) {
+        char buf[96];
+        std::snprintf(buf, sizeof buf, "chunk descriptor %zu rejected (%s)", bad,
+                      vrc == OHP_E_INVALID_DESC ? "invalid" : "out of range");
+        return fail(ctx, vrc, buf);
+    }
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = grow(ctx, ctx->d_in, ctx->d_in_cap, in_bytes + 16)) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_out, ctx->d_out_cap, out_bytes + 16)) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, (uint64_t)n * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+
+    // Slices of consecutive descriptors, each moving about kSliceBytes over PCIe, pipelined over three streams:
+    //   copy_in: H2D of the slice's descriptors and of the input span its chunks read
+    //   stream : kernel over the slice
+    //   copy_out: D2H of the output span its chunks write
+    // The device arenas are full size, so slices never alias; spans are [min offset, max end) over the slice.
+    // Bytes of h_out inside a slice's span that no chunk covers receive unspecified values.
+    const uint64_t kSliceBytes = 48ull << 20;
+    std::vector<cudaEvent_t>& evs = ctx->slice_events;
+    size_t ev_used = 0;
+    auto next_event = [&](cudaEvent_t* out_ev) -> cudaError_t {
+        if (ev_used == evs.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (err != cudaSuccess) return err;
+            evs.push_back(e);
+        }
+        *out_ev = evs[ev_used++];
+        return cudaSuccess;
+    };
+    const bool timing = ctx->timing;
+    ctx->timing = false; // per-kernel events are only meaningful for a single launch
+    size_t lo = 0;
+    while (lo < n) {
+        uint64_t in_lo = UINT64_MAX, in_hi = 0, out_lo = UINT64_MAX, out_hi = 0, moved = 0;
+        size_t hi = lo;
+        while (hi < n && (moved < kSliceBytes || hi == lo)) {
+            const ohp_chunk_desc& d = h_descs[hi];
+            if (d.bytes) {
+                if (!(d.flags & OHP_F_SILENCE)) {
+                    in_lo = d.src_off < in_lo ? d.src_off : in_lo;
+                    in_hi = d.src_off + d.bytes > in_hi ? d.src_off + d.bytes : in_hi;
+                }
+                out_lo = d.dst_off < out_lo ? d.dst_off : out_lo;
+                out_hi = d.dst_off + d.bytes > out_hi ? d.dst_off + d.bytes : out_hi;
+                moved += 2ull * d.bytes;
+            }
+            hi++;
+        }
+        cudaEvent_t ev_in, ev_k;
+        OHP_CUDA(ctx, next_event(&ev_in));
+        OHP_CUDA(ctx, next_event(&ev_k));
+        OHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_descs + lo, h_descs + lo, (hi - lo) * sizeof(ohp_chunk_desc),
+                                      cudaMemcpyHostToDevice, ctx->copy_in));
+        if (in_hi > in_lo) {
+            OHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in + in_lo, h_in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
+        OHP_CUDA(ctx, cudaEventRecord(ev_in, ctx->copy_in));
+        OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+        if ((rc = launch(ctx, ctx->d_descs + lo, hi - lo, ctx->d_in, in_bytes, ctx->d_out, out_bytes, ctx->stream)) != OHP_OK) {
+            ctx->timing = timing;
+            return rc;
+        }
+        OHP_CUDA(ctx, cudaEventRecord(ev_k, ctx->stream));
+        OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k, 0));
+        if (out_hi > out_lo) {
+            OHP_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+        lo = hi;
+    }
+    ctx->timing = timing;
+    OHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    OHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return read_status(ctx, ctx->stream);
+}
+
+int ohp_checksums_device(ohp_context* ctx, const uint8_t* d_out, const uint64_t* d_stream_off, size_t n_streams,
+                         uint64_t* d_sums, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (n_streams == 0) return OHP_OK;
+    if (!d_out || !d_stream_off || !d_sums) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    uint64_t grid = (uint64_t)ctx->sm_count * 8u;
+    if (grid > n_streams) grid = n_streams;
+    checksum_kernel<<<(unsigned)grid, 256, 0, st>>>(d_out, d_stream_off, n_streams, d_sums);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return OHP_OK;
+}
+
+int ohp_device_alloc(ohp_context* ctx, uint64_t bytes, void** out_dptr)
+{
+    if (!ctx || !out_dptr) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    OHP_CUDA(ctx, cudaMalloc(out_dptr, bytes ? bytes : 1));
+    return OHP_OK;
+}
+
+int ohp_device_free(ohp_context* ctx, void* dptr)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    OHP_CUDA(ctx, cudaFree(dptr));
+    return OHP_OK;
+}
+
+int ohp_host_alloc(ohp_context* ctx, uint64_t bytes, void** out_hptr)
+{
+    if (!ctx || !out_hptr) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    OHP_CUDA(ctx, cudaMallocHost(out_hptr, bytes ? bytes : 1));
+    return OHP_OK;
+}
+
+int ohp_host_free(ohp_context* ctx, void* hptr)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaFreeHost(hptr));
+    return OHP_OK;
+}
+
+int ohp_memcpy_h2d(ohp_context* ctx, void* dptr, const void* hptr, uint64_t bytes, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    OHP_CUDA(ctx, cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, st));
+    return OHP_OK;
+}
+
+int ohp_memcpy_d2h(ohp_context* ctx, void* hptr, const void* dptr, uint64_t bytes, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    OHP_CUDA(ctx, cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, st));
+    return OHP_OK;
+}
+
+uint64_t ohp_launch_count(const ohp_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int ohp_set_timing(ohp_context* ctx, int enabled)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    ctx->timing = enabled != 0;
+    ctx->timed = false;
+    return OHP_OK;
+}
+
+double ohp_last_kernel_ms(ohp_context* ctx)
+{
+    if (!ctx || !ctx->timing || !ctx->timed) return -1.0;
+    if (cudaEventSynchronize(ctx->ev_stop) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+} // extern "C"

@@ -1,0 +1,205 @@
+// schedule.cpp -- the C ABI of include/ohp_schedule.h on top of the host message model.
+//
+// Runs every stream's ramp events through the stage chain (stage_chain.h) on the mirror classes
+// (msg_model.h) and records one ohp_chunk_desc per MsgPlayable.  Threaded over streams; streams are
+// independent, so no synchronisation beyond the final gather.
+#include "msg_model.h"
+#include "stage_chain.h"
+
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace ohp;
+using namespace ohp::media;
+
+namespace {
+
+struct MirrorApi
+{
+    using MsgAudio = media::MsgAudio;
+    using MsgAudioPcm = media::MsgAudioPcm;
+    using MsgSilence = media::MsgSilence;
+    using MsgPlayable = media::MsgPlayable;
+    using Factory = media::MsgFactory;
+    static const uint32_t kRampMax = Ramp::kMax;
+    static const uint32_t kRampMin = Ramp::kMin;
+    static const Ramp::EDirection kDirUp = Ramp::EUp;
+    static const Ramp::EDirection kDirDown = Ramp::EDown;
+    static MsgAudioPcm* CreatePcm(Factory& f, const ohp_stream_spec& sp, uint64_t firstFrame, uint32_t frames)
+    {
+        const uint32_t frameBytes = sp.channels * (sp.bit_depth / 8u);
+        return f.CreateMsgAudioPcm(sp.src_base + firstFrame * frameBytes, frames * frameBytes, sp.channels, sp.sample_rate,
+                                   sp.bit_depth, sp.in_little_endian ? AudioDataEndian::Little : AudioDataEndian::Big,
+                                   firstFrame * (uint64_t)Jiffies::PerSampleOrZero(sp.sample_rate));
+    }
+    static MsgSilence* CreateSilence(Factory& f, const ohp_stream_spec& sp, uint32_t& jiffies)
+    {
+        return f.CreateMsgSilence(jiffies, sp.sample_rate, sp.bit_depth, sp.channels);
+    }
+    static uint32_t JiffiesPerSample(uint32_t rate) { return Jiffies::PerSampleOrZero(rate); }
+    static void Assert(bool ok) { OHP_ASSERT(ok); }
+};
+
+struct StreamRecord
+{
+    std::vector<ohp_chunk_desc> chunks;
+    std::vector<ohp_chunk_info> info;
+    uint64_t outBytes = 0;
+};
+
+class DescSink
+{
+public:
+    DescSink(const ohp_stream_spec& sp, StreamRecord& rec) : iSpec(sp), iRec(rec) {}
+    void OnPlayable(MsgPlayable* p)
+    {
+        iRec.chunks.push_back(p->Descriptor(iSpec.dst_base + iRec.outBytes, iSpec.out_fmt));
+        iRec.info.push_back(ohp_chunk_info{(uint32_t)p->Ramp().Direction(), p->Jiffies()});
+        iRec.outBytes += p->Bytes();
+        p->RemoveRef();
+    }
+private:
+    const ohp_stream_spec& iSpec;
+    StreamRecord& iRec;
+};
+
+thread_local std::string g_error;
+
+} // namespace
+
+struct ohp_schedule
+{
+    std::vector<ohp_chunk_desc> chunks;
+    std::vector<ohp_chunk_info> info;
+    std::vector<uint64_t> chunkBegin;
+    std::vector<uint64_t> outBytes;
+};
+
+extern "C" {
+
+int ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams, const ohp_ramp_event* events, size_t n_events,
+                       int threads, ohp_schedule** out)
+{
+    if (!out || (!streams && n_streams) || (!events && n_events)) {
+        g_error = "null argument";
+        return OHP_E_INVALID_ARG;
+    }
+    *out = nullptr;
+    for (size_t s = 0; s < n_streams; s++) {
+        if ((uint64_t)streams[s].first_event + streams[s].num_events > n_events) {
+            g_error = "stream " + std::to_string(s) + ": event slice out of range";
+            return OHP_E_INVALID_ARG;
+        }
+        if (!(streams[s].out_fmt == OHP_OUT_PACKED_BE || streams[s].out_fmt == OHP_OUT_PACKED_LE)) {
+            g_error = "stream " + std::to_string(s) + ": schedule runs produce packed BE or LE output";
+            return OHP_E_INVALID_ARG;
+        }
+    }
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if ((size_t)threads > n_streams) threads = (int)(n_streams ? n_streams : 1);
+
+    std::vector<StreamRecord> recs(n_streams);
+    std::vector<int> rcs((size_t)threads, 0);
+    std::vector<std::string> errs((size_t)threads);
+    auto worker = [&](int t) {
+        MsgFactory factory;
+        const size_t lo = n_streams * (size_t)t / (size_t)threads;
+        const size_t hi = n_streams * (size_t)(t + 1) / (size_t)threads;
+        for (size_t s = lo; s < hi; s++) {
+            DescSink sink(streams[s], recs[s]);
+            try {
+                StageChain<MirrorApi, DescSink> chain(factory, streams[s], events + streams[s].first_event, sink);
+                const int rc = chain.Run();
+                if (rc != 0) {
+                    rcs[(size_t)t] = OHP_E_INVALID_ARG;
+                    errs[(size_t)t] = "stream " + std::to_string(s) + ": spec not representable";
+                    return;
+                }
+            }
+            catch (const std::exception& e) {
+                // the reference would ASSERT here
+                rcs[(size_t)t] = OHP_E_INVALID_DESC;
+                errs[(size_t)t] = "stream " + std::to_string(s) + ": " + e.what();
+                return;
+            }
+        }
+    };
+    if (threads == 1) {
+        worker(0);
+    }
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+        for (auto& th : pool) th.join();
+    }
+    for (size_t t = 0; t < (size_t)threads; t++) {
+        if (rcs[t] != 0) {
+            g_error = errs[t];
+            return rcs[t];
+        }
+    }
+    ohp_schedule* sch = new ohp_schedule();
+    size_t total = 0;
+    for (auto& r : recs) total += r.chunks.size();
+    sch->chunks.reserve(total);
+    sch->info.reserve(total);
+    sch->chunkBegin.resize(n_streams + 1);
+    sch->outBytes.resize(n_streams);
+    for (size_t s = 0; s < n_streams; s++) {
+        sch->chunkBegin[s] = sch->chunks.size();
+        sch->outBytes[s] = recs[s].outBytes;
+        sch->chunks.insert(sch->chunks.end(), recs[s].chunks.begin(), recs[s].chunks.end());
+        sch->info.insert(sch->info.end(), recs[s].info.begin(), recs[s].info.end());
+        std::vector<ohp_chunk_desc>().swap(recs[s].chunks);
+        std::vector<ohp_chunk_info>().swap(recs[s].info);
+    }
+    sch->chunkBegin[n_streams] = sch->chunks.size();
+    *out = sch;
+    return OHP_OK;
+}
+
+size_t ohp_schedule_num_chunks(const ohp_schedule* s) { return s ? s->chunks.size() : 0; }
+const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s) { return s ? s->chunks.data() : nullptr; }
+const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s) { return s ? s->info.data() : nullptr; }
+const uint64_t* ohp_schedule_stream_chunk_begin(const ohp_schedule* s) { return s ? s->chunkBegin.data() : nullptr; }
+const uint64_t* ohp_schedule_stream_out_bytes(const ohp_schedule* s) { return s ? s->outBytes.data() : nullptr; }
+const char* ohp_schedule_last_error(void) { return g_error.c_str(); }
+void ohp_schedule_free(ohp_schedule* s) { delete s; }
+
+uint32_t ohp_jiffies_per_sample(uint32_t sample_rate) { return Jiffies::PerSampleOrZero(sample_rate); }
+
+int ohp_ramp_set(ohp_ramp* ramp, uint32_t start, uint32_t fragment_size, uint32_t remaining_duration, uint32_t direction,
+                 ohp_ramp* split, uint32_t* split_pos)
+{
+    if (!ramp || !split || !split_pos) return -2;
+    Ramp r = Ramp::FromAbi(*ramp);
+    Ramp s;
+    try {
+        const bool ret = r.Set(start, fragment_size, remaining_duration, (Ramp::EDirection)direction, s, *split_pos);
+        *ramp = r.ToAbi();
+        *split = s.ToAbi();
+        return ret ? 1 : 0;
+    }
+    catch (const AssertionFailed&) {
+        return -1;
+    }
+}
+
+int ohp_ramp_split(ohp_ramp* ramp, uint32_t new_size, uint32_t current_size, ohp_ramp* remaining)
+{
+    if (!ramp || !remaining) return -2;
+    Ramp r = Ramp::FromAbi(*ramp);
+    try {
+        const Ramp rest = r.Split(new_size, current_size);
+        *ramp = r.ToAbi();
+        *remaining = rest.ToAbi();
+        return 0;
+    }
+    catch (const AssertionFailed&) {
+        return -1;
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,113 @@
+"""The C-ABI libraries load without a GPU and export every symbol include/*.h declares; struct layouts match."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ohpipeline_b200 import abi, capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ohp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    lib = capi.cuda_lib()
+    names = declared_functions("ohp_b200.h")
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = capi.host_lib()
+    names = declared_functions("ohp_schedule.h")
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_abi_version_and_constants():
+    assert capi.cuda_lib().ohp_abi_version() == abi.ABI_VERSION
+    hdr = open(os.path.join(ROOT, "include", "ohp_b200.h")).read()
+    assert "#define OHP_RAMP_MAX 16384u" in hdr
+    assert "#define OHP_MAX_PCM_CHUNK_BYTES 9216u" in hdr
+
+
+def test_struct_layout_matches_header():
+    # compile a tiny C program that prints sizeof/offsetof and compare with the numpy dtypes
+    import subprocess
+    import tempfile
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "ohp_schedule.h"
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("ohp_chunk_desc %zu\n", sizeof(ohp_chunk_desc));
+  P(ohp_chunk_desc, src_off); P(ohp_chunk_desc, dst_off); P(ohp_chunk_desc, bytes); P(ohp_chunk_desc, ramp_start);
+  P(ohp_chunk_desc, ramp_end); P(ohp_chunk_desc, attenuation); P(ohp_chunk_desc, bit_depth); P(ohp_chunk_desc, channels);
+  P(ohp_chunk_desc, flags); P(ohp_chunk_desc, out_fmt); P(ohp_chunk_desc, aux);
+  printf("ohp_ramp_event %zu\n", sizeof(ohp_ramp_event));
+  P(ohp_ramp_event, at_jiffies); P(ohp_ramp_event, stage); P(ohp_ramp_event, op); P(ohp_ramp_event, arg);
+  printf("ohp_stream_spec %zu\n", sizeof(ohp_stream_spec));
+  P(ohp_stream_spec, sample_rate); P(ohp_stream_spec, chunk_frames); P(ohp_stream_spec, out_fmt); P(ohp_stream_spec, total_frames);
+  P(ohp_stream_spec, src_base); P(ohp_stream_spec, dst_base); P(ohp_stream_spec, first_event); P(ohp_stream_spec, driver_block_frames);
+  printf("ohp_chunk_info %zu\n", sizeof(ohp_chunk_info));
+  printf("ohp_ramp %zu\n", sizeof(ohp_ramp));
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "l.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "l")
+        subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, stdout=subprocess.PIPE, text=True).stdout
+    got = dict(line.rsplit(" ", 1) for line in out.strip().splitlines())
+    dts = {"ohp_chunk_desc": abi.CHUNK_DESC, "ohp_ramp_event": abi.RAMP_EVENT, "ohp_stream_spec": abi.STREAM_SPEC,
+           "ohp_chunk_info": abi.CHUNK_INFO, "ohp_ramp": abi.RAMP}
+    for name, dt in dts.items():
+        assert int(got[name]) == dt.itemsize, name
+    for key, val in got.items():
+        if "." in key:
+            t, f = key.split(".")
+            assert dts[t].fields[f][1] == int(val), key
+
+
+def test_ramp_table_matches_oracle(port):
+    assert np.array_equal(capi.ramp_table().astype(np.uint32), port.ramp_array)
+
+
+def test_no_device_is_reported_not_hidden():
+    """Without a GPU the library must say so (no CPU fallback)."""
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.OhpError) as e:
+        capi.Context(0)
+    assert e.value.status == abi.E_NO_DEVICE
+
+
+def test_validate_rejects_what_the_reference_asserts_on():
+    from util import make_desc
+    ok = make_desc(bytes=24, bit_depth=24, channels=2)
+    assert capi.validate(ok, 64, 64) == (abi.OK, 0)
+    cases = [
+        make_desc(bytes=25, bit_depth=24, channels=2),                      # not a whole frame (ProcessorAudioUtils.cpp:45)
+        make_desc(bytes=24, bit_depth=20, channels=2),                      # ConstructPcm ASSERT (Msg.cpp:349)
+        make_desc(bytes=24, bit_depth=24, channels=0),
+        make_desc(bytes=24, bit_depth=24, channels=2, attenuation=128),     # ApplyAttenuation ASSERT(iBitDepth == 16) (Msg.cpp:2741)
+        make_desc(bytes=24, bit_depth=24, channels=2, ramp_start=16385),    # Ramp::DoValidate (Msg.cpp:747)
+        make_desc(bytes=32, bit_depth=32, channels=2, out_fmt=abi.OUT_PACKED_LE),  # ProcessorPcmSwpEndianPacked 32-bit ASSERTS
+        make_desc(bytes=24, bit_depth=24, channels=2, out_fmt=abi.OUT_PACKED_LE, flags=abi.F_SILENCE),  # ProcessSilence ASSERTS
+        make_desc(bytes=9216 + 6, bit_depth=24, channels=2),                # larger than a DecodedAudio cell
+    ]
+    for d in cases:
+        assert capi.validate(d, 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC, d
+    assert capi.validate(make_desc(bytes=24, bit_depth=24, channels=2, src_off=60), 64, 64)[0] == abi.E_OUT_OF_RANGE
+    assert capi.validate(make_desc(bytes=24, bit_depth=24, channels=2, dst_off=60), 64, 64)[0] == abi.E_OUT_OF_RANGE
