@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self.power = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self._active = threading.Event()
         self.ok = False
         try:
@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
         if not self.ok:
             return
         nv = self.nv
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             if self._active.is_set():
                 try:
                     self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
@@ -115,7 +115,7 @@ class ClockSampler(threading.Thread):
         (self._active.set if on else self._active.clear)()
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         if self.ok:
             self.join(timeout=2)
         s = sorted(self.samples)
@@ -260,8 +260,13 @@ def main():
     d_in = torch.randint(0, 256, (w.in_bytes,), dtype=torch.uint8, device="cuda", generator=g)
     d_out = torch.zeros(w.out_bytes, dtype=torch.uint8, device="cuda")
     d_desc = torch.from_numpy(chunks.view(np.uint8).copy()).cuda()
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: a NULL stream argument would select the context's own stream, and the
+    # CUDA events below must sit on the stream the kernels are launched on
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     st = stream.cuda_stream
+    assert st != 0
 
     def step():
         ctx.process_device(d_desc.data_ptr(), n_chunks, d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes, st)

@@ -23,7 +23,9 @@ def run_device(ctx, chunks, inp, out_bytes, fill=0xA5):
     d_desc = torch.from_numpy(chunks.view(np.uint8).copy()).cuda()
     d_in = torch.from_numpy(np.ascontiguousarray(inp)).cuda() if inp.size else torch.zeros(16, dtype=torch.uint8, device="cuda")
     d_out = torch.full((max(out_bytes, 1),), fill, dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream()  # the caller's stream (NULL would mean the context's own)
+    st = stream.cuda_stream
     ctx.process_device(d_desc.data_ptr(), len(chunks), d_in.data_ptr(), int(inp.size), d_out.data_ptr(), out_bytes, st)
     ctx.sync(st)
     return d_out.cpu().numpy()[:out_bytes]
