@@ -20,100 +20,223 @@ namespace ohp {
 
 __constant__ uint32_t c_ch_magic[33]; // ceil(2^32 / ch); [0],[1] = 0 (mono divides by one)
 
-__device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uint64_t chunk)
+// Decode and check one descriptor (the reference's ASSERTs, restated); fill the consumer record.
+// Returns 0, or the error bits to report (the chunk is then skipped).
+__device__ __forceinline__ uint32_t decode_chunk(const KernelParams& p, const uint4& d0, const uint4& d1, ChunkRec& r,
+                                                 uint64_t& src_off)
 {
-    if (threadIdx.x == 0) {
-        atomicOr(&p.status[0], bits);
-        atomicCAS(&p.status[1], 0u, (uint32_t)(chunk + 1 > 0xffffffffull ? 0xffffffffull : chunk + 1));
+    src_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
+    const uint64_t dst_off = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+    const uint32_t bytes = d1.x;
+    const uint32_t ramp_start = d1.y & 0xffffu;
+    const uint32_t ramp_end = d1.y >> 16;
+    const uint32_t attenuation = d1.z & 0xffffu;
+    const uint32_t bit_depth = (d1.z >> 16) & 0xffu;
+    const uint32_t channels = d1.z >> 24;
+    const uint32_t flags = d1.w & 0xffu;
+    const uint32_t out_fmt = (d1.w >> 8) & 0xffu;
+    const bool silence = (flags & OHP_F_SILENCE) != 0;
+    const uint32_t B = bit_depth >> 3;
+
+    r.kind = kSkip;
+    bool ok = (bit_depth == 8 || bit_depth == 16 || bit_depth == 24 || bit_depth == 32)
+           && channels >= 1 && channels <= 32
+           && ramp_start <= OHP_RAMP_MAX && ramp_end <= OHP_RAMP_MAX
+           && (out_fmt == OHP_OUT_PACKED_BE || out_fmt == OHP_OUT_PACKED_LE);
+    uint32_t frames = 0;
+    if (ok) {
+        frames = bytes / (B * channels);
+        ok = frames * (B * channels) == bytes
+          && (silence || bytes <= kMaxChunk)
+          && (silence || attenuation == OHP_UNITY_ATTENUATION || bit_depth == 16)  // Msg.cpp:2741
+          && (out_fmt != OHP_OUT_PACKED_LE || (!silence && B <= 3));                // TestCodecInteractiveMain.cpp:546-567
     }
+    if (!ok) return kErrInvalidDesc;
+    if (dst_off > p.out_bytes || bytes > p.out_bytes - dst_off
+        || (!silence && (src_off > p.in_bytes || bytes > p.in_bytes - src_off))) {
+        return kErrOutOfRange;
+    }
+    if (bytes == 0) return 0; // MsgPlayable::Read only calls ReadBlock when iSize > 0 (Msg.cpp:2649)
+
+    const uint64_t dst = reinterpret_cast<uint64_t>(p.out) + dst_off;
+    r.kind = silence ? kSilence : kPcm;
+    r.bytes = bytes;
+    r.head = (uint32_t)((reinterpret_cast<uint64_t>(p.in) + src_off) & 15u);
+    r.channels = channels;
+    r.ch_magic = c_ch_magic[channels];
+    r.attenuation = attenuation;
+    r.bytes_per_subsample = B;
+    r.dst_lo = (uint32_t)dst;
+    r.dst_hi = (uint32_t)(dst >> 32);
+    const bool ramped = (flags & OHP_F_RAMP_ENABLED) != 0;
+    const bool in_le = (flags & OHP_F_IN_LITTLE_ENDIAN) != 0 && B > 1;
+    const bool out_le = (out_fmt == OHP_OUT_PACKED_LE) && B > 1;
+    const bool transform = ramped || (in_le != out_le) || attenuation != OHP_UNITY_ATTENUATION;
+    r.mode = (ramped ? kModeRamped : 0u) | (in_le ? kModeInLe : 0u) | (out_le ? kModeOutLe : 0u)
+           | ((channels == 6) ? kModeTag6 : 0u) | (transform ? kModeTransform : 0u);
+    make_ramp_const(r, ramp_start, ramp_end, frames);
+    return 0;
 }
 
-// Persistent CTAs: CTA b handles chunks b, b+grid, b+2*grid, ...  The ramp table is loaded to shared
-// memory once per CTA.  Every branch on descriptor fields is uniform across the CTA.
+__device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uint64_t chunk)
+{
+    atomicOr(&p.status[0], bits);
+    atomicCAS(&p.status[1], 0u, (uint32_t)(chunk + 1 > 0xffffffffull ? 0xffffffffull : chunk + 1));
+}
+
+// Persistent, warp-specialised CTAs (see ohp_kernels.cuh): CTA b handles chunks b, b+grid, b+2*grid, ...
 __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
 {
-    __shared__ __align__(16) uint8_t s_in[kSinBytes];
-    __shared__ __align__(16) uint8_t s_out[kSoutBytes];
-    __shared__ uint16_t s_table2[OHP_RAMP_TABLE_ENTRIES];
-    __shared__ RampConst s_rc;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SharedStorage& sm = *reinterpret_cast<SharedStorage*>(smem_raw);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
 
-    for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) s_table2[i] = p.table2[i];
-
-    for (uint64_t c = blockIdx.x; c < p.n; c += gridDim.x) {
-        const uint4* dp = reinterpret_cast<const uint4*>(p.descs + c);
-        const uint4 d0 = __ldg(dp);
-        const uint4 d1 = __ldg(dp + 1);
-        const uint64_t src_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
-        const uint64_t dst_off = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
-        const uint32_t bytes = d1.x;
-        const uint32_t ramp_start = d1.y & 0xffffu;
-        const uint32_t ramp_end = d1.y >> 16;
-        const uint32_t attenuation = d1.z & 0xffffu;
-        const uint32_t bit_depth = (d1.z >> 16) & 0xffu;
-        const uint32_t channels = d1.z >> 24;
-        const uint32_t flags = d1.w & 0xffu;
-        const uint32_t out_fmt = (d1.w >> 8) & 0xffu;
-
-        const bool silence = (flags & OHP_F_SILENCE) != 0;
-        const uint32_t B = bit_depth >> 3;
-        // the reference's ASSERTs, restated (a chunk that fails is skipped and reported)
-        bool ok = (bit_depth == 8 || bit_depth == 16 || bit_depth == 24 || bit_depth == 32)
-               && channels >= 1 && channels <= 32
-               && ramp_start <= OHP_RAMP_MAX && ramp_end <= OHP_RAMP_MAX
-               && (out_fmt == OHP_OUT_PACKED_BE || out_fmt == OHP_OUT_PACKED_LE);
-        if (ok) {
-            ok = (bytes % (B * channels)) == 0
-              && (silence || bytes <= kMaxChunk)
-              && (silence || attenuation == OHP_UNITY_ATTENUATION || bit_depth == 16)  // Msg.cpp:2741
-              && (out_fmt != OHP_OUT_PACKED_LE || (!silence && B <= 3));                // TestCodecInteractiveMain.cpp:546-567
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kInStages; s++) {
+            mbar_init(smem_u32(&sm.full_in[s]), 1);
+            mbar_init(smem_u32(&sm.empty_in[s]), kConsumerWarps);
         }
-        if (!ok) {
-            report(p, kErrInvalidDesc, c);
-            continue;
+        for (int s = 0; s < kOutStages; s++) {
+            mbar_init(smem_u32(&sm.full_out[s]), kConsumerWarps);
+            mbar_init(smem_u32(&sm.empty_out[s]), 1);
         }
-        if (dst_off > p.out_bytes || bytes > p.out_bytes - dst_off
-            || (!silence && (src_off > p.in_bytes || bytes > p.in_bytes - src_off))) {
-            report(p, kErrOutOfRange, c);
-            continue;
-        }
-        if (bytes == 0) continue; // MsgPlayable::Read only calls ReadBlock when iSize > 0 (Msg.cpp:2649)
+        fence_mbar_init();
+    }
+    for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) sm.table2[i] = p.table2[i];
+    __syncthreads();
 
-        uint8_t* dst = p.out + dst_off;
-        if (silence) {
-            write_silence(dst, bytes, channels, B);
-            continue;
-        }
-
-        ChunkCtx cx;
-        cx.bytes = bytes;
-        cx.channels = channels;
-        cx.ch_magic = c_ch_magic[channels];
-        cx.attenuation = attenuation;
-        cx.ramped = (flags & OHP_F_RAMP_ENABLED) != 0;
-        cx.in_le = (flags & OHP_F_IN_LITTLE_ENDIAN) != 0 && B > 1;
-        cx.out_le = (out_fmt == OHP_OUT_PACKED_LE) && B > 1;
-        cx.tag6 = (channels == 6);
-
-        const uint32_t head = stage_in(p.in, p.in_bytes, src_off, bytes, s_in);
-        if (cx.ramped && threadIdx.x == 0) s_rc = make_ramp_const(ramp_start, ramp_end, bytes / (B * channels));
-        __syncthreads();
-
-        const bool transform = cx.ramped || (cx.in_le != cx.out_le) || attenuation != OHP_UNITY_ATTENUATION;
-        if (transform) {
-            RampConst rc = s_rc; // broadcast read; meaningful only when ramped
-            switch (B) {
-            case 1: transform_chunk<1>(cx, rc, s_table2, s_in, head, s_out); break;
-            case 2: transform_chunk<2>(cx, rc, s_table2, s_in, head, s_out); break;
-            case 3: transform_chunk<3>(cx, rc, s_table2, s_in, head, s_out); break;
-            default: transform_chunk<4>(cx, rc, s_table2, s_in, head, s_out); break;
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader
+        if (lane == 0) {
+            const uint4* dp = reinterpret_cast<const uint4*>(p.descs);
+            uint64_t c = blockIdx.x;
+            uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+            if (c < p.n) { n0 = __ldg(dp + 2 * c); n1 = __ldg(dp + 2 * c + 1); }
+            for (uint32_t it = 0; c < p.n; c += gridDim.x, it++) {
+                const uint4 d0 = n0, d1 = n1;
+                const uint64_t cn = c + gridDim.x;
+                if (cn < p.n) { n0 = __ldg(dp + 2 * cn); n1 = __ldg(dp + 2 * cn + 1); } // next descriptor, a step ahead
+                ChunkRec r;
+                uint64_t src_off;
+                const uint32_t err = decode_chunk(p, d0, d1, r, src_off);
+                if (err) report(p, err, c);
+                const uint32_t s = it % kInStages;
+                const uint32_t ph = (it / kInStages) & 1u;
+                mbar_wait(smem_u32(&sm.empty_in[s]), ph ^ 1u, p.status);
+                sm.rec[s] = r;
+                const uint32_t full = smem_u32(&sm.full_in[s]);
+                if (r.kind == kPcm) {
+                    const uint8_t* al = p.in + src_off - r.head;
+                    uint32_t span = (r.head + r.bytes + 15u) & ~15u;
+                    const uint64_t room = (uint64_t)(p.in + p.in_bytes - al);
+                    const uint32_t stage = smem_u32(&sm.in_stage[s][0]);
+                    if (span > room) {
+                        // last 16-byte word of the arena is partial: fetch its bytes one by one
+                        const uint32_t whole = (uint32_t)(room & ~15ull);
+                        for (uint32_t i = whole; i < (uint32_t)room; i++) sm.in_stage[s][i] = al[i];
+                        span = whole;
+                    }
+                    if (span != 0) {
+                        mbar_arrive_expect_tx(full, span);
+                        tma_load(stage, al, span, full);
+                    } else {
+                        mbar_arrive(full);
+                    }
+                } else {
+                    mbar_arrive(full);
+                }
             }
-            __syncthreads();
-            stage_out(s_out, 0, dst, bytes);
-        } else {
-            // verbatim pass-through (Msg.cpp:2782-2784)
-            stage_out(s_in, head, dst, bytes);
         }
-        __syncthreads(); // the next chunk overwrites the staging buffers
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ storer
+        uint32_t pending_slot = 0xffffffffu;
+        for (uint32_t k = 0;; k++) {
+            const uint32_t o = k % kOutStages;
+            const uint32_t ph = (k / kOutStages) & 1u;
+            mbar_wait(smem_u32(&sm.full_out[o]), ph, p.status);
+            const StoreRec sr = sm.store_rec[o];
+            if (sr.kind == kSkip) break; // end of this CTA's work
+            uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)sr.dst_lo | ((uint64_t)sr.dst_hi << 32));
+            store_image_warp(smem_u32(&sm.out_stage[o][0]) + sr.s_off, dst, sr.bytes, lane);
+            __syncwarp();
+            if (lane == 0) {
+                tma_commit();
+                // at most one bulk store may still be reading shared memory: the one just issued.  The previous
+                // one has finished with its stage, which can go back to the consumers.
+                tma_wait_read<1>();
+                if (pending_slot != 0xffffffffu) mbar_arrive(smem_u32(&sm.empty_out[pending_slot]));
+            }
+            pending_slot = o;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            tma_wait_all<0>(); // all bulk stores complete before the CTA (and its shared memory) goes away
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const uint32_t t = threadIdx.x - 64;
+        RampRegs rr;
+        rr.table = smem_u32(&sm.table2[0]);
+        uint32_t k = 0; // chunks handed to the storer so far
+        uint32_t it = 0;
+        for (uint64_t c = blockIdx.x; c < p.n; c += gridDim.x, it++) {
+            const uint32_t s = it % kInStages;
+            const uint32_t ph = (it / kInStages) & 1u;
+            mbar_wait(smem_u32(&sm.full_in[s]), ph, p.status);
+            const ChunkRec cr = sm.rec[s];
+            if (cr.kind == kPcm) {
+                const uint32_t o = k % kOutStages;
+                const uint32_t oph = (k / kOutStages) & 1u;
+                k++;
+                mbar_wait(smem_u32(&sm.empty_out[o]), oph ^ 1u, p.status);
+                const uint32_t s_off = cr.dst_lo & 12u;
+                const uint32_t in_addr = smem_u32(&sm.in_stage[s][0]);
+                const uint32_t out_addr = smem_u32(&sm.out_stage[o][0]) + s_off;
+                if (cr.mode & kModeTransform) {
+                    rr.c = cr.ramp_c; rr.sign = cr.ramp_sign; rr.total = cr.ramp_total;
+                    rr.magic = cr.ramp_magic; rr.shift = cr.ramp_shift; rr.div1 = cr.ramp_div1;
+                    switch (cr.bytes_per_subsample) {
+                    case 1: transform_dispatch<1>(cr, rr, in_addr, out_addr, t); break;
+                    case 2: transform_dispatch<2>(cr, rr, in_addr, out_addr, t); break;
+                    case 3: transform_dispatch<3>(cr, rr, in_addr, out_addr, t); break;
+                    default: transform_dispatch<4>(cr, rr, in_addr, out_addr, t); break;
+                    }
+                } else {
+                    copy_chunk(in_addr, cr.head, out_addr, cr.bytes, t);
+                }
+                if (t == 0) {
+                    StoreRec sr;
+                    sr.kind = kPcm; sr.bytes = cr.bytes; sr.s_off = s_off; sr.pad = 0;
+                    sr.dst_lo = cr.dst_lo; sr.dst_hi = cr.dst_hi; sr.pad2[0] = sr.pad2[1] = 0;
+                    sm.store_rec[o] = sr;
+                }
+                fence_proxy_async(); // this thread's shared-memory writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&sm.full_out[o]));
+                    mbar_arrive(smem_u32(&sm.empty_in[s]));
+                }
+            } else {
+                if (cr.kind == kSilence) {
+                    uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
+                    write_silence(dst, cr.bytes, cr.channels, cr.bytes_per_subsample, t);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty_in[s]));
+            }
+        }
+        // tell the storer there is nothing more
+        const uint32_t o = k % kOutStages;
+        const uint32_t oph = (k / kOutStages) & 1u;
+        mbar_wait(smem_u32(&sm.empty_out[o]), oph ^ 1u, p.status);
+        if (t == 0) {
+            StoreRec sr;
+            sr.kind = kSkip; sr.bytes = 0; sr.s_off = 0; sr.pad = 0; sr.dst_lo = sr.dst_hi = 0; sr.pad2[0] = sr.pad2[1] = 0;
+            sm.store_rec[o] = sr;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.full_out[o]));
     }
 }
 
@@ -251,7 +374,7 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctx->ctas_per_sm;
     if (grid > n) grid = n;
     if (ctx->timing) OHP_CUDA(ctx, cudaEventRecord(ctx->ev_start, st));
-    ramp_convert_kernel<<<(unsigned)grid, kThreads, 0, st>>>(p);
+    ramp_convert_kernel<<<(unsigned)grid, kThreads, sizeof(SharedStorage), st>>>(p);
     OHP_CUDA(ctx, cudaGetLastError());
     if (ctx->timing) {
         OHP_CUDA(ctx, cudaEventRecord(ctx->ev_stop, st));
@@ -284,6 +407,7 @@ static int read_status(ohp_context* ctx, cudaStream_t st)
     OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, 2 * sizeof(uint32_t), st));
     OHP_CUDA(ctx, cudaStreamSynchronize(st));
     char buf[128];
+    if (bits & kErrWatchdog) return fail(ctx, OHP_E_CUDA, "kernel watchdog: a pipeline barrier never completed");
     std::snprintf(buf, sizeof buf, "device rejected chunk descriptor %u (%s)", first - 1,
                   (bits & kErrInvalidDesc) ? "invalid" : "out of range");
     return fail(ctx, (bits & kErrInvalidDesc) ? OHP_E_INVALID_DESC : OHP_E_OUT_OF_RANGE, buf);
@@ -401,7 +525,8 @@ int ohp_create(int device, ohp_context** out_ctx)
     }
     {
         int per_sm = 0;
-        OHP_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ramp_convert_kernel, kThreads, 0));
+        OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedStorage)));
+        OHP_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ramp_convert_kernel, kThreads, sizeof(SharedStorage)));
         ctx->ctas_per_sm = per_sm > 0 ? per_sm : 1;
     }
 #undef OHP_CREATE

@@ -1,19 +1,26 @@
 // ohp_kernels.cuh -- device code of the fused ramp + format-convert path (sm_100a).
 //
-// One MsgPlayable ("chunk") is the unit of work.  Per chunk a CTA
-//   1. fetches the 32-byte descriptor (two 128-bit loads, broadcast to the CTA),
-//   2. stages the chunk's source bytes into shared memory with coalesced 128-bit loads of the
-//      16-byte-aligned span that covers it (chunks start at arbitrary byte offsets: a 24-bit stereo
-//      frame is 6 bytes, a split playable starts wherever the ramp ended),
-//   3. transforms "units" of four subsamples held in registers: unpack (BE or LE wire order,
-//      DecodedAudio::CopyToBigEndian*, Msg.cpp:380-408), attenuate (MsgPlayablePcm::ApplyAttenuation,
-//      Msg.cpp:2736-2751), ramp (RampApplicator::GetNextSample, Msg.cpp:832-899) and repack for the
-//      IPcmProcessor sink (packed BE / packed LE) -- byte shuffles are PRMT, the ramp is one IMAD,
-//   4. writes the result with 128-bit stores to the 16-byte-aligned span of the destination and
-//      byte stores for the ragged head/tail.
-// The 512-entry ramp curve sits in shared memory (as 2*multiplier so that the Q15 product's high half
-// is the answer), and the per-frame ramp position trunc(i*total/(N-1)) is an exact multiply-high by a
-// per-chunk magic reciprocal instead of the reference's per-frame integer divide.
+// One MsgPlayable ("chunk") is the unit of work.  The kernel is persistent and warp-specialised; every CTA runs
+//
+//   loader  (warp 0, one lane)  walks this CTA's chunks: fetches the 32-byte descriptor, restates the reference's
+//                               ASSERTs, precomputes the per-chunk ramp constants, and pulls the 16-byte-aligned
+//                               span that covers the chunk's source bytes into a shared-memory ring with ONE
+//                               TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on an mbarrier);
+//   consumers (kConsumerWarps)  wait on the ring's "full" mbarrier and transform "units" of four subsamples held in
+//                               registers: unpack (BE or LE wire order -- DecodedAudio::CopyToBigEndian*,
+//                               Msg.cpp:380-408), attenuate (MsgPlayablePcm::ApplyAttenuation, Msg.cpp:2736-2751),
+//                               ramp (RampApplicator::GetNextSample, Msg.cpp:832-899) and repack for the
+//                               IPcmProcessor sink (packed BE / packed LE); byte shuffles are PRMT, the ramp is one
+//                               IMAD per subsample; results go to a second shared-memory ring;
+//   storer  (warp 1)            drains that ring: the 16-byte-aligned interior of the destination with ONE TMA bulk
+//                               store (cp.async.bulk.global.shared::cta), the ragged head/tail (chunks start at
+//                               arbitrary byte offsets: a 24-bit stereo frame is 6 bytes, a split playable starts
+//                               wherever the ramp ended) with byte stores.
+//
+// The 512-entry ramp curve sits in shared memory as 2*multiplier, so that the high half of the 16x16 product is
+// the reference's (s16 * mult) >> 15; the per-frame ramp position trunc(i*total/(N-1)) is an exact multiply-high by
+// a per-chunk magic reciprocal instead of the reference's per-frame integer divide.  Silence chunks
+// (MsgPlayableSilence::ReadBlock, Msg.cpp:2874-2893) are written straight to global memory by the consumers.
 //
 // Everything is integer; results are bit-exact against the reference (see oracle/).
 #pragma once
@@ -25,14 +32,19 @@
 
 namespace ohp {
 
-constexpr int kThreads = 128;                 // threads per CTA
+constexpr int kConsumerWarps = 4;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = 64 + kConsumerThreads;   // loader warp + storer warp + consumers
+constexpr int kInStages = 3;
+constexpr int kOutStages = 2;
 constexpr uint32_t kMaxChunk = OHP_MAX_PCM_CHUNK_BYTES;
-constexpr uint32_t kSinBytes = kMaxChunk + 48;  // aligned span (<= 9216+30 rounded) + one pad word for funnel reads
-constexpr uint32_t kSoutBytes = kMaxChunk + 32; // transformed image at offset 0 + pad for the last partial unit / funnel
+constexpr uint32_t kInStageBytes = kMaxChunk + 32;   // aligned span <= 15 + 9216 rounded up to 16, + a pad word for funnel reads
+constexpr uint32_t kOutStageBytes = kMaxChunk + 32;  // image at offset (dst & 12), + room for the last partial unit
 
 // device status word bits (OR-ed by the kernel, read back by ohp_sync)
 constexpr uint32_t kErrInvalidDesc = 1u;
 constexpr uint32_t kErrOutOfRange = 2u;
+constexpr uint32_t kErrWatchdog = 4u;
 
 struct KernelParams
 {
@@ -46,16 +58,171 @@ struct KernelParams
     uint32_t* status;        // [0] error bits, [1] index of first offending chunk + 1
 };
 
-// ---------------------------------------------------------------------------------------------
-// small helpers
+// What the loader hands to the consumers for one chunk (one 64-byte shared-memory record per ring stage).
+enum ChunkKind : uint32_t { kSkip = 0, kPcm = 1, kSilence = 2 };
 
-__device__ __forceinline__ uint4 ldg128_stream(const void* p)
+struct ChunkRec
 {
-    // streaming data, read once: do not allocate in L1
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
+    uint32_t kind;
+    uint32_t bytes;       // payload bytes (== output bytes for the packed sinks)
+    uint32_t head;        // src & 15: where the chunk starts inside the staged span
+    uint32_t mode;        // bit0 ramped, bit1 in_le, bit2 out_le, bit3 tag6, bit4 transform needed
+    uint32_t channels;
+    uint32_t ch_magic;    // ceil(2^32 / channels); 0 for mono
+    uint32_t attenuation;
+    uint32_t bytes_per_subsample;
+    // ramp: table index for frame i is min(511, (ramp_c + ramp_sign * q(i)) >> 5), q(i) = (i * total) / (N - 1)
+    uint32_t ramp_c;      // 16384 + 16 - Start
+    int32_t  ramp_sign;   // +1 ramp down, -1 ramp up
+    uint32_t ramp_total;  // |Start - End|
+    uint32_t ramp_magic;  // ceil(2^(32+shift) / (N-1)) ...
+    uint32_t ramp_shift;  // ... so that q = umulhi(i*total, magic) >> shift exactly
+    uint32_t ramp_div1;   // N - 1 == 1: q = i * total
+    uint32_t dst_lo, dst_hi;
+};
+static_assert(sizeof(ChunkRec) == 64, "ChunkRec is one 64-byte record");
+
+constexpr uint32_t kModeRamped = 1u, kModeInLe = 2u, kModeOutLe = 4u, kModeTag6 = 8u, kModeTransform = 16u;
+
+// What the consumers hand to the storer.
+struct StoreRec
+{
+    uint32_t kind;     // kPcm, or kSkip = end of this CTA's work
+    uint32_t bytes;
+    uint32_t s_off;    // byte offset of the image inside the out stage (== dst & 12)
+    uint32_t pad;
+    uint32_t dst_lo, dst_hi;
+    uint32_t pad2[2];
+};
+
+struct __align__(128) SharedStorage
+{
+    uint8_t in_stage[kInStages][kInStageBytes];
+    uint8_t out_stage[kOutStages][kOutStageBytes];
+    ChunkRec rec[kInStages];
+    StoreRec store_rec[kOutStages];
+    uint16_t table2[OHP_RAMP_TABLE_ENTRIES];
+    uint64_t full_in[kInStages];
+    uint64_t empty_in[kInStages];
+    uint64_t full_out[kOutStages];
+    uint64_t empty_out[kOutStages];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (mbarrier, TMA bulk copies, shared-memory accesses by 32-bit address)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait with a watchdog: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) { // ~2 s at 1.9 GHz: far beyond any legitimate wait
+            atomicOr(&status[0], kErrWatchdog);
+            __trap();
+        }
+    }
+}
+// global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared -> global bulk copy (TMA), tracked by bulk async-groups.
+__device__ __forceinline__ void tma_store(void* dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (the TMA store that follows)
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// PRMT with the full selector semantics (bit 3 of a selector nibble replicates the sign of the chosen byte);
+// __byte_perm only honours the low three bits of each nibble.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("{\n .reg .u16 t;\n ld.shared.u16 t, [%1];\n cvt.u32.u16 %0, t;\n}" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("{\n .reg .u16 t;\n ld.shared.u8 t, [%1];\n cvt.u32.u16 %0, t;\n}" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 __device__ __forceinline__ void stg128_stream(void* p, const uint4& v)
@@ -64,60 +231,74 @@ __device__ __forceinline__ void stg128_stream(void* p, const uint4& v)
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// floor(k / ch) for k < 2^27, ch in 1..32: multiply-high by ceil(2^32/ch) (exact: error < ch * k / 2^32 < 1)
-__device__ __forceinline__ uint32_t div_channels(uint32_t k, uint32_t ch_magic)
-{
-    return ch_magic == 0 ? k : __umulhi(k, ch_magic);
-}
+// ---------------------------------------------------------------------------------------------
+// ramp position -> multiplier
 
-// Per-chunk ramp constants, computed once by one thread (Msg.cpp:820-837 restated).
-struct RampConst
+// Per-chunk constants (Msg.cpp:820-837 restated).  Called by the loader lane only.
+__device__ __forceinline__ void make_ramp_const(ChunkRec& r, uint32_t start, uint32_t end, uint32_t frames)
 {
-    uint32_t start;     // Ramp::Start()
-    uint32_t total;     // |Start - End|
-    uint32_t up;        // End > Start: ramp value rises with the frame index
-    uint32_t magic;     // ceil(2^(32+shift) / (N-1)); q = umulhi(i*total, magic) >> shift == (i*total)/(N-1) exactly
-    uint32_t shift;
-    uint32_t div_by_one; // N-1 == 1: q = i*total
-};
-
-__device__ __forceinline__ RampConst make_ramp_const(uint32_t start, uint32_t end, uint32_t frames)
-{
-    RampConst rc;
-    rc.start = start;
-    rc.up = end > start;
-    rc.total = rc.up ? end - start : start - end;
+    const bool up = end > start;
+    r.ramp_c = OHP_RAMP_MAX + 16u - start;
+    r.ramp_sign = up ? -1 : 1;
+    r.ramp_total = up ? end - start : start - end;
     const uint32_t d = frames > 1 ? frames - 1 : 0;
-    rc.div_by_one = (d == 1);
-    rc.magic = 0;
-    rc.shift = 0;
+    r.ramp_div1 = (d == 1);
+    r.ramp_magic = 0;
+    r.ramp_shift = 0;
     if (d > 1) {
         // x = i*total < 9216*16384 < 2^28.  With L = ceil(log2 d) and p = 31 + L:
         //   magic = ceil(2^p / d) < 2^32 and magic*d - 2^p < d <= 2^L, so the error term x*2^L/2^p < 2^(28-31) < 1.
         const uint32_t L = 32 - __clz(d - 1);
         const uint32_t p = 31 + L;
-        rc.magic = (uint32_t)((((uint64_t)1 << p) + d - 1) / d);
-        rc.shift = p - 32;
+        r.ramp_magic = (uint32_t)((((uint64_t)1 << p) + d - 1) / d);
+        r.ramp_shift = p - 32;
     }
-    return rc;
 }
 
-// 2 * kRampArray[rampIndex] for frame i (RampApplicator::GetNextSample, Msg.cpp:835-837, 864)
-__device__ __forceinline__ uint32_t ramp_mult2(const RampConst& rc, const uint16_t* s_table2, uint32_t frame)
+struct RampRegs
 {
-    const uint32_t x = frame * rc.total;
-    const uint32_t q = rc.div_by_one ? x : (__umulhi(x, rc.magic) >> rc.shift);
-    const uint32_t ramp = rc.up ? rc.start + q : rc.start - q;
-    // (kFullRampSpan - ramp + 16) >> 5, clamped to the last table entry.  Frames past the end of a chunk
-    // (tail of the last unit) can take ramp out of range; the unsigned wrap lands on the clamp.
-    const uint32_t idx = min(511u, (OHP_RAMP_MAX + 16u - ramp) >> 5);
-    return s_table2[idx];
+    uint32_t c;
+    int32_t sign;
+    uint32_t total, magic, shift, div1;
+    uint32_t table; // shared-memory address of table2
+};
+
+// 2 * kRampArray[rampIndex] for frame i (RampApplicator::GetNextSample, Msg.cpp:835-837, 864).
+// Frames past the end of a chunk (tail of the last unit) can push the index out of range; the unsigned clamp
+// catches both directions and the value is never stored.
+__device__ __forceinline__ uint32_t ramp_mult2(const RampRegs& rr, uint32_t frame)
+{
+    const uint32_t x = frame * rr.total;
+    const uint32_t q = rr.div1 ? x : (__umulhi(x, rr.magic) >> rr.shift);
+    const uint32_t idx = min(511u, (rr.c + (uint32_t)(rr.sign * (int32_t)q)) >> 5);
+    return lds16(rr.table + 2u * idx);
 }
 
 // ---------------------------------------------------------------------------------------------
 // unit transform: four subsamples of B bytes each (4*B bytes = B words) in registers
 
-// Left-justified big-endian value of subsample j (low 4-B bytes are don't-care).
+// Subsample j's two most significant bytes as a sign-extended 16-bit value (8-bit: byte << 8): one PRMT with
+// sign replication (selector nibble | 8).  r holds the unit's B words (+1 zero word).
+template <int B>
+__device__ __forceinline__ int32_t unit_s16(const uint32_t (&r)[B + 1], int j, bool le)
+{
+    const int o = j * B;
+    const int wi = o >> 2;
+    const int oo = o & 3;
+    // byte indices (within the register pair) of the most significant and next byte
+    const int msb_be = oo, nxt_be = oo + 1;
+    const int msb_le = oo + B - 1, nxt_le = oo + B - 2;
+    if (B == 1) {
+        // (int8)b << 8: low byte zero -- take it from the always-zero top word r[B]... use a shift instead
+        const uint32_t sel = (uint32_t)msb_be | ((uint32_t)msb_be << 4) | ((uint32_t)(msb_be | 8) << 8) | ((uint32_t)(msb_be | 8) << 12);
+        return (int32_t)(prmt(r[wi], r[wi + 1], sel) & 0xffffff00u);
+    }
+    const uint32_t sel_be = (uint32_t)nxt_be | ((uint32_t)msb_be << 4) | ((uint32_t)(msb_be | 8) << 8) | ((uint32_t)(msb_be | 8) << 12);
+    const uint32_t sel_le = (uint32_t)nxt_le | ((uint32_t)msb_le << 4) | ((uint32_t)(msb_le | 8) << 8) | ((uint32_t)(msb_le | 8) << 12);
+    return (int32_t)prmt(r[wi], r[wi + 1], le ? sel_le : sel_be);
+}
+
+// Left-justified big-endian value of subsample j (low 4-B bytes are don't-care) -- the unramped paths.
 template <int B>
 __device__ __forceinline__ uint32_t unit_extract(const uint32_t (&r)[B + 1], int j, bool le)
 {
@@ -135,161 +316,186 @@ __device__ __forceinline__ uint32_t unit_extract(const uint32_t (&r)[B + 1], int
     return __byte_perm(r[wi], r[wi + 1], le ? sel_le : sel_be);
 }
 
-// Pack four left-justified results into B output words in BE or LE subsample byte order.
+// Pack four left-justified results into B output words in BE or LE subsample byte order.  With `ramped` the bytes
+// below the 16-bit result must read as zero (Msg.cpp:868-895): masked per output word after packing.
 template <int B>
-__device__ __forceinline__ void unit_pack(const uint32_t (&o)[4], uint32_t (&w)[B], bool le)
+__device__ __forceinline__ void unit_pack(const uint32_t (&o)[4], uint32_t (&w)[B], bool le, bool ramped)
 {
     if constexpr (B == 1) {
-        // top byte of each result
         const uint32_t lo = __byte_perm(o[0], o[1], 0x0073);
         const uint32_t hi = __byte_perm(o[2], o[3], 0x0073);
         w[0] = __byte_perm(lo, hi, 0x5410);
     } else {
 #pragma unroll
-    for (int m = 0; m < B; m++) {
-        const int j_lo = (4 * m) / B;
-        uint32_t sel_be = 0, sel_le = 0;
+        for (int m = 0; m < B; m++) {
+            const int j_lo = (4 * m) / B;
+            const int j_hi = (4 * m + 3) / B;
+            uint32_t sel_be = 0, sel_le = 0, keep_be = 0, keep_le = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int q = 4 * m + i;
-            const int j = q / B;
-            const int t = q % B;
-            const int src = (j == j_lo) ? 0 : 4;          // first or second PRMT operand
-            const int bbe = 3 - t;                        // MSB first
-            const int ble = 3 - (B - 1 - t);              // LSB first
-            sel_be |= (uint32_t)(src + bbe) << (4 * i);
-            sel_le |= (uint32_t)(src + ble) << (4 * i);
+            for (int i = 0; i < 4; i++) {
+                const int q = 4 * m + i;
+                const int j = q / B;
+                const int t = q % B;
+                const int src = (j == j_lo) ? 0 : 4;          // first or second PRMT operand
+                const int bbe = 3 - t;                        // MSB first
+                const int ble = 3 - (B - 1 - t);              // LSB first
+                sel_be |= (uint32_t)(src + bbe) << (4 * i);
+                sel_le |= (uint32_t)(src + ble) << (4 * i);
+                // a ramped result only has its two top bytes (index 3 and 2) populated
+                if (bbe >= 2) keep_be |= 0xffu << (8 * i);
+                if (ble >= 2) keep_le |= 0xffu << (8 * i);
+            }
+            uint32_t v = __byte_perm(o[j_lo], o[j_hi], le ? sel_le : sel_be);
+            if (B == 3 && ramped) v &= (le ? keep_le : keep_be); // 32-bit results carry their own zero/tag bytes
+            w[m] = v;
         }
-        const int j_hi = (4 * m + 3) / B;
-        w[m] = __byte_perm(o[j_lo], o[j_hi], le ? sel_le : sel_be);
-    }
     }
 }
 
-struct ChunkCtx
+// Transform one chunk: staged source image at in_addr (+head) -> image at out_addr.  `t` is the consumer thread
+// index (0..kConsumerThreads-1).  CHM selects how the four subsamples of a unit map to frames:
+//   1 mono (4 frames per unit), 2 stereo (2 frames), 4 channels % 4 == 0 (1 frame), 0 anything else (<= 2 frames).
+template <int B, int CHM>
+__device__ __forceinline__ void transform_chunk(const ChunkRec& cr, const RampRegs& rr, uint32_t in_addr, uint32_t out_addr, uint32_t t)
 {
-    uint32_t bytes;        // payload bytes (== output bytes for packed sinks)
-    uint32_t channels;
-    uint32_t ch_magic;     // ceil(2^32/ch), 0 for mono
-    uint32_t attenuation;  // 256 = unity
-    bool ramped;
-    bool in_le;
-    bool out_le;
-    bool tag6;             // 6-channel 32-bit: channel id in the low byte of ramped subsamples
-};
-
-// Transform the whole chunk from the staged source image (s_in + head) into s_out (offset 0).
-template <int B>
-__device__ __forceinline__ void transform_chunk(const ChunkCtx& cx, const RampConst& rc, const uint16_t* s_table2,
-                                                const uint8_t* s_in, uint32_t head, uint8_t* s_out)
-{
-    const uint32_t subsamples = cx.bytes / B;
+    const uint32_t subsamples = (B == 3) ? __umulhi(cr.bytes, 0x55555556u) : cr.bytes / B; // exact: bytes % B == 0
     const uint32_t units = (subsamples + 3) >> 2;
-    const uint32_t* in_w = reinterpret_cast<const uint32_t*>(s_in) + (head >> 2);
-    const uint32_t fshift = (head & 3) * 8;
-    uint32_t* out_w = reinterpret_cast<uint32_t*>(s_out);
-    for (uint32_t u = threadIdx.x; u < units; u += kThreads) {
+    const bool ramped = (cr.mode & kModeRamped) != 0;
+    const bool in_le = (cr.mode & kModeInLe) != 0;
+    const bool out_le = (cr.mode & kModeOutLe) != 0;
+    const bool tag6 = (cr.mode & kModeTag6) != 0;
+    const uint32_t src = in_addr + (cr.head & ~3u);
+    const uint32_t fshift = (cr.head & 3u) * 8u;
+    const uint32_t channels = cr.channels;
+    for (uint32_t u = t; u < units; u += kConsumerThreads) {
         // B source words, realigned when the chunk starts off a word boundary
-        uint32_t raw[B + 1];
-#pragma unroll
-        for (int i = 0; i <= B; i++) raw[i] = in_w[u * B + i];
         uint32_t r[B + 1];
+        {
+            uint32_t raw[B + 1];
+            const uint32_t a = src + u * (4u * B);
 #pragma unroll
-        for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
-        r[B] = 0;
-
-        uint32_t o[4];
-        uint32_t frame = 0, chan = 0, mult2 = 0;
-        if (cx.ramped) {
-            const uint32_t k0 = 4 * u;
-            frame = div_channels(k0, cx.ch_magic);
-            chan = k0 - frame * cx.channels;
-            mult2 = ramp_mult2(rc, s_table2, frame);
+            for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
+#pragma unroll
+            for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
+            r[B] = 0;
         }
+        uint32_t o[4];
+        if (ramped) {
+            // frames of the unit's subsamples and their multipliers
+            uint32_t m[4];
+            uint32_t chan0 = 0;
+            if (CHM == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t v = unit_extract<B>(r, j, cx.in_le);
-            if (B == 2 && cx.attenuation != OHP_UNITY_ATTENUATION) {
-                // ((TInt)sample) * iAttenuation / 256 in UNSIGNED 32-bit arithmetic, truncated to 16 bits (Msg.cpp:2746)
-                const uint32_t s = (uint32_t)((int32_t)v >> 16);
-                v = ((s * cx.attenuation) >> 8) << 16;
+                for (int j = 0; j < 4; j++) m[j] = ramp_mult2(rr, 4u * u + j);
+            } else if (CHM == 2) {
+                m[0] = m[1] = ramp_mult2(rr, 2u * u);
+                m[2] = m[3] = ramp_mult2(rr, 2u * u + 1u);
+            } else if (CHM == 4) {
+                const uint32_t f0 = __umulhi(4u * u, cr.ch_magic);
+                chan0 = 4u * u - f0 * channels;
+                m[0] = m[1] = m[2] = m[3] = ramp_mult2(rr, f0);
+            } else {
+                // channels >= 3, not a multiple of 4: the unit touches frames f0 and possibly f0+1
+                const uint32_t f0 = __umulhi(4u * u, cr.ch_magic);
+                chan0 = 4u * u - f0 * channels;
+                const uint32_t ma = ramp_mult2(rr, f0);
+                const uint32_t mb = ramp_mult2(rr, f0 + 1u);
+#pragma unroll
+                for (int j = 0; j < 4; j++) m[j] = (chan0 + j >= channels) ? mb : ma;
             }
-            if (cx.ramped) {
-                if (j > 0) {
-                    chan++;
-                    if (chan == cx.channels) {
-                        chan = 0;
-                        frame++;
-                        mult2 = ramp_mult2(rc, s_table2, frame);
-                    }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int32_t s16 = unit_s16<B>(r, j, in_le);
+                if (B == 2 && cr.attenuation != OHP_UNITY_ATTENUATION) {
+                    // ((TInt)sample) * iAttenuation / 256 in UNSIGNED 32-bit arithmetic, truncated to 16 bits (Msg.cpp:2746)
+                    s16 = (int32_t)(int16_t)(((uint32_t)s16 * cr.attenuation) >> 8);
                 }
-                // subsample16 from the two most significant bytes (8-bit: byte << 8), Msg.cpp:840-862
-                const int32_t s16 = (B == 1) ? (((int32_t)v >> 24) << 8) : ((int32_t)v >> 16);
-                // (s16 * mult) >> 15 kept to 16 bits == high half of s16 * (2*mult); low bytes are zero (Msg.cpp:865-895)
-                const uint32_t prod2 = (uint32_t)(s16 * (int32_t)mult2);
-                v = prod2 & (B == 1 ? 0xFF000000u : 0xFFFF0000u);
-                if (B == 4 && cx.tag6) v |= chan << 4;
+                // (s16 * mult) >> 15 kept to 16 bits == high half of s16 * (2*mult) (Msg.cpp:865)
+                uint32_t v = (uint32_t)(s16 * (int32_t)m[j]);
+                if (B == 4) {
+                    // bytes: hi, lo, 00, channel tag on 6-channel audio (Msg.cpp:880-891)
+                    uint32_t c = chan0 + j;
+                    if (CHM == 0) c = (c >= channels) ? c - channels : c;
+                    v = (v & 0xffff0000u) | (tag6 ? (c << 4) : 0u);
+                }
+                o[j] = v;
             }
-            o[j] = v;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t v = unit_extract<B>(r, j, in_le);
+                if (B == 2 && cr.attenuation != OHP_UNITY_ATTENUATION) {
+                    const uint32_t s = (uint32_t)((int32_t)v >> 16);
+                    v = ((s * cr.attenuation) >> 8) << 16;
+                }
+                o[j] = v;
+            }
         }
         uint32_t w[B];
-        unit_pack<B>(o, w, cx.out_le);
+        unit_pack<B>(o, w, out_le, ramped);
+        const uint32_t d = out_addr + u * (4u * B);
 #pragma unroll
-        for (int i = 0; i < B; i++) out_w[u * B + i] = w[i];
+        for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
+    }
+}
+
+template <int B>
+__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, const RampRegs& rr, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+{
+    const uint32_t ch = cr.channels;
+    if (ch == 2) transform_chunk<B, 2>(cr, rr, in_addr, out_addr, t);
+    else if ((ch & 3u) == 0) transform_chunk<B, 4>(cr, rr, in_addr, out_addr, t);
+    else if (ch == 1) transform_chunk<B, 1>(cr, rr, in_addr, out_addr, t);
+    else transform_chunk<B, 0>(cr, rr, in_addr, out_addr, t);
+}
+
+// Verbatim pass-through (Msg.cpp:2782-2784): copy the staged image to the out stage, realigning from
+// (head) to (s_off) byte offsets.  Both are congruent mod 4 only when src == dst mod 4; handle the general case
+// with a funnel shift on whole words.
+__device__ __forceinline__ void copy_chunk(uint32_t in_addr, uint32_t head, uint32_t out_addr, uint32_t bytes, uint32_t t)
+{
+    const uint32_t words = (bytes + 3u) >> 2;
+    const uint32_t src = in_addr + (head & ~3u);
+    const uint32_t fshift = (head & 3u) * 8u;
+    for (uint32_t w = t; w < words; w += kConsumerThreads) {
+        const uint32_t a = lds32(src + 4u * w);
+        const uint32_t b = lds32(src + 4u * w + 4u);
+        sts32(out_addr + 4u * w, __funnelshift_r(a, b, fshift));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// staging in / out
+// storing a finished image: `bytes` bytes at shared address s_addr -> global dst, by ONE warp.
+// Fast path (s_addr == dst mod 16): head/tail bytes + one TMA bulk store.  Otherwise a register funnel path.
 
-// Load the 16-byte-aligned span covering [src, src+bytes) into s_in; returns src & 15.
-__device__ __forceinline__ uint32_t stage_in(const uint8_t* in_base, uint64_t in_bytes, uint64_t src_off, uint32_t bytes,
-                                             uint8_t* s_in)
+__device__ __forceinline__ void store_ragged(uint32_t s_addr, uint8_t* dst, uint32_t from, uint32_t to, uint32_t lane)
 {
-    const uint64_t addr = reinterpret_cast<uint64_t>(in_base) + src_off;
-    const uint32_t head = (uint32_t)(addr & 15u);
-    const uint8_t* al = reinterpret_cast<const uint8_t*>(addr - head);
-    const uint32_t words = (head + bytes + 15u) >> 4;
-    const uint8_t* in_end = in_base + in_bytes;
-    uint4* s4 = reinterpret_cast<uint4*>(s_in);
-    for (uint32_t w = threadIdx.x; w < words; w += kThreads) {
-        const uint8_t* p = al + 16u * w;
-        if (p + 16 <= in_end) {
-            s4[w] = ldg128_stream(p);
-        } else {
-            // last word of the arena: touch only bytes that exist
-            for (uint32_t i = 0; i < 16; i++) s_in[16u * w + i] = (p + i < in_end) ? p[i] : 0;
-        }
-    }
-    return head;
+    // at most 15 bytes
+    const uint32_t i = from + lane;
+    if (i < to) dst[i] = (uint8_t)lds8(s_addr + i);
 }
 
-// Store `bytes` bytes found at s_src + s_off to the (arbitrarily aligned) global address dst.
-__device__ __forceinline__ void stage_out(const uint8_t* s_src, uint32_t s_off, uint8_t* dst, uint32_t bytes)
+__device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, uint32_t bytes, uint32_t lane)
 {
     const uint32_t lead = (uint32_t)((16u - (reinterpret_cast<uint64_t>(dst) & 15u)) & 15u);
     const uint32_t head_n = min(lead, bytes);
     const uint32_t words = (bytes - head_n) >> 4;
     const uint32_t tail_at = head_n + (words << 4);
-    // ragged head and tail: at most 15 bytes each
-    if (threadIdx.x < head_n) dst[threadIdx.x] = s_src[s_off + threadIdx.x];
-    if (threadIdx.x >= 32 && threadIdx.x - 32 < bytes - tail_at) {
-        const uint32_t i = tail_at + threadIdx.x - 32;
-        dst[i] = s_src[s_off + i];
-    }
-    const uint32_t base = s_off + head_n;          // byte offset in s_src of the first aligned store
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_src) + (base >> 2);
-    const uint32_t fshift = (base & 3) * 8;
-    uint4* d4 = reinterpret_cast<uint4*>(dst + head_n);
-    if (fshift == 0) {
-        for (uint32_t w = threadIdx.x; w < words; w += kThreads) {
-            uint4 v;
-            v.x = sw[4 * w + 0]; v.y = sw[4 * w + 1]; v.z = sw[4 * w + 2]; v.w = sw[4 * w + 3];
-            stg128_stream(d4 + w, v);
+    store_ragged(s_addr, dst, 0, head_n, lane);
+    store_ragged(s_addr, dst, tail_at, bytes, lane);
+    if (((s_addr + head_n) & 15u) == 0) {
+        if (lane == 0 && words != 0) {
+            tma_store(dst + head_n, s_addr + head_n, words << 4);
         }
     } else {
-        for (uint32_t w = threadIdx.x; w < words; w += kThreads) {
-            const uint32_t a0 = sw[4 * w + 0], a1 = sw[4 * w + 1], a2 = sw[4 * w + 2], a3 = sw[4 * w + 3], a4 = sw[4 * w + 4];
+        // destination and image disagree mod 16 (dst not 4-byte aligned): realign through registers
+        const uint32_t base = s_addr + head_n;
+        const uint32_t wbase = base & ~3u;
+        const uint32_t fshift = (base & 3u) * 8u;
+        uint4* d4 = reinterpret_cast<uint4*>(dst + head_n);
+        for (uint32_t w = lane; w < words; w += 32) {
+            const uint32_t a = wbase + 16u * w;
+            const uint32_t a0 = lds32(a), a1 = lds32(a + 4), a2 = lds32(a + 8), a3 = lds32(a + 12), a4 = lds32(a + 16);
             uint4 v;
             v.x = __funnelshift_r(a0, a1, fshift);
             v.y = __funnelshift_r(a1, a2, fshift);
@@ -302,7 +508,8 @@ __device__ __forceinline__ void stage_out(const uint8_t* s_src, uint32_t s_off, 
 
 // MsgPlayableSilence::ReadBlock (Msg.cpp:2874-2893): zeros; with 6 channels every emitted block of
 // maxBytes starts with 00 00 00 c0 for c0 = 0x00,0x10..0x70 (32 bytes, whatever the bit depth).
-__device__ __forceinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint32_t channels, uint32_t B)
+// Written straight to global memory by the consumer threads (t = 0..kConsumerThreads-1).
+__device__ __forceinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint32_t channels, uint32_t B, uint32_t t)
 {
     const uint32_t block = kMaxChunk - (kMaxChunk % (channels * B));
     const uint32_t lead = (uint32_t)((16u - (reinterpret_cast<uint64_t>(dst) & 15u)) & 15u);
@@ -314,20 +521,20 @@ __device__ __forceinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint
         const uint32_t r = i % block;
         return (r < 32u && (r & 3u) == 3u) ? ((r >> 2) << 4) : 0u;
     };
-    if (threadIdx.x < head_n) dst[threadIdx.x] = (uint8_t)value_at(threadIdx.x);
-    if (threadIdx.x >= 32 && threadIdx.x - 32 < bytes - tail_at) {
-        const uint32_t i = tail_at + threadIdx.x - 32;
+    if (t < head_n) dst[t] = (uint8_t)value_at(t);
+    if (t >= 32 && t - 32 < bytes - tail_at) {
+        const uint32_t i = tail_at + t - 32;
         dst[i] = (uint8_t)value_at(i);
     }
     uint4* d4 = reinterpret_cast<uint4*>(dst + head_n);
-    for (uint32_t w = threadIdx.x; w < words; w += kThreads) {
+    for (uint32_t w = t; w < words; w += kConsumerThreads) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (channels == 6) {
             const uint32_t i0 = head_n + 16u * w;
             if ((i0 % block) < 32u || (i0 % block) + 16u > block) {
-                uint32_t t[4] = {0, 0, 0, 0};
-                for (uint32_t i = 0; i < 16; i++) t[i >> 2] |= value_at(i0 + i) << (8 * (i & 3));
-                v = make_uint4(t[0], t[1], t[2], t[3]);
+                uint32_t tmp[4] = {0, 0, 0, 0};
+                for (uint32_t i = 0; i < 16; i++) tmp[i >> 2] |= value_at(i0 + i) << (8 * (i & 3));
+                v = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
             }
         }
         stg128_stream(d4 + w, v);
