@@ -15,7 +15,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_CUDA = os.path.join(_HERE, "libohp_b200.so")
+LIB_CUDA = os.environ.get("OHP_LIB_CUDA") or os.path.join(_HERE, "libohp_b200.so")  # override: kernel-tuning experiments
 LIB_HOST = os.path.join(_HERE, "libohp_host.so")
 
 

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t decode_chunk(const KernelParams& p, const ui
     r.channels = channels;
     r.ch_magic = c_ch_magic[channels];
     r.attenuation = attenuation;
-    r.bytes_per_subsample = B;
+    r.units = (bytes / B + 3u) >> 2;
     r.dst_lo = (uint32_t)dst;
     r.dst_hi = (uint32_t)(dst >> 32);
     const bool ramped = (flags & OHP_F_RAMP_ENABLED) != 0;
@@ -74,6 +74,9 @@ __device__ __forceinline__ uint32_t decode_chunk(const KernelParams& p, const ui
     const bool transform = ramped || (in_le != out_le) || attenuation != OHP_UNITY_ATTENUATION;
     r.mode = (ramped ? kModeRamped : 0u) | (in_le ? kModeInLe : 0u) | (out_le ? kModeOutLe : 0u)
            | ((channels == 6) ? kModeTag6 : 0u) | (transform ? kModeTransform : 0u);
+    const uint32_t chm = channels == 2 ? kChmStereo : ((channels & 3u) == 0 ? kChmMul4 : (channels == 1 ? kChmMono : kChmOther));
+    const bool aligned = r.head == 0 && (dst & 15u) == 0; // both images start on a 16-byte boundary of their stage
+    r.variant = (B - 1u) | (chm << 2) | (aligned ? 16u : 0u);
     make_ramp_const(r, ramp_start, ramp_end, frames);
     return 0;
 }
@@ -83,6 +86,17 @@ __device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uin
     atomicOr(&p.status[0], bits);
     atomicCAS(&p.status[1], 0u, (uint32_t)(chunk + 1 > 0xffffffffull ? 0xffffffffull : chunk + 1));
 }
+
+// Optional instrumentation (-DOHP_PROFILE_WAITS): cycles each role spends blocked on each barrier, summed over CTAs
+// into status[4..] in units of 4096 cycles.  [4] loader/empty_in [5] consumer/full_in [6] consumer/empty_out
+// [7] storer/full_out [8] CTA lifetime [9] loader busy (decode) [10] consumer busy (transform)
+#ifdef OHP_PROFILE_WAITS
+#define OHP_ACC(var, expr) (var) += (expr)
+#define OHP_FLUSH(slot, var) atomicAdd(&p.status[slot], (uint32_t)((var) >> 12))
+#else
+#define OHP_ACC(var, expr) (void)(expr)
+#define OHP_FLUSH(slot, var) (void)0
+#endif
 
 // Persistent, warp-specialised CTAs (see ohp_kernels.cuh): CTA b handles chunks b, b+grid, b+2*grid, ...
 __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
@@ -106,137 +120,145 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) sm.table2[i] = p.table2[i];
     __syncthreads();
 
+    long long w_loader = 0, w_storer = 0, w_full = 0, w_out = 0;
+    (void)w_loader; (void)w_storer; (void)w_full; (void)w_out;
+#ifdef OHP_PROFILE_WAITS
+    const long long t_begin = clock64();
+#endif
     if (warp == 0) {
         // ------------------------------------------------------------------ loader
-        if (lane == 0) {
-            const uint4* dp = reinterpret_cast<const uint4*>(p.descs);
-            uint64_t c = blockIdx.x;
-            uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-            if (c < p.n) { n0 = __ldg(dp + 2 * c); n1 = __ldg(dp + 2 * c + 1); }
-            for (uint32_t it = 0; c < p.n; c += gridDim.x, it++) {
-                const uint4 d0 = n0, d1 = n1;
-                const uint64_t cn = c + gridDim.x;
-                if (cn < p.n) { n0 = __ldg(dp + 2 * cn); n1 = __ldg(dp + 2 * cn + 1); } // next descriptor, a step ahead
-                ChunkRec r;
+        // chunks of this CTA: ordinal k <-> chunk blockIdx.x + k * gridDim.x
+        const uint64_t my_n = blockIdx.x < p.n ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint4* dp = reinterpret_cast<const uint4*>(p.descs);
+        for (uint64_t base = 0; base < my_n; base += 32) {
+            // all lanes: decode 32 descriptors into the record table (the half the consumers are done with)
+            const uint64_t k = base + lane;
+            ChunkRec r;
+            r.kind = kSkip;
+            uint64_t src_al = 0;
+            if (k < my_n) {
+                const uint64_t c = blockIdx.x + k * gridDim.x;
+                const uint4 d0 = __ldg(dp + 2 * c);
+                const uint4 d1 = __ldg(dp + 2 * c + 1);
                 uint64_t src_off;
                 const uint32_t err = decode_chunk(p, d0, d1, r, src_off);
                 if (err) report(p, err, c);
-                const uint32_t s = it % kInStages;
-                const uint32_t ph = (it / kInStages) & 1u;
-                mbar_wait(smem_u32(&sm.empty_in[s]), ph ^ 1u, p.status);
-                sm.rec[s] = r;
-                const uint32_t full = smem_u32(&sm.full_in[s]);
-                if (r.kind == kPcm) {
-                    const uint8_t* al = p.in + src_off - r.head;
-                    uint32_t span = (r.head + r.bytes + 15u) & ~15u;
-                    const uint64_t room = (uint64_t)(p.in + p.in_bytes - al);
-                    const uint32_t stage = smem_u32(&sm.in_stage[s][0]);
-                    if (span > room) {
-                        // last 16-byte word of the arena is partial: fetch its bytes one by one
-                        const uint32_t whole = (uint32_t)(room & ~15ull);
-                        for (uint32_t i = whole; i < (uint32_t)room; i++) sm.in_stage[s][i] = al[i];
-                        span = whole;
-                    }
-                    if (span != 0) {
-                        mbar_arrive_expect_tx(full, span);
-                        tma_load(stage, al, span, full);
+                src_al = reinterpret_cast<uint64_t>(p.in) + src_off - r.head;
+            }
+            const uint32_t slot = (uint32_t)(k & (kRecSlots - 1));
+            sm.rec[slot] = r;
+            sm.load_src[slot] = src_al;
+            __syncwarp();
+            // one lane: feed the ring in order
+            if (lane == 0) {
+                const uint32_t count = (uint32_t)(my_n - base < 32 ? my_n - base : 32);
+                for (uint32_t j = 0; j < count; j++) {
+                    const uint64_t it = base + j;
+                    const uint32_t s = (uint32_t)(it % kInStages);
+                    const uint32_t ph = (uint32_t)(it / kInStages) & 1u;
+                    const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
+                    OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty_in[s]), ph ^ 1u, p.status));
+                    const uint32_t full = smem_u32(&sm.full_in[s]);
+                    if (sm.rec[sl].kind == kPcm) {
+                        const uint8_t* al = reinterpret_cast<const uint8_t*>(sm.load_src[sl]);
+                        uint32_t span = (sm.rec[sl].head + sm.rec[sl].bytes + 15u) & ~15u;
+                        const uint64_t room = (uint64_t)(p.in + p.in_bytes - al);
+                        if (span > room) {
+                            // last 16-byte word of the arena is partial: fetch its bytes one by one
+                            const uint32_t whole = (uint32_t)(room & ~15ull);
+                            for (uint32_t i = whole; i < (uint32_t)room; i++) sm.in_stage[s][i] = al[i];
+                            span = whole;
+                        }
+                        if (span != 0) {
+                            mbar_arrive_expect_tx(full, span);
+                            tma_load(smem_u32(&sm.in_stage[s][0]), al, span, full);
+                        } else {
+                            mbar_arrive(full);
+                        }
                     } else {
                         mbar_arrive(full);
                     }
-                } else {
-                    mbar_arrive(full);
                 }
             }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            OHP_FLUSH(4, w_loader);
+#ifdef OHP_PROFILE_WAITS
+            atomicAdd(&p.status[8], (uint32_t)((clock64() - t_begin) >> 12));
+#endif
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ storer
-        uint32_t pending_slot = 0xffffffffu;
-        for (uint32_t k = 0;; k++) {
-            const uint32_t o = k % kOutStages;
-            const uint32_t ph = (k / kOutStages) & 1u;
-            mbar_wait(smem_u32(&sm.full_out[o]), ph, p.status);
-            const StoreRec sr = sm.store_rec[o];
-            if (sr.kind == kSkip) break; // end of this CTA's work
-            uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)sr.dst_lo | ((uint64_t)sr.dst_hi << 32));
-            store_image_warp(smem_u32(&sm.out_stage[o][0]) + sr.s_off, dst, sr.bytes, lane);
+        // Every chunk, whatever its kind, passes through one out-ring slot, so the storer walks the same sequence as
+        // the consumers.  It reads the loader's record of the chunk after the consumers have signalled it (that is
+        // the ordering edge; the record table outlives the few chunks the storer can lag behind).
+        const uint64_t my_n = blockIdx.x < p.n ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        for (uint64_t it = 0; it < my_n; it++) {
+            const uint32_t o = (uint32_t)(it % kOutStages);
+            const uint32_t ph = (uint32_t)(it / kOutStages) & 1u;
+            OHP_ACC(w_storer, mbar_wait(smem_u32(&sm.full_out[o]), ph, p.status));
+            const ChunkRec& cr = sm.rec[it & (kRecSlots - 1)];
+            if (cr.kind == kPcm) {
+                uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
+                store_image_warp(smem_u32(&sm.out_stage[o][0]) + (cr.dst_lo & 12u), dst, cr.bytes, lane);
+            }
             __syncwarp();
             if (lane == 0) {
-                tma_commit();
-                // at most one bulk store may still be reading shared memory: the one just issued.  The previous
-                // one has finished with its stage, which can go back to the consumers.
-                tma_wait_read<1>();
-                if (pending_slot != 0xffffffffu) mbar_arrive(smem_u32(&sm.empty_out[pending_slot]));
+                tma_commit(); // possibly an empty group
+                // hand the stage back as soon as the bulk store has finished READING it (the global writes may still
+                // be in flight); meanwhile the consumers fill the other stage(s)
+                tma_wait_read<0>();
+                mbar_arrive(smem_u32(&sm.empty_out[o]));
             }
-            pending_slot = o;
             __syncwarp();
         }
         if (lane == 0) {
             tma_wait_all<0>(); // all bulk stores complete before the CTA (and its shared memory) goes away
+            OHP_FLUSH(7, w_storer);
         }
     } else {
         // ------------------------------------------------------------------ consumers
         const uint32_t t = threadIdx.x - 64;
-        RampRegs rr;
-        rr.table = smem_u32(&sm.table2[0]);
-        uint32_t k = 0; // chunks handed to the storer so far
+        const uint32_t table = smem_u32(&sm.table2[0]);
         uint32_t it = 0;
         for (uint64_t c = blockIdx.x; c < p.n; c += gridDim.x, it++) {
             const uint32_t s = it % kInStages;
             const uint32_t ph = (it / kInStages) & 1u;
-            mbar_wait(smem_u32(&sm.full_in[s]), ph, p.status);
-            const ChunkRec cr = sm.rec[s];
-            if (cr.kind == kPcm) {
-                const uint32_t o = k % kOutStages;
-                const uint32_t oph = (k / kOutStages) & 1u;
-                k++;
-                mbar_wait(smem_u32(&sm.empty_out[o]), oph ^ 1u, p.status);
-                const uint32_t s_off = cr.dst_lo & 12u;
+            const uint32_t o = it % kOutStages;
+            const uint32_t oph = (it / kOutStages) & 1u;
+            OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full_in[s]), ph, p.status));
+            OHP_ACC(w_out, mbar_wait(smem_u32(&sm.empty_out[o]), oph ^ 1u, p.status));
+            const ChunkRec& cr = sm.rec[it & (kRecSlots - 1)];
+            const uint32_t kind = cr.kind;
+            if (kind == kPcm) {
                 const uint32_t in_addr = smem_u32(&sm.in_stage[s][0]);
-                const uint32_t out_addr = smem_u32(&sm.out_stage[o][0]) + s_off;
+                const uint32_t out_addr = smem_u32(&sm.out_stage[o][0]) + (cr.dst_lo & 12u);
                 if (cr.mode & kModeTransform) {
-                    rr.c = cr.ramp_c; rr.sign = cr.ramp_sign; rr.total = cr.ramp_total;
-                    rr.magic = cr.ramp_magic; rr.shift = cr.ramp_shift; rr.div1 = cr.ramp_div1;
-                    switch (cr.bytes_per_subsample) {
-                    case 1: transform_dispatch<1>(cr, rr, in_addr, out_addr, t); break;
-                    case 2: transform_dispatch<2>(cr, rr, in_addr, out_addr, t); break;
-                    case 3: transform_dispatch<3>(cr, rr, in_addr, out_addr, t); break;
-                    default: transform_dispatch<4>(cr, rr, in_addr, out_addr, t); break;
+                    switch (cr.variant & 3u) {
+                    case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, t); break;
+                    case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, t); break;
+                    case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, t); break;
+                    default: transform_dispatch<4>(cr, table, in_addr, out_addr, t); break;
                     }
                 } else {
                     copy_chunk(in_addr, cr.head, out_addr, cr.bytes, t);
                 }
-                if (t == 0) {
-                    StoreRec sr;
-                    sr.kind = kPcm; sr.bytes = cr.bytes; sr.s_off = s_off; sr.pad = 0;
-                    sr.dst_lo = cr.dst_lo; sr.dst_hi = cr.dst_hi; sr.pad2[0] = sr.pad2[1] = 0;
-                    sm.store_rec[o] = sr;
-                }
                 fence_proxy_async(); // this thread's shared-memory writes -> visible to the TMA store
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(smem_u32(&sm.full_out[o]));
-                    mbar_arrive(smem_u32(&sm.empty_in[s]));
-                }
-            } else {
-                if (cr.kind == kSilence) {
-                    uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
-                    write_silence(dst, cr.bytes, cr.channels, cr.bytes_per_subsample, t);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.empty_in[s]));
+            } else if (kind == kSilence) {
+                uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
+                write_silence(dst, cr.bytes, cr.channels, (cr.variant & 3u) + 1u, t);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&sm.full_out[o]));
+                mbar_arrive(smem_u32(&sm.empty_in[s]));
             }
         }
-        // tell the storer there is nothing more
-        const uint32_t o = k % kOutStages;
-        const uint32_t oph = (k / kOutStages) & 1u;
-        mbar_wait(smem_u32(&sm.empty_out[o]), oph ^ 1u, p.status);
         if (t == 0) {
-            StoreRec sr;
-            sr.kind = kSkip; sr.bytes = 0; sr.s_off = 0; sr.pad = 0; sr.dst_lo = sr.dst_hi = 0; sr.pad2[0] = sr.pad2[1] = 0;
-            sm.store_rec[o] = sr;
+            OHP_FLUSH(5, w_full);
+            OHP_FLUSH(6, w_out);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.full_out[o]));
     }
 }
 
@@ -399,12 +421,12 @@ static int grow(ohp_context* ctx, T*& ptr, uint64_t& cap, uint64_t need)
 
 static int read_status(ohp_context* ctx, cudaStream_t st)
 {
-    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     OHP_CUDA(ctx, cudaStreamSynchronize(st));
     const uint32_t bits = ctx->h_status[0];
     if (bits == 0) return OHP_OK;
     const uint32_t first = ctx->h_status[1];
-    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, 2 * sizeof(uint32_t), st));
+    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, 16 * sizeof(uint32_t), st));
     OHP_CUDA(ctx, cudaStreamSynchronize(st));
     char buf[128];
     if (bits & kErrWatchdog) return fail(ctx, OHP_E_CUDA, "kernel watchdog: a pipeline barrier never completed");
@@ -511,9 +533,9 @@ int ohp_create(int device, ohp_context** out_ctx)
     OHP_CREATE(cudaEventCreate(&ctx->ev_start));
     OHP_CREATE(cudaEventCreate(&ctx->ev_stop));
     OHP_CREATE(cudaMalloc(reinterpret_cast<void**>(&ctx->d_table2), sizeof(uint16_t) * OHP_RAMP_TABLE_ENTRIES));
-    OHP_CREATE(cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), 2 * sizeof(uint32_t)));
-    OHP_CREATE(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), 2 * sizeof(uint32_t)));
-    OHP_CREATE(cudaMemset(ctx->d_status, 0, 2 * sizeof(uint32_t)));
+    OHP_CREATE(cudaMalloc(reinterpret_cast<void**>(&ctx->d_status), 16 * sizeof(uint32_t)));
+    OHP_CREATE(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), 16 * sizeof(uint32_t)));
+    OHP_CREATE(cudaMemset(ctx->d_status, 0, 16 * sizeof(uint32_t)));
     {
         uint16_t t2[OHP_RAMP_TABLE_ENTRIES];
         for (unsigned i = 0; i < OHP_RAMP_TABLE_ENTRIES; i++) t2[i] = (uint16_t)(2u * kRampTable[i]);
@@ -730,6 +752,17 @@ int ohp_memcpy_d2h(ohp_context* ctx, void* hptr, const void* dptr, uint64_t byte
 }
 
 uint64_t ohp_launch_count(const ohp_context* ctx) { return ctx ? ctx->launches : 0; }
+
+// Instrumentation builds only (-DOHP_PROFILE_WAITS): copy out and clear the 16 status words.
+int ohp_debug_counters(ohp_context* ctx, uint32_t* out16)
+{
+    if (!ctx || !out16) return OHP_E_INVALID_ARG;
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    OHP_CUDA(ctx, cudaDeviceSynchronize());
+    OHP_CUDA(ctx, cudaMemcpy(out16, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    OHP_CUDA(ctx, cudaMemset(ctx->d_status + 4, 0, 12 * sizeof(uint32_t)));
+    return OHP_OK;
+}
 
 int ohp_set_timing(ohp_context* ctx, int enabled)
 {

@@ -2,10 +2,11 @@
 //
 // One MsgPlayable ("chunk") is the unit of work.  The kernel is persistent and warp-specialised; every CTA runs
 //
-//   loader  (warp 0, one lane)  walks this CTA's chunks: fetches the 32-byte descriptor, restates the reference's
-//                               ASSERTs, precomputes the per-chunk ramp constants, and pulls the 16-byte-aligned
-//                               span that covers the chunk's source bytes into a shared-memory ring with ONE
-//                               TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on an mbarrier);
+//   loader  (warp 0)            walks this CTA's chunks: its 32 lanes fetch and decode 32 descriptors at a time
+//                               (restating the reference's ASSERTs and precomputing the per-chunk ramp constants),
+//                               then one lane pulls, chunk by chunk, the 16-byte-aligned span that covers the
+//                               chunk's source bytes into a shared-memory ring with ONE TMA bulk copy
+//                               (cp.async.bulk.shared::cluster.global, completion on an mbarrier);
 //   consumers (kConsumerWarps)  wait on the ring's "full" mbarrier and transform "units" of four subsamples held in
 //                               registers: unpack (BE or LE wire order -- DecodedAudio::CopyToBigEndian*,
 //                               Msg.cpp:380-408), attenuate (MsgPlayablePcm::ApplyAttenuation, Msg.cpp:2736-2751),
@@ -32,14 +33,28 @@
 
 namespace ohp {
 
-constexpr int kConsumerWarps = 4;
+// Tunables (overridable with -D for experiments; the defaults are what ships)
+#ifndef OHP_CONSUMER_WARPS
+#define OHP_CONSUMER_WARPS 4
+#endif
+#ifndef OHP_IN_STAGES
+#define OHP_IN_STAGES 3
+#endif
+#ifndef OHP_OUT_STAGES
+#define OHP_OUT_STAGES 2
+#endif
+#ifndef OHP_STAGE_CHUNK
+#define OHP_STAGE_CHUNK OHP_MAX_PCM_CHUNK_BYTES  /* experiments only: smaller stages cannot hold every legal chunk */
+#endif
+constexpr int kConsumerWarps = OHP_CONSUMER_WARPS;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = 64 + kConsumerThreads;   // loader warp + storer warp + consumers
-constexpr int kInStages = 3;
-constexpr int kOutStages = 2;
+constexpr int kInStages = OHP_IN_STAGES;
+constexpr int kOutStages = OHP_OUT_STAGES;
+constexpr int kRecSlots = 64;                     // two batches of 32 decoded chunk records
 constexpr uint32_t kMaxChunk = OHP_MAX_PCM_CHUNK_BYTES;
-constexpr uint32_t kInStageBytes = kMaxChunk + 32;   // aligned span <= 15 + 9216 rounded up to 16, + a pad word for funnel reads
-constexpr uint32_t kOutStageBytes = kMaxChunk + 32;  // image at offset (dst & 12), + room for the last partial unit
+constexpr uint32_t kInStageBytes = OHP_STAGE_CHUNK + 80;   // aligned span (<= 15 + 9216, rounded up to 16) + over-read of the last 16-subsample group
+constexpr uint32_t kOutStageBytes = OHP_STAGE_CHUNK + 80;  // image at offset (dst & 12) + over-write of the last 16-subsample group
 
 // device status word bits (OR-ed by the kernel, read back by ohp_sync)
 constexpr uint32_t kErrInvalidDesc = 1u;
@@ -58,7 +73,7 @@ struct KernelParams
     uint32_t* status;        // [0] error bits, [1] index of first offending chunk + 1
 };
 
-// What the loader hands to the consumers for one chunk (one 64-byte shared-memory record per ring stage).
+// What the loader hands to the consumers (and the storer) for one chunk: one 64-byte shared-memory record.
 enum ChunkKind : uint32_t { kSkip = 0, kPcm = 1, kSilence = 2 };
 
 struct ChunkRec
@@ -66,41 +81,32 @@ struct ChunkRec
     uint32_t kind;
     uint32_t bytes;       // payload bytes (== output bytes for the packed sinks)
     uint32_t head;        // src & 15: where the chunk starts inside the staged span
-    uint32_t mode;        // bit0 ramped, bit1 in_le, bit2 out_le, bit3 tag6, bit4 transform needed
+    uint32_t mode;        // kMode* bits
     uint32_t channels;
     uint32_t ch_magic;    // ceil(2^32 / channels); 0 for mono
     uint32_t attenuation;
-    uint32_t bytes_per_subsample;
+    uint32_t variant;     // consumer dispatch: (B-1) | chm << 2 | aligned << 4   (see kVar*)
     // ramp: table index for frame i is min(511, (ramp_c + ramp_sign * q(i)) >> 5), q(i) = (i * total) / (N - 1)
     uint32_t ramp_c;      // 16384 + 16 - Start
     int32_t  ramp_sign;   // +1 ramp down, -1 ramp up
-    uint32_t ramp_total;  // |Start - End|
+    uint32_t ramp_total;  // |Start - End|   (doubled when N - 1 == 1, see make_ramp_const)
     uint32_t ramp_magic;  // ceil(2^(32+shift) / (N-1)) ...
     uint32_t ramp_shift;  // ... so that q = umulhi(i*total, magic) >> shift exactly
-    uint32_t ramp_div1;   // N - 1 == 1: q = i * total
+    uint32_t units;       // ceil(subsamples / 4)
     uint32_t dst_lo, dst_hi;
 };
 static_assert(sizeof(ChunkRec) == 64, "ChunkRec is one 64-byte record");
 
 constexpr uint32_t kModeRamped = 1u, kModeInLe = 2u, kModeOutLe = 4u, kModeTag6 = 8u, kModeTransform = 16u;
-
-// What the consumers hand to the storer.
-struct StoreRec
-{
-    uint32_t kind;     // kPcm, or kSkip = end of this CTA's work
-    uint32_t bytes;
-    uint32_t s_off;    // byte offset of the image inside the out stage (== dst & 12)
-    uint32_t pad;
-    uint32_t dst_lo, dst_hi;
-    uint32_t pad2[2];
-};
+// how the four subsamples of a unit map to frames
+constexpr uint32_t kChmOther = 0u, kChmMono = 1u, kChmStereo = 2u, kChmMul4 = 3u;
 
 struct __align__(128) SharedStorage
 {
     uint8_t in_stage[kInStages][kInStageBytes];
     uint8_t out_stage[kOutStages][kOutStageBytes];
-    ChunkRec rec[kInStages];
-    StoreRec store_rec[kOutStages];
+    ChunkRec rec[kRecSlots];          // indexed by (chunk ordinal & (kRecSlots-1)); decoded 32 at a time
+    uint64_t load_src[kRecSlots];     // loader's own notes: 16-byte aligned source of the chunk's span
     uint16_t table2[OHP_RAMP_TABLE_ENTRIES];
     uint64_t full_in[kInStages];
     uint64_t empty_in[kInStages];
@@ -140,16 +146,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 // Wait with a watchdog: a protocol bug must surface as an error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status)
+__device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status)
 {
-    if (mbar_try_wait(bar, parity)) return;
+#ifdef OHP_PROFILE_WAITS
+    const long long t0 = clock64(); // try_wait itself suspends the thread, so time the first call too
+#else
+    if (mbar_try_wait(bar, parity)) return 0;
     const long long t0 = clock64();
+#endif
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) { // ~2 s at 1.9 GHz: far beyond any legitimate wait
             atomicOr(&status[0], kErrWatchdog);
             __trap();
         }
     }
+    return clock64() - t0; // cycles spent blocked (used by the OHP_PROFILE_WAITS instrumentation only)
 }
 // global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void tma_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
@@ -234,16 +245,21 @@ __device__ __forceinline__ void stg128_stream(void* p, const uint4& v)
 // ---------------------------------------------------------------------------------------------
 // ramp position -> multiplier
 
-// Per-chunk constants (Msg.cpp:820-837 restated).  Called by the loader lane only.
+// Per-chunk constants (Msg.cpp:820-837 restated).  Called by the loader.
 __device__ __forceinline__ void make_ramp_const(ChunkRec& r, uint32_t start, uint32_t end, uint32_t frames)
 {
     const bool up = end > start;
     r.ramp_c = OHP_RAMP_MAX + 16u - start;
     r.ramp_sign = up ? -1 : 1;
-    r.ramp_total = up ? end - start : start - end;
-    const uint32_t d = frames > 1 ? frames - 1 : 0;
-    r.ramp_div1 = (d == 1);
-    r.ramp_magic = 0;
+    uint32_t total = up ? end - start : start - end;
+    uint32_t d = frames > 1 ? frames - 1 : 0;
+    if (d == 1) {
+        // (i * total) / 1 == (i * 2 total) / 2: keeps the divisor >= 2 so that one formula serves every chunk
+        d = 2;
+        total *= 2;
+    }
+    r.ramp_total = total;
+    r.ramp_magic = 0;   // N == 1: q = 0, the ramp value is Start() (Msg.cpp:835)
     r.ramp_shift = 0;
     if (d > 1) {
         // x = i*total < 9216*16384 < 2^28.  With L = ceil(log2 d) and p = 31 + L:
@@ -259,17 +275,17 @@ struct RampRegs
 {
     uint32_t c;
     int32_t sign;
-    uint32_t total, magic, shift, div1;
+    uint32_t total, magic, shift;
     uint32_t table; // shared-memory address of table2
 };
 
 // 2 * kRampArray[rampIndex] for frame i (RampApplicator::GetNextSample, Msg.cpp:835-837, 864).
-// Frames past the end of a chunk (tail of the last unit) can push the index out of range; the unsigned clamp
+// Frames past the end of a chunk (tail of the last group) can push the index out of range; the unsigned clamp
 // catches both directions and the value is never stored.
 __device__ __forceinline__ uint32_t ramp_mult2(const RampRegs& rr, uint32_t frame)
 {
     const uint32_t x = frame * rr.total;
-    const uint32_t q = rr.div1 ? x : (__umulhi(x, rr.magic) >> rr.shift);
+    const uint32_t q = __umulhi(x, rr.magic) >> rr.shift;
     const uint32_t idx = min(511u, (rr.c + (uint32_t)(rr.sign * (int32_t)q)) >> 5);
     return lds16(rr.table + 2u * idx);
 }
@@ -352,108 +368,154 @@ __device__ __forceinline__ void unit_pack(const uint32_t (&o)[4], uint32_t (&w)[
     }
 }
 
-// Transform one chunk: staged source image at in_addr (+head) -> image at out_addr.  `t` is the consumer thread
-// index (0..kConsumerThreads-1).  CHM selects how the four subsamples of a unit map to frames:
-//   1 mono (4 frames per unit), 2 stereo (2 frames), 4 channels % 4 == 0 (1 frame), 0 anything else (<= 2 frames).
-template <int B, int CHM>
-__device__ __forceinline__ void transform_chunk(const ChunkRec& cr, const RampRegs& rr, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+struct UnitCtx
 {
-    const uint32_t subsamples = (B == 3) ? __umulhi(cr.bytes, 0x55555556u) : cr.bytes / B; // exact: bytes % B == 0
-    const uint32_t units = (subsamples + 3) >> 2;
-    const bool ramped = (cr.mode & kModeRamped) != 0;
-    const bool in_le = (cr.mode & kModeInLe) != 0;
-    const bool out_le = (cr.mode & kModeOutLe) != 0;
-    const bool tag6 = (cr.mode & kModeTag6) != 0;
+    uint32_t channels, ch_magic, attenuation;
+    bool ramped, in_le, out_le, tag6;
+};
+
+// One unit: four subsamples (B words in r[0..B-1]; r[B] may be anything) -> B output words.
+// CHM says how the unit's subsamples map to frames (kChm*); u is the unit's index inside the chunk.
+template <int B, uint32_t CHM>
+__device__ __forceinline__ void process_unit(const UnitCtx& cx, const RampRegs& rr, uint32_t u, const uint32_t (&r)[B + 1], uint32_t (&w)[B])
+{
+    uint32_t o[4];
+    if (cx.ramped) {
+        uint32_t m[4];
+        uint32_t chan0 = 0;
+        if (CHM == kChmMono) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) m[j] = ramp_mult2(rr, 4u * u + j);
+        } else if (CHM == kChmStereo) {
+            m[0] = m[1] = ramp_mult2(rr, 2u * u);
+            m[2] = m[3] = ramp_mult2(rr, 2u * u + 1u);
+        } else if (CHM == kChmMul4) {
+            const uint32_t f0 = __umulhi(4u * u, cx.ch_magic);
+            chan0 = 4u * u - f0 * cx.channels;
+            m[0] = m[1] = m[2] = m[3] = ramp_mult2(rr, f0);
+        } else {
+            // channels >= 3, not a multiple of 4: the unit touches frame f0 and possibly f0+1
+            const uint32_t f0 = __umulhi(4u * u, cx.ch_magic);
+            chan0 = 4u * u - f0 * cx.channels;
+            const uint32_t ma = ramp_mult2(rr, f0);
+            const uint32_t mb = ramp_mult2(rr, f0 + 1u);
+#pragma unroll
+            for (int j = 0; j < 4; j++) m[j] = (chan0 + j >= cx.channels) ? mb : ma;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int32_t s16 = unit_s16<B>(r, j, cx.in_le);
+            if (B == 2 && cx.attenuation != OHP_UNITY_ATTENUATION) {
+                // ((TInt)sample) * iAttenuation / 256 in UNSIGNED 32-bit arithmetic, truncated to 16 bits (Msg.cpp:2746)
+                s16 = (int32_t)(int16_t)(((uint32_t)s16 * cx.attenuation) >> 8);
+            }
+            // (s16 * mult) >> 15 kept to 16 bits == high half of s16 * (2*mult) (Msg.cpp:865)
+            uint32_t v = (uint32_t)(s16 * (int32_t)m[j]);
+            if (B == 4) {
+                // bytes: hi, lo, 00, channel tag on 6-channel audio (Msg.cpp:880-891)
+                uint32_t c = chan0 + j;
+                if (CHM == kChmOther) c = (c >= cx.channels) ? c - cx.channels : c;
+                v = (v & 0xffff0000u) | (cx.tag6 ? (c << 4) : 0u);
+            }
+            o[j] = v;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t v = unit_extract<B>(r, j, cx.in_le);
+            if (B == 2 && cx.attenuation != OHP_UNITY_ATTENUATION) {
+                const uint32_t s = (uint32_t)((int32_t)v >> 16);
+                v = ((s * cx.attenuation) >> 8) << 16;
+            }
+            o[j] = v;
+        }
+    }
+    unit_pack<B>(o, w, cx.out_le, cx.ramped);
+}
+
+__device__ __forceinline__ void load_ctx(const ChunkRec& cr, UnitCtx& cx, RampRegs& rr)
+{
+    cx.channels = cr.channels;
+    cx.ch_magic = cr.ch_magic;
+    cx.attenuation = cr.attenuation;
+    cx.ramped = (cr.mode & kModeRamped) != 0;
+    cx.in_le = (cr.mode & kModeInLe) != 0;
+    cx.out_le = (cr.mode & kModeOutLe) != 0;
+    cx.tag6 = (cr.mode & kModeTag6) != 0;
+    rr.c = cr.ramp_c; rr.sign = cr.ramp_sign; rr.total = cr.ramp_total; rr.magic = cr.ramp_magic; rr.shift = cr.ramp_shift;
+}
+
+// General path: the chunk starts at any byte of the staged span (in_addr + head); one unit per thread per step,
+// word loads realigned with a funnel shift.
+template <int B, uint32_t CHM>
+__device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+{
+    UnitCtx cx;
+    RampRegs rr;
+    rr.table = table;
+    load_ctx(cr, cx, rr);
+    const uint32_t units = cr.units;
     const uint32_t src = in_addr + (cr.head & ~3u);
     const uint32_t fshift = (cr.head & 3u) * 8u;
-    const uint32_t channels = cr.channels;
     for (uint32_t u = t; u < units; u += kConsumerThreads) {
-        // B source words, realigned when the chunk starts off a word boundary
-        uint32_t r[B + 1];
-        {
-            uint32_t raw[B + 1];
-            const uint32_t a = src + u * (4u * B);
+        uint32_t raw[B + 1], r[B + 1], w[B];
+        const uint32_t a = src + u * (4u * B);
 #pragma unroll
-            for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
+        for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
 #pragma unroll
-            for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
-            r[B] = 0;
-        }
-        uint32_t o[4];
-        if (ramped) {
-            // frames of the unit's subsamples and their multipliers
-            uint32_t m[4];
-            uint32_t chan0 = 0;
-            if (CHM == 1) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) m[j] = ramp_mult2(rr, 4u * u + j);
-            } else if (CHM == 2) {
-                m[0] = m[1] = ramp_mult2(rr, 2u * u);
-                m[2] = m[3] = ramp_mult2(rr, 2u * u + 1u);
-            } else if (CHM == 4) {
-                const uint32_t f0 = __umulhi(4u * u, cr.ch_magic);
-                chan0 = 4u * u - f0 * channels;
-                m[0] = m[1] = m[2] = m[3] = ramp_mult2(rr, f0);
-            } else {
-                // channels >= 3, not a multiple of 4: the unit touches frames f0 and possibly f0+1
-                const uint32_t f0 = __umulhi(4u * u, cr.ch_magic);
-                chan0 = 4u * u - f0 * channels;
-                const uint32_t ma = ramp_mult2(rr, f0);
-                const uint32_t mb = ramp_mult2(rr, f0 + 1u);
-#pragma unroll
-                for (int j = 0; j < 4; j++) m[j] = (chan0 + j >= channels) ? mb : ma;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int32_t s16 = unit_s16<B>(r, j, in_le);
-                if (B == 2 && cr.attenuation != OHP_UNITY_ATTENUATION) {
-                    // ((TInt)sample) * iAttenuation / 256 in UNSIGNED 32-bit arithmetic, truncated to 16 bits (Msg.cpp:2746)
-                    s16 = (int32_t)(int16_t)(((uint32_t)s16 * cr.attenuation) >> 8);
-                }
-                // (s16 * mult) >> 15 kept to 16 bits == high half of s16 * (2*mult) (Msg.cpp:865)
-                uint32_t v = (uint32_t)(s16 * (int32_t)m[j]);
-                if (B == 4) {
-                    // bytes: hi, lo, 00, channel tag on 6-channel audio (Msg.cpp:880-891)
-                    uint32_t c = chan0 + j;
-                    if (CHM == 0) c = (c >= channels) ? c - channels : c;
-                    v = (v & 0xffff0000u) | (tag6 ? (c << 4) : 0u);
-                }
-                o[j] = v;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t v = unit_extract<B>(r, j, in_le);
-                if (B == 2 && cr.attenuation != OHP_UNITY_ATTENUATION) {
-                    const uint32_t s = (uint32_t)((int32_t)v >> 16);
-                    v = ((s * cr.attenuation) >> 8) << 16;
-                }
-                o[j] = v;
-            }
-        }
-        uint32_t w[B];
-        unit_pack<B>(o, w, out_le, ramped);
+        for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
+        r[B] = 0;
+        process_unit<B, CHM>(cx, rr, u, r, w);
         const uint32_t d = out_addr + u * (4u * B);
 #pragma unroll
         for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
     }
 }
 
-template <int B>
-__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, const RampRegs& rr, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+// Fast path: source image and destination image both start on a 16-byte boundary of their stage.  Each thread
+// takes groups of four units (16 subsamples = B x 16 bytes) with 128-bit shared-memory loads and stores.
+template <int B, uint32_t CHM>
+__device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
 {
-    const uint32_t ch = cr.channels;
-    if (ch == 2) transform_chunk<B, 2>(cr, rr, in_addr, out_addr, t);
-    else if ((ch & 3u) == 0) transform_chunk<B, 4>(cr, rr, in_addr, out_addr, t);
-    else if (ch == 1) transform_chunk<B, 1>(cr, rr, in_addr, out_addr, t);
-    else transform_chunk<B, 0>(cr, rr, in_addr, out_addr, t);
+    UnitCtx cx;
+    RampRegs rr;
+    rr.table = table;
+    load_ctx(cr, cx, rr);
+    const uint32_t groups = (cr.units + 3u) >> 2;
+    for (uint32_t g = t; g < groups; g += kConsumerThreads) {
+        uint32_t r[4 * B + 1];
+        uint32_t w[4 * B];
+        const uint32_t a = in_addr + g * (16u * B);
+#pragma unroll
+        for (int i = 0; i < B; i++) {
+            const uint4 v = lds128(a + 16u * i);
+            r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        r[4 * B] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t ru[B + 1], wu[B];
+#pragma unroll
+            for (int k = 0; k <= B; k++) ru[k] = r[i * B + k];
+            process_unit<B, CHM>(cx, rr, 4u * g + i, ru, wu);
+#pragma unroll
+            for (int k = 0; k < B; k++) w[i * B + k] = wu[k];
+        }
+        const uint32_t d = out_addr + g * (16u * B);
+#pragma unroll
+        for (int i = 0; i < B; i++) sts128(d + 16u * i, make_uint4(w[4 * i + 0], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+    }
 }
 
-// Verbatim pass-through (Msg.cpp:2782-2784): copy the staged image to the out stage, realigning from
-// (head) to (s_off) byte offsets.  Both are congruent mod 4 only when src == dst mod 4; handle the general case
-// with a funnel shift on whole words.
-__device__ __forceinline__ void copy_chunk(uint32_t in_addr, uint32_t head, uint32_t out_addr, uint32_t bytes, uint32_t t)
+// Verbatim pass-through (Msg.cpp:2782-2784): copy the staged image to the out stage.  The source starts at
+// in_addr + head, the destination at out_addr (4-byte aligned): realign whole words with a funnel shift.
+__device__ __noinline__ void copy_chunk(uint32_t in_addr, uint32_t head, uint32_t out_addr, uint32_t bytes, uint32_t t)
 {
+    if (((head | out_addr) & 15u) == 0) {
+        const uint32_t vecs = (bytes + 15u) >> 4;
+        for (uint32_t v = t; v < vecs; v += kConsumerThreads) sts128(out_addr + 16u * v, lds128(in_addr + 16u * v));
+        return;
+    }
     const uint32_t words = (bytes + 3u) >> 2;
     const uint32_t src = in_addr + (head & ~3u);
     const uint32_t fshift = (head & 3u) * 8u;
@@ -462,6 +524,19 @@ __device__ __forceinline__ void copy_chunk(uint32_t in_addr, uint32_t head, uint
         const uint32_t b = lds32(src + 4u * w + 4u);
         sts32(out_addr + 4u * w, __funnelshift_r(a, b, fshift));
     }
+}
+
+template <int B>
+__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+{
+    const uint32_t chm = (cr.variant >> 2) & 3u;
+    const bool aligned = (cr.variant & 16u) != 0;
+    if (aligned && chm == kChmStereo) transform_aligned<B, kChmStereo>(cr, table, in_addr, out_addr, t);
+    else if (aligned && chm == kChmMul4) transform_aligned<B, kChmMul4>(cr, table, in_addr, out_addr, t);
+    else if (chm == kChmStereo) transform_any<B, kChmStereo>(cr, table, in_addr, out_addr, t);
+    else if (chm == kChmMul4) transform_any<B, kChmMul4>(cr, table, in_addr, out_addr, t);
+    else if (chm == kChmMono) transform_any<B, kChmMono>(cr, table, in_addr, out_addr, t);
+    else transform_any<B, kChmOther>(cr, table, in_addr, out_addr, t);
 }
 
 // ---------------------------------------------------------------------------------------------
