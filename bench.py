@@ -57,12 +57,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+def recorded_traffic(workload_name, algo_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture of a slice of
+    the same workload (profiles/traffic.json), scaled to this launch by algorithmic bytes.  None when no capture exists."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload_name)
+            rec = json.load(open(p)).get(workload_name)
+            if rec:
+                return rec["capture_dram_bytes"] / rec["capture_algorithmic_bytes"] * algo_bytes
         except Exception:
             return None
     return None
@@ -352,7 +355,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                "traffic": recorded_traffic(args.workload, algo_bytes), "peak_source": peak_src,
                 "kernel": "ohp::ramp_convert_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_ms": ms_per_step}
 
