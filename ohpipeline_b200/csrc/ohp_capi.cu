@@ -98,7 +98,8 @@ __device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uin
 #define OHP_FLUSH(slot, var) (void)0
 #endif
 
-// Persistent, warp-specialised CTAs (see ohp_kernels.cuh): CTA b handles chunks b, b+grid, b+2*grid, ...
+// Persistent, warp-specialised CTAs (see ohp_kernels.cuh): chunks are dealt block-cyclically to the CTAs; inside the
+// CTA the chunk with ordinal k belongs to consumer warp k % kConsumerWarps and to ring slot k % kRingSlots.
 __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -107,37 +108,38 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     const uint32_t lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kInStages; s++) {
-            mbar_init(smem_u32(&sm.full_in[s]), 1);
-            mbar_init(smem_u32(&sm.empty_in[s]), kConsumerWarps);
-        }
-        for (int s = 0; s < kOutStages; s++) {
-            mbar_init(smem_u32(&sm.full_out[s]), kConsumerWarps);
-            mbar_init(smem_u32(&sm.empty_out[s]), 1);
+        for (uint32_t s = 0; s < kRingSlots; s++) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), 1);
         }
         fence_mbar_init();
     }
     for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) sm.table2[i] = p.table2[i];
     __syncthreads();
 
-    long long w_loader = 0, w_storer = 0, w_full = 0, w_out = 0;
-    (void)w_loader; (void)w_storer; (void)w_full; (void)w_out;
+    [[maybe_unused]] long long w_loader = 0, w_full = 0, w_store = 0, w_xform = 0, w_fence = 0, w_issue = 0;
 #ifdef OHP_PROFILE_WAITS
     const long long t_begin = clock64();
 #endif
+    // chunks of this CTA: ordinal k <-> chunk cta_chunk_index(k)
+    const uint64_t my_n = cta_chunk_count(p.n, blockIdx.x, gridDim.x);
+    const uint32_t ring = smem_u32(&sm.ring[0]);
+
     if (warp == 0) {
         // ------------------------------------------------------------------ loader
-        // chunks of this CTA: ordinal k <-> chunk blockIdx.x + k * gridDim.x
-        const uint64_t my_n = blockIdx.x < p.n ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const uint4* dp = reinterpret_cast<const uint4*>(p.descs);
+        uint32_t wr = 0;              // next free byte of the ring
+        uint32_t free_bytes = kRingBytes;
+        uint64_t rd = 0;              // oldest chunk whose slot has not been reclaimed yet
         for (uint64_t base = 0; base < my_n; base += 32) {
-            // all lanes: decode 32 descriptors into the record table (the half the consumers are done with)
+            // all lanes: decode 32 descriptors into the record table (the half the consumers are done with:
+            // at most kRingSlots <= 32 chunks are ever in flight)
             const uint64_t k = base + lane;
             ChunkRec r;
             r.kind = kSkip;
             uint64_t src_al = 0;
             if (k < my_n) {
-                const uint64_t c = blockIdx.x + k * gridDim.x;
+                const uint64_t c = cta_chunk_index(k, blockIdx.x, gridDim.x);
                 const uint4 d0 = __ldg(dp + 2 * c);
                 const uint4 d1 = __ldg(dp + 2 * c + 1);
                 uint64_t src_off;
@@ -145,36 +147,55 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 if (err) report(p, err, c);
                 src_al = reinterpret_cast<uint64_t>(p.in) + src_off - r.head;
             }
-            const uint32_t slot = (uint32_t)(k & (kRecSlots - 1));
-            sm.rec[slot] = r;
-            sm.load_src[slot] = src_al;
+            const uint32_t rslot = (uint32_t)(k & (kRecSlots - 1));
+            sm.rec[rslot] = r;
+            sm.load_src[rslot] = src_al;
             __syncwarp();
-            // one lane: feed the ring in order
+            // one lane: carve slots out of the ring and start the loads, in order
             if (lane == 0) {
                 const uint32_t count = (uint32_t)(my_n - base < 32 ? my_n - base : 32);
                 for (uint32_t j = 0; j < count; j++) {
                     const uint64_t it = base + j;
-                    const uint32_t s = (uint32_t)(it % kInStages);
-                    const uint32_t ph = (uint32_t)(it / kInStages) & 1u;
                     const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
-                    OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty_in[s]), ph ^ 1u, p.status));
-                    const uint32_t full = smem_u32(&sm.full_in[s]);
-                    if (sm.rec[sl].kind == kPcm) {
+                    const uint32_t bs = (uint32_t)(it & (kRingSlots - 1));
+                    const bool pcm = sm.rec[sl].kind == kPcm;
+                    uint32_t span = 0, need = 0;
+                    if (pcm) {
+                        span = (sm.rec[sl].head + sm.rec[sl].bytes + 15u) & ~15u;
+                        need = kSlotFront + span + kSlotBack;
+                    }
+                    uint32_t waste = 0;
+                    const bool wrap = wr + need > kRingBytes;           // the slot must be contiguous: skip the end of the ring
+                    if (wrap) waste = kRingBytes - wr;
+                    // reclaim, oldest first, until the slot fits and its barrier pair is free
+                    while (free_bytes < need + waste || it - rd >= kRingSlots) {
+                        const uint32_t os = (uint32_t)(rd & (kRingSlots - 1));
+                        OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[os]), (uint32_t)(rd / kRingSlots) & 1u, p.status));
+                        free_bytes += sm.slot_bytes[os];
+                        rd++;
+                    }
+                    if (wrap) wr = 0;
+                    sm.slot_bytes[bs] = need + waste;
+                    free_bytes -= need + waste;
+                    sm.ring_off[sl] = wr;
+                    const uint32_t full = smem_u32(&sm.full[bs]);
+                    if (pcm) {
                         const uint8_t* al = reinterpret_cast<const uint8_t*>(sm.load_src[sl]);
-                        uint32_t span = (sm.rec[sl].head + sm.rec[sl].bytes + 15u) & ~15u;
+                        const uint32_t dst_smem = ring + wr + kSlotFront;
                         const uint64_t room = (uint64_t)(p.in + p.in_bytes - al);
                         if (span > room) {
                             // last 16-byte word of the arena is partial: fetch its bytes one by one
                             const uint32_t whole = (uint32_t)(room & ~15ull);
-                            for (uint32_t i = whole; i < (uint32_t)room; i++) sm.in_stage[s][i] = al[i];
+                            for (uint32_t i = whole; i < (uint32_t)room; i++) sm.ring[wr + kSlotFront + i] = al[i];
                             span = whole;
                         }
                         if (span != 0) {
                             mbar_arrive_expect_tx(full, span);
-                            tma_load(smem_u32(&sm.in_stage[s][0]), al, span, full);
+                            tma_load(dst_smem, al, span, full);
                         } else {
                             mbar_arrive(full);
                         }
+                        wr += need;
                     } else {
                         mbar_arrive(full);
                     }
@@ -188,76 +209,79 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
             atomicAdd(&p.status[8], (uint32_t)((clock64() - t_begin) >> 12));
 #endif
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ storer
-        // Every chunk, whatever its kind, passes through one out-ring slot, so the storer walks the same sequence as
-        // the consumers.  It reads the loader's record of the chunk after the consumers have signalled it (that is
-        // the ordering edge; the record table outlives the few chunks the storer can lag behind).
-        const uint64_t my_n = blockIdx.x < p.n ? (p.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        for (uint64_t it = 0; it < my_n; it++) {
-            const uint32_t o = (uint32_t)(it % kOutStages);
-            const uint32_t ph = (uint32_t)(it / kOutStages) & 1u;
-            OHP_ACC(w_storer, mbar_wait(smem_u32(&sm.full_out[o]), ph, p.status));
-            const ChunkRec& cr = sm.rec[it & (kRecSlots - 1)];
-            if (cr.kind == kPcm) {
-                uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
-                store_image_warp(smem_u32(&sm.out_stage[o][0]) + (cr.dst_lo & 12u), dst, cr.bytes, lane);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                tma_commit(); // possibly an empty group
-                // hand the stage back as soon as the bulk store has finished READING it (the global writes may still
-                // be in flight); meanwhile the consumers fill the other stage(s)
-                tma_wait_read<0>();
-                mbar_arrive(smem_u32(&sm.empty_out[o]));
-            }
-            __syncwarp();
-        }
-        if (lane == 0) {
-            tma_wait_all<0>(); // all bulk stores complete before the CTA (and its shared memory) goes away
-            OHP_FLUSH(7, w_storer);
-        }
     } else {
-        // ------------------------------------------------------------------ consumers
-        const uint32_t t = threadIdx.x - 64;
+        // ------------------------------------------------------------------ consumers: one warp per chunk
+        const uint32_t cw = warp - 1;
         const uint32_t table = smem_u32(&sm.table2[0]);
-        uint32_t it = 0;
-        for (uint64_t c = blockIdx.x; c < p.n; c += gridDim.x, it++) {
-            const uint32_t s = it % kInStages;
-            const uint32_t ph = (it / kInStages) & 1u;
-            const uint32_t o = it % kOutStages;
-            const uint32_t oph = (it / kOutStages) & 1u;
-            OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full_in[s]), ph, p.status));
-            OHP_ACC(w_out, mbar_wait(smem_u32(&sm.empty_out[o]), oph ^ 1u, p.status));
-            const ChunkRec& cr = sm.rec[it & (kRecSlots - 1)];
+        for (uint64_t it = cw; it < my_n; it += kConsumerWarps) {
+            const uint32_t bs = (uint32_t)(it & (kRingSlots - 1));
+            const uint32_t ph = (uint32_t)(it / kRingSlots) & 1u;
+            OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
+            const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
+            const ChunkRec& cr = sm.rec[sl];
             const uint32_t kind = cr.kind;
             if (kind == kPcm) {
-                const uint32_t in_addr = smem_u32(&sm.in_stage[s][0]);
-                const uint32_t out_addr = smem_u32(&sm.out_stage[o][0]) + (cr.dst_lo & 12u);
+                uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
+                const uint32_t head = cr.head;
+                const uint32_t in_addr = ring + sm.ring_off[sl] + kSlotFront;          // 16-byte aligned; image at +head
+                // the output image goes where it is congruent to the destination mod 16, at or just below the input
+                const uint32_t image = in_addr + head - ((head - cr.dst_lo) & 15u);
+                const uint32_t out_addr = image & ~3u;                                 // word stores; == image unless dst is odd
+#ifdef OHP_PROFILE_WAITS
+                const long long tx0 = clock64();
+#endif
                 if (cr.mode & kModeTransform) {
                     switch (cr.variant & 3u) {
-                    case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, t); break;
-                    case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, t); break;
-                    case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, t); break;
-                    default: transform_dispatch<4>(cr, table, in_addr, out_addr, t); break;
+                    case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, lane); break;
+                    case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, lane); break;
+                    case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, lane); break;
+                    default: transform_dispatch<4>(cr, table, in_addr, out_addr, lane); break;
                     }
-                } else {
-                    copy_chunk(in_addr, cr.head, out_addr, cr.bytes, t);
+                } else if (out_addr != in_addr + head) {
+                    shift_chunk(in_addr, head, out_addr, cr.bytes, lane);
                 }
-                fence_proxy_async(); // this thread's shared-memory writes -> visible to the TMA store
-            } else if (kind == kSilence) {
-                uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
-                write_silence(dst, cr.bytes, cr.channels, (cr.variant & 3u) + 1u, t);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(smem_u32(&sm.full_out[o]));
-                mbar_arrive(smem_u32(&sm.empty_in[s]));
+#ifdef OHP_PROFILE_WAITS
+                const long long tx1 = clock64();
+                w_xform += tx1 - tx0;
+#endif
+                fence_proxy_async(); // this lane's shared-memory writes -> visible to the TMA store
+                __syncwarp();
+#ifdef OHP_PROFILE_WAITS
+                const long long tx2 = clock64();
+                w_fence += tx2 - tx1;
+#endif
+                // image == out_addr: TMA bulk store of the aligned interior; otherwise (destination not 4-byte aligned)
+                // the image sits (dst & 3) bytes above out_addr... it does not: the transform wrote the image AT out_addr,
+                // and store_image_warp realigns through registers because out_addr and dst then disagree mod 16.
+                store_image_warp(out_addr, dst, cr.bytes, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    tma_commit();
+#ifdef OHP_PROFILE_WAITS
+                    const long long ts = clock64();
+                    w_issue += ts - tx2;
+#endif
+#ifndef OHP_EXPERIMENT_NO_STORE_WAIT /* timing experiment only: releasing early is a data race */
+                    tma_wait_read<0>(); // the slot can be reused once the bulk store has READ it
+#endif
+#ifdef OHP_PROFILE_WAITS
+                    w_store += clock64() - ts;
+#endif
+                    mbar_arrive(smem_u32(&sm.empty[bs]));
+                }
+                __syncwarp();
+            } else {
+                if (kind == kSilence) {
+                    uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
+                    write_silence(dst, cr.bytes, cr.channels, (cr.variant & 3u) + 1u, lane);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs]));
             }
         }
-        if (t == 0) {
-            OHP_FLUSH(5, w_full);
-            OHP_FLUSH(6, w_out);
+        if (lane == 0) {
+            tma_wait_all<0>(); // every bulk store complete before the CTA (and its shared memory) goes away
+            if (cw == 0) { OHP_FLUSH(5, w_full); OHP_FLUSH(6, w_store); OHP_FLUSH(9, w_xform); OHP_FLUSH(10, w_fence); OHP_FLUSH(11, w_issue); }
         }
     }
 }
@@ -394,7 +418,8 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
     p.table2 = ctx->d_table2;
     p.status = ctx->d_status;
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctx->ctas_per_sm;
-    if (grid > n) grid = n;
+    const uint64_t blocks = (n + kChunkBlock - 1) / kChunkBlock; // chunks are dealt kChunkBlock at a time
+    if (grid > blocks) grid = blocks;
     if (ctx->timing) OHP_CUDA(ctx, cudaEventRecord(ctx->ev_start, st));
     ramp_convert_kernel<<<(unsigned)grid, kThreads, sizeof(SharedStorage), st>>>(p);
     OHP_CUDA(ctx, cudaGetLastError());

@@ -4,24 +4,28 @@
 //
 //   loader  (warp 0)            walks this CTA's chunks: its 32 lanes fetch and decode 32 descriptors at a time
 //                               (restating the reference's ASSERTs and precomputing the per-chunk ramp constants),
-//                               then one lane pulls, chunk by chunk, the 16-byte-aligned span that covers the
-//                               chunk's source bytes into a shared-memory ring with ONE TMA bulk copy
-//                               (cp.async.bulk.shared::cluster.global, completion on an mbarrier);
-//   consumers (kConsumerWarps)  wait on the ring's "full" mbarrier and transform "units" of four subsamples held in
-//                               registers: unpack (BE or LE wire order -- DecodedAudio::CopyToBigEndian*,
+//                               then one lane carves, chunk by chunk, a slot out of a shared-memory BYTE RING and
+//                               pulls the 16-byte-aligned span that covers the chunk's source bytes into it with ONE
+//                               TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on an mbarrier);
+//   consumers (kConsumerWarps)  each warp owns every kConsumerWarps-th chunk from start to finish: it waits on the
+//                               slot's "full" mbarrier, transforms the chunk IN PLACE in "units" of four subsamples
+//                               held in registers -- unpack (BE or LE wire order: DecodedAudio::CopyToBigEndian*,
 //                               Msg.cpp:380-408), attenuate (MsgPlayablePcm::ApplyAttenuation, Msg.cpp:2736-2751),
-//                               ramp (RampApplicator::GetNextSample, Msg.cpp:832-899) and repack for the
-//                               IPcmProcessor sink (packed BE / packed LE); byte shuffles are PRMT, the ramp is one
-//                               IMAD per subsample; results go to a second shared-memory ring;
-//   storer  (warp 1)            drains that ring: the 16-byte-aligned interior of the destination with ONE TMA bulk
-//                               store (cp.async.bulk.global.shared::cta), the ragged head/tail (chunks start at
-//                               arbitrary byte offsets: a 24-bit stereo frame is 6 bytes, a split playable starts
-//                               wherever the ramp ended) with byte stores.
+//                               ramp (RampApplicator::GetNextSample, Msg.cpp:832-899), repack for the IPcmProcessor
+//                               sink (packed BE / packed LE); byte shuffles are PRMT, the ramp one IMAD per subsample
+//                               -- then writes it out itself: the 16-byte-aligned interior of the destination with
+//                               ONE TMA bulk store (cp.async.bulk.global.shared::cta), the ragged head/tail (chunks
+//                               start at arbitrary byte offsets: a 24-bit stereo frame is 6 bytes, a split playable
+//                               starts wherever the ramp ended) with byte stores, and hands the slot back.
+//
+// In place means a chunk in flight costs one buffer, not two, so the 227 KB of an SM hold twice as many chunks between
+// "load issued" and "store drained" -- that, not arithmetic, is what bounds an HBM-bound kernel.  A warp per chunk means
+// no cross-warp synchronisation on the data path and one setup per chunk.
 //
 // The 512-entry ramp curve sits in shared memory as 2*multiplier, so that the high half of the 16x16 product is
 // the reference's (s16 * mult) >> 15; the per-frame ramp position trunc(i*total/(N-1)) is an exact multiply-high by
 // a per-chunk magic reciprocal instead of the reference's per-frame integer divide.  Silence chunks
-// (MsgPlayableSilence::ReadBlock, Msg.cpp:2874-2893) are written straight to global memory by the consumers.
+// (MsgPlayableSilence::ReadBlock, Msg.cpp:2874-2893) are written straight to global memory by their consumer warp.
 //
 // Everything is integer; results are bit-exact against the reference (see oracle/).
 #pragma once
@@ -37,24 +41,30 @@ namespace ohp {
 #ifndef OHP_CONSUMER_WARPS
 #define OHP_CONSUMER_WARPS 4
 #endif
-#ifndef OHP_IN_STAGES
-#define OHP_IN_STAGES 3
+#ifndef OHP_RING_BYTES
+#define OHP_RING_BYTES 47104
 #endif
-#ifndef OHP_OUT_STAGES
-#define OHP_OUT_STAGES 2
+#ifndef OHP_RING_SLOTS
+#define OHP_RING_SLOTS 16
 #endif
-#ifndef OHP_STAGE_CHUNK
-#define OHP_STAGE_CHUNK OHP_MAX_PCM_CHUNK_BYTES  /* experiments only: smaller stages cannot hold every legal chunk */
+#ifndef OHP_CHUNK_BLOCK
+#define OHP_CHUNK_BLOCK 16
 #endif
+#ifndef OHP_GROUPS_PER_STEP
+#define OHP_GROUPS_PER_STEP 1
+#endif
+constexpr int kGroupsPerStep = OHP_GROUPS_PER_STEP; // independent 16-subsample groups a lane works on at once
+constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of this many consecutive chunks
 constexpr int kConsumerWarps = OHP_CONSUMER_WARPS;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = 64 + kConsumerThreads;   // loader warp + storer warp + consumers
-constexpr int kInStages = OHP_IN_STAGES;
-constexpr int kOutStages = OHP_OUT_STAGES;
-constexpr int kRecSlots = 64;                     // two batches of 32 decoded chunk records
+constexpr int kThreads = 32 + kConsumerWarps * 32; // loader warp + consumer warps
+constexpr int kRecSlots = 64;                      // two batches of 32 decoded chunk records
+constexpr uint32_t kRingSlots = OHP_RING_SLOTS;    // chunks in flight per CTA (barrier pairs); <= 32
+constexpr uint32_t kRingBytes = OHP_RING_BYTES;    // shared-memory byte ring the chunk slots are carved from
 constexpr uint32_t kMaxChunk = OHP_MAX_PCM_CHUNK_BYTES;
-constexpr uint32_t kInStageBytes = OHP_STAGE_CHUNK + 80;   // aligned span (<= 15 + 9216, rounded up to 16) + over-read of the last 16-subsample group
-constexpr uint32_t kOutStageBytes = OHP_STAGE_CHUNK + 80;  // image at offset (dst & 12) + over-write of the last 16-subsample group
+constexpr uint32_t kSlotFront = 16;                // the output image may start up to 15 bytes before the input image
+constexpr uint32_t kSlotBack = 80;                 // over-read / over-write of the last 16-subsample group + funnel word
+static_assert(kRingBytes % 16 == 0 && kRingBytes >= 2 * (kSlotFront + kMaxChunk + 16 + kSlotBack), "ring too small");
+static_assert(kRingSlots <= 32 && (kRingSlots & (kRingSlots - 1)) == 0, "ring slots: power of two, at most one decode batch");
 
 // device status word bits (OR-ed by the kernel, read back by ohp_sync)
 constexpr uint32_t kErrInvalidDesc = 1u;
@@ -103,16 +113,33 @@ constexpr uint32_t kChmOther = 0u, kChmMono = 1u, kChmStereo = 2u, kChmMul4 = 3u
 
 struct __align__(128) SharedStorage
 {
-    uint8_t in_stage[kInStages][kInStageBytes];
-    uint8_t out_stage[kOutStages][kOutStageBytes];
+    uint8_t ring[kRingBytes];
     ChunkRec rec[kRecSlots];          // indexed by (chunk ordinal & (kRecSlots-1)); decoded 32 at a time
     uint64_t load_src[kRecSlots];     // loader's own notes: 16-byte aligned source of the chunk's span
+    uint32_t ring_off[kRecSlots];     // where the chunk's slot starts in the ring (written when the load is issued)
+    uint32_t slot_bytes[kRingSlots];  // loader's own notes: bytes to reclaim when the slot is released
     uint16_t table2[OHP_RAMP_TABLE_ENTRIES];
-    uint64_t full_in[kInStages];
-    uint64_t empty_in[kInStages];
-    uint64_t full_out[kOutStages];
-    uint64_t empty_out[kOutStages];
+    uint64_t full[kRingSlots];
+    uint64_t empty[kRingSlots];
 };
+
+// Work distribution: chunks are dealt to the CTAs block-cyclically, kChunkBlock consecutive chunks at a time, so that
+// the chunks one CTA has in flight are neighbours in HBM (its loads and stores walk DRAM pages instead of hopping
+// grid * chunk bytes apart) while the grid as a whole still sweeps one narrow window of the arenas.
+__device__ __forceinline__ uint64_t cta_chunk_count(uint64_t n, uint32_t cta, uint32_t grid)
+{
+    const uint64_t round = (uint64_t)grid * kChunkBlock;
+    const uint64_t full = n / round;
+    const uint64_t rem = n - full * round;
+    const uint64_t mine = (uint64_t)cta * kChunkBlock;
+    const uint64_t extra = rem > mine ? (rem - mine < kChunkBlock ? rem - mine : kChunkBlock) : 0;
+    return full * kChunkBlock + extra;
+}
+// chunk index of this CTA's k-th chunk
+__device__ __forceinline__ uint64_t cta_chunk_index(uint64_t k, uint32_t cta, uint32_t grid)
+{
+    return ((k / kChunkBlock) * grid + cta) * kChunkBlock + (k % kChunkBlock);
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (mbarrier, TMA bulk copies, shared-memory accesses by 32-bit address)
@@ -162,17 +189,34 @@ __device__ __forceinline__ long long mbar_wait(uint32_t bar, uint32_t parity, ui
     }
     return clock64() - t0; // cycles spent blocked (used by the OHP_PROFILE_WAITS instrumentation only)
 }
+// L2 eviction policy for data that is touched exactly once (both arenas stream through)
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 // global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void tma_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
 {
+#ifdef OHP_L2_HINT_LOAD
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(l2_evict_first_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+#endif
 }
 // shared -> global bulk copy (TMA), tracked by bulk async-groups.
 __device__ __forceinline__ void tma_store(void* dst, uint32_t src_smem, uint32_t bytes)
 {
+#ifdef OHP_L2_HINT_STORE
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(dst), "r"(src_smem), "r"(bytes), "l"(l2_evict_first_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_commit()
 {
@@ -447,8 +491,10 @@ __device__ __forceinline__ void load_ctx(const ChunkRec& cr, UnitCtx& cx, RampRe
 
 // General path: the chunk starts at any byte of the staged span (in_addr + head); one unit per thread per step,
 // word loads realigned with a funnel shift.
+// In place: the output image starts at out_addr <= the input image (in_addr + head), so a warp step's stores never
+// reach bytes a LATER step still has to read; inside a step every lane loads before any lane stores (__syncwarp).
 template <int B, uint32_t CHM>
-__device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+__device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t lane)
 {
     UnitCtx cx;
     RampRegs rr;
@@ -457,23 +503,32 @@ __device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, u
     const uint32_t units = cr.units;
     const uint32_t src = in_addr + (cr.head & ~3u);
     const uint32_t fshift = (cr.head & 3u) * 8u;
-    for (uint32_t u = t; u < units; u += kConsumerThreads) {
+    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
+        const uint32_t u = u0 + lane;
         uint32_t raw[B + 1], r[B + 1], w[B];
         const uint32_t a = src + u * (4u * B);
+        if (u < units) {
 #pragma unroll
-        for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
+            for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
+        } else {
+#pragma unroll
+            for (int i = 0; i <= B; i++) raw[i] = 0;
+        }
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
         r[B] = 0;
         process_unit<B, CHM>(cx, rr, u, r, w);
-        const uint32_t d = out_addr + u * (4u * B);
+        if (u < units) {
+            const uint32_t d = out_addr + u * (4u * B);
 #pragma unroll
-        for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
+            for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
+        }
     }
 }
 
-// Fast path: source image and destination image both start on a 16-byte boundary of their stage.  Each thread
-// takes groups of four units (16 subsamples = B x 16 bytes) with 128-bit shared-memory loads and stores.
+// Fast path: the image starts on a 16-byte boundary and the output goes back to the same bytes.  Each lane takes
+// groups of four units (16 subsamples = B x 16 bytes) with 128-bit shared-memory loads and stores.
 template <int B, uint32_t CHM>
 __device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
 {
@@ -482,47 +537,67 @@ __device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t tabl
     rr.table = table;
     load_ctx(cr, cx, rr);
     const uint32_t groups = (cr.units + 3u) >> 2;
-    for (uint32_t g = t; g < groups; g += kConsumerThreads) {
-        uint32_t r[4 * B + 1];
-        uint32_t w[4 * B];
-        const uint32_t a = in_addr + g * (16u * B);
+    // kGroupsPerStep independent groups per lane per step: one basic block, so their dependency chains interleave
+    // (a lone warp per chunk has no other warp to hide LDS / IMAD latency behind)
+    for (uint32_t gb = 0; gb < groups; gb += 32u * kGroupsPerStep) { // warp-uniform trip count (the step synchronises the warp)
+        const uint32_t g0 = gb + t;
+        uint32_t r[kGroupsPerStep][4 * B + 1];
+        uint32_t w[kGroupsPerStep][4 * B];
 #pragma unroll
-        for (int i = 0; i < B; i++) {
-            const uint4 v = lds128(a + 16u * i);
-            r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        for (int s = 0; s < kGroupsPerStep; s++) {
+            const uint32_t g = min(g0 + 32u * s, groups - 1u); // clamp: the surplus copy recomputes the last group, unstored
+            const uint32_t a = in_addr + g * (16u * B);
+#pragma unroll
+            for (int i = 0; i < B; i++) {
+                const uint4 v = lds128(a + 16u * i);
+                r[s][4 * i + 0] = v.x; r[s][4 * i + 1] = v.y; r[s][4 * i + 2] = v.z; r[s][4 * i + 3] = v.w;
+            }
+            r[s][4 * B] = 0;
         }
-        r[4 * B] = 0;
+        __syncwarp(); // (clamped lanes re-read a group another lane is about to overwrite in place)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t ru[B + 1], wu[B];
+        for (int s = 0; s < kGroupsPerStep; s++) {
+            const uint32_t g = min(g0 + 32u * s, groups - 1u);
 #pragma unroll
-            for (int k = 0; k <= B; k++) ru[k] = r[i * B + k];
-            process_unit<B, CHM>(cx, rr, 4u * g + i, ru, wu);
+            for (int i = 0; i < 4; i++) {
+                uint32_t ru[B + 1], wu[B];
 #pragma unroll
-            for (int k = 0; k < B; k++) w[i * B + k] = wu[k];
+                for (int k = 0; k <= B; k++) ru[k] = r[s][i * B + k];
+                process_unit<B, CHM>(cx, rr, 4u * g + i, ru, wu);
+#pragma unroll
+                for (int k = 0; k < B; k++) w[s][i * B + k] = wu[k];
+            }
         }
-        const uint32_t d = out_addr + g * (16u * B);
 #pragma unroll
-        for (int i = 0; i < B; i++) sts128(d + 16u * i, make_uint4(w[4 * i + 0], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+        for (int s = 0; s < kGroupsPerStep; s++) {
+            const uint32_t g = g0 + 32u * s;
+            if (g < groups) {
+                const uint32_t d = out_addr + g * (16u * B);
+#pragma unroll
+                for (int i = 0; i < B; i++) {
+                    sts128(d + 16u * i, make_uint4(w[s][4 * i + 0], w[s][4 * i + 1], w[s][4 * i + 2], w[s][4 * i + 3]));
+                }
+            }
+        }
     }
 }
 
-// Verbatim pass-through (Msg.cpp:2782-2784): copy the staged image to the out stage.  The source starts at
-// in_addr + head, the destination at out_addr (4-byte aligned): realign whole words with a funnel shift.
-__device__ __noinline__ void copy_chunk(uint32_t in_addr, uint32_t head, uint32_t out_addr, uint32_t bytes, uint32_t t)
+// Verbatim pass-through (Msg.cpp:2782-2784) when source and destination disagree mod 16: slide the image down from
+// in_addr + head to out_addr (4-byte aligned, <= in_addr + head), whole words realigned with a funnel shift.
+__device__ __noinline__ void shift_chunk(uint32_t in_addr, uint32_t head, uint32_t out_addr, uint32_t bytes, uint32_t lane)
 {
-    if (((head | out_addr) & 15u) == 0) {
-        const uint32_t vecs = (bytes + 15u) >> 4;
-        for (uint32_t v = t; v < vecs; v += kConsumerThreads) sts128(out_addr + 16u * v, lds128(in_addr + 16u * v));
-        return;
-    }
     const uint32_t words = (bytes + 3u) >> 2;
     const uint32_t src = in_addr + (head & ~3u);
     const uint32_t fshift = (head & 3u) * 8u;
-    for (uint32_t w = t; w < words; w += kConsumerThreads) {
-        const uint32_t a = lds32(src + 4u * w);
-        const uint32_t b = lds32(src + 4u * w + 4u);
-        sts32(out_addr + 4u * w, __funnelshift_r(a, b, fshift));
+    for (uint32_t w0 = 0; w0 < words; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        uint32_t a = 0, b = 0;
+        if (w < words) {
+            a = lds32(src + 4u * w);
+            b = lds32(src + 4u * w + 4u);
+        }
+        __syncwarp();
+        if (w < words) sts32(out_addr + 4u * w, __funnelshift_r(a, b, fshift));
     }
 }
 
@@ -583,7 +658,7 @@ __device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, 
 
 // MsgPlayableSilence::ReadBlock (Msg.cpp:2874-2893): zeros; with 6 channels every emitted block of
 // maxBytes starts with 00 00 00 c0 for c0 = 0x00,0x10..0x70 (32 bytes, whatever the bit depth).
-// Written straight to global memory by the consumer threads (t = 0..kConsumerThreads-1).
+// Written straight to global memory by the chunk's consumer warp (t = lane).
 __device__ __forceinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint32_t channels, uint32_t B, uint32_t t)
 {
     const uint32_t block = kMaxChunk - (kMaxChunk % (channels * B));
@@ -597,12 +672,12 @@ __device__ __forceinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint
         return (r < 32u && (r & 3u) == 3u) ? ((r >> 2) << 4) : 0u;
     };
     if (t < head_n) dst[t] = (uint8_t)value_at(t);
-    if (t >= 32 && t - 32 < bytes - tail_at) {
-        const uint32_t i = tail_at + t - 32;
+    if (t < bytes - tail_at) {
+        const uint32_t i = tail_at + t;
         dst[i] = (uint8_t)value_at(i);
     }
     uint4* d4 = reinterpret_cast<uint4*>(dst + head_n);
-    for (uint32_t w = t; w < words; w += kConsumerThreads) {
+    for (uint32_t w = t; w < words; w += 32) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (channels == 6) {
             const uint32_t i0 = head_n + 16u * w;

@@ -45,6 +45,10 @@ L.ohp_debug_counters(ctx._h, buf)
 v = [buf[i] * 4096.0 for i in range(16)]
 life = v[8]
 print("%s: kernel %.3f ms, %d chunks; CTA-lifetime cycles summed over CTAs: %.3g" % (w.name, ev0.elapsed_time(ev1), len(sched.chunks), life))
-for label, i in (("loader blocked on empty_in (ring full)", 4), ("consumer blocked on full_in (waiting for data)", 5),
-                 ("consumer blocked on empty_out (waiting for storer)", 6), ("storer blocked on full_out (idle)", 7)):
-    print("  %-52s %5.1f%% of CTA lifetime" % (label, 100.0 * v[i] / max(life, 1)))
+for label, i in (("loader blocked: ring full, waiting for a slot to be released", 4),
+                 ("consumer warp 0 blocked: waiting for its chunk's data", 5),
+                 ("consumer warp 0 blocked: waiting for its bulk store to finish reading the slot", 6),
+                 ("consumer warp 0: transform (or shift) of the chunk", 9),
+                 ("consumer warp 0: fence.proxy.async + __syncwarp", 10),
+                 ("consumer warp 0: issuing the store (ragged bytes + TMA)", 11)):
+    print("  %-82s %5.1f%% of CTA lifetime" % (label, 100.0 * v[i] / max(life, 1)))
