@@ -25,59 +25,52 @@ __constant__ uint32_t c_ch_magic[33]; // ceil(2^32 / ch); [0],[1] = 0 (mono divi
 __device__ __forceinline__ uint32_t decode_chunk(const KernelParams& p, const uint4& d0, const uint4& d1, ChunkRec& r,
                                                  uint64_t& src_off)
 {
-    src_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
-    const uint64_t dst_off = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
-    const uint32_t bytes = d1.x;
-    const uint32_t ramp_start = d1.y & 0xffffu;
-    const uint32_t ramp_end = d1.y >> 16;
-    const uint32_t attenuation = d1.z & 0xffffu;
-    const uint32_t bit_depth = (d1.z >> 16) & 0xffu;
-    const uint32_t channels = d1.z >> 24;
-    const uint32_t flags = d1.w & 0xffu;
-    const uint32_t out_fmt = (d1.w >> 8) & 0xffu;
-    const bool silence = (flags & OHP_F_SILENCE) != 0;
-    const uint32_t B = bit_depth >> 3;
-
+    DescFields d;
+    d.src_off = src_off = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
+    d.dst_off = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+    d.bytes = d1.x;
+    d.ramp_start = d1.y & 0xffffu;
+    d.ramp_end = d1.y >> 16;
+    d.attenuation = d1.z & 0xffffu;
+    d.bit_depth = (d1.z >> 16) & 0xffu;
+    d.channels = d1.z >> 24;
+    d.flags = d1.w & 0xffu;
+    d.out_fmt = (d1.w >> 8) & 0xffu;
+    d.aux = d1.w >> 16;
     r.kind = kSkip;
-    bool ok = (bit_depth == 8 || bit_depth == 16 || bit_depth == 24 || bit_depth == 32)
-           && channels >= 1 && channels <= 32
-           && ramp_start <= OHP_RAMP_MAX && ramp_end <= OHP_RAMP_MAX
-           && (out_fmt == OHP_OUT_PACKED_BE || out_fmt == OHP_OUT_PACKED_LE);
-    uint32_t frames = 0;
-    if (ok) {
-        frames = bytes / (B * channels);
-        ok = frames * (B * channels) == bytes
-          && (silence || bytes <= kMaxChunk)
-          && (silence || attenuation == OHP_UNITY_ATTENUATION || bit_depth == 16)  // Msg.cpp:2741
-          && (out_fmt != OHP_OUT_PACKED_LE || (!silence && B <= 3));                // TestCodecInteractiveMain.cpp:546-567
-    }
-    if (!ok) return kErrInvalidDesc;
-    if (dst_off > p.out_bytes || bytes > p.out_bytes - dst_off
-        || (!silence && (src_off > p.in_bytes || bytes > p.in_bytes - src_off))) {
-        return kErrOutOfRange;
-    }
-    if (bytes == 0) return 0; // MsgPlayable::Read only calls ReadBlock when iSize > 0 (Msg.cpp:2649)
+    DescDerived dv;
+    const uint32_t err = check_desc_fields(d, p.in_bytes, p.out_bytes, dv);
+    if (err) return err == 1u ? kErrInvalidDesc : kErrOutOfRange;
+    if (d.bytes == 0) return 0; // MsgPlayable::Read only calls ReadBlock when iSize > 0 (Msg.cpp:2649)
 
-    const uint64_t dst = reinterpret_cast<uint64_t>(p.out) + dst_off;
-    r.kind = silence ? kSilence : kPcm;
-    r.bytes = bytes;
-    r.head = (uint32_t)((reinterpret_cast<uint64_t>(p.in) + src_off) & 15u);
+    const bool silence = (d.flags & OHP_F_SILENCE) != 0;
+    const bool packed = d.out_fmt == OHP_OUT_PACKED_BE || d.out_fmt == OHP_OUT_PACKED_LE;
+    const uint32_t B = d.bit_depth >> 3;
+    const uint32_t channels = d.channels;
+    const uint64_t dst = reinterpret_cast<uint64_t>(p.out) + d.dst_off;
+    r.kind = silence ? (packed ? kSilence : kSilenceConv) : kPcm;
+    r.bytes = d.bytes;
+    r.head = silence ? 0u : (uint32_t)((reinterpret_cast<uint64_t>(p.in) + src_off) & 15u);
     r.channels = channels;
     r.ch_magic = c_ch_magic[channels];
-    r.attenuation = attenuation;
-    r.units = (bytes / B + 3u) >> 2;
+    r.attenuation = silence ? OHP_UNITY_ATTENUATION : d.attenuation;
+    r.units = (d.bytes / B + 3u) >> 2;
+    r.frames = dv.frames;
+    r.out_fmt = d.out_fmt;
+    r.aux = d.aux;
+    r.out_bytes = dv.out_bytes;
     r.dst_lo = (uint32_t)dst;
     r.dst_hi = (uint32_t)(dst >> 32);
-    const bool ramped = (flags & OHP_F_RAMP_ENABLED) != 0;
-    const bool in_le = (flags & OHP_F_IN_LITTLE_ENDIAN) != 0 && B > 1;
-    const bool out_le = (out_fmt == OHP_OUT_PACKED_LE) && B > 1;
-    const bool transform = ramped || (in_le != out_le) || attenuation != OHP_UNITY_ATTENUATION;
+    const bool ramped = (d.flags & OHP_F_RAMP_ENABLED) != 0 && !silence; // silence is never ramped (Msg.cpp:2874-2893)
+    const bool in_le = (d.flags & OHP_F_IN_LITTLE_ENDIAN) != 0 && B > 1 && !silence;
+    const bool out_le = (d.out_fmt == OHP_OUT_PACKED_LE) && B > 1;
+    const bool transform = ramped || (in_le != out_le) || r.attenuation != OHP_UNITY_ATTENUATION;
     r.mode = (ramped ? kModeRamped : 0u) | (in_le ? kModeInLe : 0u) | (out_le ? kModeOutLe : 0u)
            | ((channels == 6) ? kModeTag6 : 0u) | (transform ? kModeTransform : 0u);
     const uint32_t chm = channels == 2 ? kChmStereo : ((channels & 3u) == 0 ? kChmMul4 : (channels == 1 ? kChmMono : kChmOther));
-    const bool aligned = r.head == 0 && (dst & 15u) == 0; // both images start on a 16-byte boundary of their stage
+    const bool aligned = r.head == 0 && (dst & 15u) == 0; // the image starts on a 16-byte boundary and stays where it is
     r.variant = (B - 1u) | (chm << 2) | (aligned ? 16u : 0u);
-    make_ramp_const(r, ramp_start, ramp_end, frames);
+    make_ramp_const(r, d.ramp_start, d.ramp_end, dv.frames);
     return 0;
 }
 
@@ -158,9 +151,10 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     const uint64_t it = base + j;
                     const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
                     const uint32_t bs = (uint32_t)(it & (kRingSlots - 1));
-                    const bool pcm = sm.rec[sl].kind == kPcm;
+                    const uint32_t kind = sm.rec[sl].kind;
+                    const bool pcm = kind == kPcm;
                     uint32_t span = 0, need = 0;
-                    if (pcm) {
+                    if (pcm || kind == kSilenceConv) {
                         span = (sm.rec[sl].head + sm.rec[sl].bytes + 15u) & ~15u;
                         need = kSlotFront + span + kSlotBack;
                     }
@@ -197,7 +191,8 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                         }
                         wr += need;
                     } else {
-                        mbar_arrive(full);
+                        mbar_arrive(full); // nothing to load (silence; a converting sink still gets its slot)
+                        wr += need;
                     }
                 }
             }
@@ -220,25 +215,53 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
             const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
             const ChunkRec& cr = sm.rec[sl];
             const uint32_t kind = cr.kind;
-            if (kind == kPcm) {
+            if (kind == kPcm || kind == kSilenceConv) {
                 uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
                 const uint32_t head = cr.head;
                 const uint32_t in_addr = ring + sm.ring_off[sl] + kSlotFront;          // 16-byte aligned; image at +head
                 // the output image goes where it is congruent to the destination mod 16, at or just below the input
                 const uint32_t image = in_addr + head - ((head - cr.dst_lo) & 15u);
                 const uint32_t out_addr = image & ~3u;                                 // word stores; == image unless dst is odd
+                const uint32_t fmt = cr.out_fmt;
+                if (kind == kSilenceConv) {
+                    silence_to_smem(in_addr, cr.bytes, cr.channels, lane);
+                    __syncwarp();
+                }
 #ifdef OHP_PROFILE_WAITS
                 const long long tx0 = clock64();
 #endif
-                if (cr.mode & kModeTransform) {
-                    switch (cr.variant & 3u) {
-                    case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, lane); break;
-                    case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, lane); break;
-                    case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, lane); break;
-                    default: transform_dispatch<4>(cr, table, in_addr, out_addr, lane); break;
+                if (fmt <= OHP_OUT_PACKED_LE) {
+                    if (cr.mode & kModeTransform) {
+                        switch (cr.variant & 3u) {
+                        case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, lane); break;
+                        case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, lane); break;
+                        case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, lane); break;
+                        default: transform_dispatch<4>(cr, table, in_addr, out_addr, lane); break;
+                        }
+                    } else if (out_addr != in_addr + head) {
+                        shift_chunk(in_addr, head, out_addr, cr.bytes, lane);
                     }
-                } else if (out_addr != in_addr + head) {
-                    shift_chunk(in_addr, head, out_addr, cr.bytes, lane);
+                } else if (fmt == OHP_OUT_PLANAR32_BE) {
+                    convert_planar32(cr, table, in_addr, dst, cr.aux * 4u, lane);
+                } else if (fmt == OHP_OUT_FROM32_BE) {
+                    switch (cr.aux) {
+                    case 8: convert_from32<1>(cr, table, in_addr, out_addr, lane); break;
+                    case 16: convert_from32<2>(cr, table, in_addr, out_addr, lane); break;
+                    case 24: convert_from32<3>(cr, table, in_addr, out_addr, lane); break;
+                    default: convert_from32<4>(cr, table, in_addr, out_addr, lane); break;
+                    }
+                } else {
+                    const uint32_t B = (cr.variant & 3u) + 1u;
+                    const uint32_t db = B < 3 ? B : 3u;
+                    if (cr.channels >= 2) {
+                        if (db == 1) convert_songcast<1, 2>(cr, table, in_addr, out_addr, cr.aux, lane);
+                        else if (db == 2) convert_songcast<2, 2>(cr, table, in_addr, out_addr, cr.aux, lane);
+                        else convert_songcast<3, 2>(cr, table, in_addr, out_addr, cr.aux, lane);
+                    } else {
+                        if (db == 1) convert_songcast<1, 1>(cr, table, in_addr, out_addr, cr.aux, lane);
+                        else if (db == 2) convert_songcast<2, 1>(cr, table, in_addr, out_addr, cr.aux, lane);
+                        else convert_songcast<3, 1>(cr, table, in_addr, out_addr, cr.aux, lane);
+                    }
                 }
 #ifdef OHP_PROFILE_WAITS
                 const long long tx1 = clock64();
@@ -250,10 +273,10 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 const long long tx2 = clock64();
                 w_fence += tx2 - tx1;
 #endif
-                // image == out_addr: TMA bulk store of the aligned interior; otherwise (destination not 4-byte aligned)
-                // the image sits (dst & 3) bytes above out_addr... it does not: the transform wrote the image AT out_addr,
-                // and store_image_warp realigns through registers because out_addr and dst then disagree mod 16.
-                store_image_warp(out_addr, dst, cr.bytes, lane);
+                // the finished image sits at out_addr: one TMA bulk store for its 16-byte aligned interior when out_addr is
+                // congruent to dst mod 16, a register funnel otherwise (destination not 4-byte aligned).  The planar sink
+                // has already written global memory itself.
+                if (fmt != OHP_OUT_PLANAR32_BE) store_image_warp(out_addr, dst, cr.out_bytes, lane);
                 __syncwarp();
                 if (lane == 0) {
                     tma_commit();
@@ -261,9 +284,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     const long long ts = clock64();
                     w_issue += ts - tx2;
 #endif
-#ifndef OHP_EXPERIMENT_NO_STORE_WAIT /* timing experiment only: releasing early is a data race */
                     tma_wait_read<0>(); // the slot can be reused once the bulk store has READ it
-#endif
 #ifdef OHP_PROFILE_WAITS
                     w_store += clock64() - ts;
 #endif
@@ -383,22 +404,16 @@ static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = 
         if (e_ != cudaSuccess) return fail((ctx), OHP_E_CUDA, #call, e_);       \
     } while (0)
 
-static int check_desc(const ohp_chunk_desc& d, uint64_t in_bytes, uint64_t out_bytes)
+static int check_desc(const ohp_chunk_desc& d, uint64_t in_bytes, uint64_t out_bytes, DescDerived* derived = nullptr)
 {
-    const uint32_t bd = d.bit_depth;
-    if (!(bd == 8 || bd == 16 || bd == 24 || bd == 32)) return OHP_E_INVALID_DESC;
-    if (d.channels < 1 || d.channels > 32) return OHP_E_INVALID_DESC;
-    if (d.ramp_start > OHP_RAMP_MAX || d.ramp_end > OHP_RAMP_MAX) return OHP_E_INVALID_DESC;
-    if (!(d.out_fmt == OHP_OUT_PACKED_BE || d.out_fmt == OHP_OUT_PACKED_LE)) return OHP_E_INVALID_DESC;
-    const uint32_t B = bd / 8;
-    const bool silence = (d.flags & OHP_F_SILENCE) != 0;
-    if (d.bytes % (B * d.channels) != 0) return OHP_E_INVALID_DESC;
-    if (!silence && d.bytes > OHP_MAX_PCM_CHUNK_BYTES) return OHP_E_INVALID_DESC;
-    if (!silence && d.attenuation != OHP_UNITY_ATTENUATION && bd != 16) return OHP_E_INVALID_DESC;
-    if (d.out_fmt == OHP_OUT_PACKED_LE && (silence || B > 3)) return OHP_E_INVALID_DESC;
-    if (d.dst_off > out_bytes || d.bytes > out_bytes - d.dst_off) return OHP_E_OUT_OF_RANGE;
-    if (!silence && (d.src_off > in_bytes || d.bytes > in_bytes - d.src_off)) return OHP_E_OUT_OF_RANGE;
-    return OHP_OK;
+    DescFields f;
+    f.src_off = d.src_off; f.dst_off = d.dst_off; f.bytes = d.bytes; f.ramp_start = d.ramp_start; f.ramp_end = d.ramp_end;
+    f.attenuation = d.attenuation; f.bit_depth = d.bit_depth; f.channels = d.channels; f.flags = d.flags;
+    f.out_fmt = d.out_fmt; f.aux = d.aux;
+    DescDerived dv;
+    const uint32_t err = check_desc_fields(f, in_bytes, out_bytes, dv);
+    if (derived) *derived = dv;
+    return err == 0 ? OHP_OK : (err == 1u ? OHP_E_INVALID_DESC : OHP_E_OUT_OF_RANGE);
 }
 
 static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, const uint8_t* d_in, uint64_t in_bytes,
@@ -495,17 +510,9 @@ uint32_t ohp_median_multiplier(uint32_t ramp_start, uint32_t ramp_end, uint32_t 
 uint32_t ohp_chunk_out_bytes(const ohp_chunk_desc* d)
 {
     if (!d) return 0;
-    const uint32_t B = d->bit_depth / 8u;
-    if (B == 0 || d->channels == 0) return 0;
-    const uint32_t frames = d->bytes / (B * d->channels);
-    switch (d->out_fmt) {
-    case OHP_OUT_PACKED_BE:
-    case OHP_OUT_PACKED_LE: return d->bytes;
-    case OHP_OUT_PLANAR32_BE: return frames * d->channels * 4u;
-    case OHP_OUT_FROM32_BE: return (d->bytes / 4u) * (d->aux / 8u);
-    case OHP_OUT_SONGCAST: return frames * (d->channels < 2 ? d->channels : 2u) * (B < 3 ? B : 3u);
-    default: return 0;
-    }
+    DescDerived dv;
+    (void)check_desc(*d, UINT64_MAX, UINT64_MAX, &dv);
+    return dv.out_bytes;
 }
 
 int ohp_validate(const ohp_chunk_desc* descs, size_t n, uint64_t in_bytes, uint64_t out_bytes, size_t* bad_index)
@@ -678,9 +685,11 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
                     in_lo = d.src_off < in_lo ? d.src_off : in_lo;
                     in_hi = d.src_off + d.bytes > in_hi ? d.src_off + d.bytes : in_hi;
                 }
+                DescDerived dv;
+                (void)check_desc(d, in_bytes, out_bytes, &dv);
                 out_lo = d.dst_off < out_lo ? d.dst_off : out_lo;
-                out_hi = d.dst_off + d.bytes > out_hi ? d.dst_off + d.bytes : out_hi;
-                moved += 2ull * d.bytes;
+                out_hi = d.dst_off + dv.out_extent > out_hi ? d.dst_off + dv.out_extent : out_hi;
+                moved += (uint64_t)d.bytes + dv.out_extent;
             }
             hi++;
         }

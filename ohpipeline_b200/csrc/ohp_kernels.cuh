@@ -83,8 +83,72 @@ struct KernelParams
     uint32_t* status;        // [0] error bits, [1] index of first offending chunk + 1
 };
 
+// One descriptor, unpacked; the checks are the reference's ASSERTs restated, shared by ohp_validate (host) and the
+// loader warp (device) so that both reject exactly the same descriptors.
+struct DescFields
+{
+    uint64_t src_off, dst_off;
+    uint32_t bytes, ramp_start, ramp_end, attenuation, bit_depth, channels, flags, out_fmt, aux;
+};
+struct DescDerived
+{
+    uint32_t frames;
+    uint32_t out_bytes;   // bytes the sink receives
+    uint64_t out_extent;  // distance from dst_off to one past the last byte written (planar output is strided)
+};
+// 0 = ok, else kErrInvalidDesc / kErrOutOfRange
+__host__ __device__ inline uint32_t check_desc_fields(const DescFields& d, uint64_t in_bytes, uint64_t out_total, DescDerived& o)
+{
+    o.frames = 0; o.out_bytes = 0; o.out_extent = 0;
+    const uint32_t bd = d.bit_depth;
+    if (!(bd == 8 || bd == 16 || bd == 24 || bd == 32)) return 1u;           // ConstructPcm ASSERTs, Msg.cpp:349-366
+    if (d.channels < 1 || d.channels > 32) return 1u;
+    if (d.ramp_start > OHP_RAMP_MAX || d.ramp_end > OHP_RAMP_MAX) return 1u;  // Ramp::DoValidate, Msg.cpp:747-752
+    if (d.out_fmt > OHP_OUT_SONGCAST) return 1u;
+    const uint32_t B = bd >> 3;
+    const bool silence = (d.flags & OHP_F_SILENCE) != 0;
+    const uint32_t frame_bytes = B * d.channels;
+    const uint32_t frames = d.bytes / frame_bytes;
+    if (frames * frame_bytes != d.bytes) return 1u;                           // whole frames (ProcessorAudioUtils.cpp:45)
+    if (!silence && d.bytes > OHP_MAX_PCM_CHUNK_BYTES) return 1u;             // a DecodedAudio cell
+    if (!silence && d.attenuation != OHP_UNITY_ATTENUATION && bd != 16) return 1u; // Msg.cpp:2741
+    o.frames = frames;
+    o.out_bytes = d.bytes;
+    o.out_extent = d.bytes;
+    switch (d.out_fmt) {
+    case OHP_OUT_PACKED_BE:
+        break;
+    case OHP_OUT_PACKED_LE:                                                   // TestCodecInteractiveMain.cpp:546-567
+        if (silence || B > 3) return 1u;
+        break;
+    case OHP_OUT_PLANAR32_BE:                                                 // StarvationRamper.cpp:90-111
+        if (d.aux < frames) return 1u;
+        if (silence && d.bytes > OHP_MAX_PCM_CHUNK_BYTES) return 1u;
+        o.out_bytes = frames * d.channels * 4u;
+        o.out_extent = frames ? (uint64_t)(d.channels - 1u) * d.aux * 4u + (uint64_t)frames * 4u : 0;
+        break;
+    case OHP_OUT_FROM32_BE:                                                   // StarvationRamper.cpp:281-343
+        if (silence || B != 4) return 1u;
+        if (!(d.aux == 8 || d.aux == 16 || d.aux == 24 || d.aux == 32)) return 1u;
+        o.out_bytes = (d.bytes / 4u) * (d.aux / 8u);
+        o.out_extent = o.out_bytes;
+        break;
+    default: {                                                                // OHP_OUT_SONGCAST, Sender.cpp:356-377
+        const uint32_t och = d.channels < 2 ? d.channels : 2u;
+        if (d.aux + och > d.channels) return 1u;
+        if (silence && d.bytes > OHP_MAX_PCM_CHUNK_BYTES) return 1u;
+        o.out_bytes = frames * och * (B < 3 ? B : 3u);
+        o.out_extent = o.out_bytes;
+        break;
+    }
+    }
+    if (d.dst_off > out_total || o.out_extent > out_total - d.dst_off) return 2u;
+    if (!silence && (d.src_off > in_bytes || d.bytes > in_bytes - d.src_off)) return 2u;
+    return 0;
+}
+
 // What the loader hands to the consumers (and the storer) for one chunk: one 64-byte shared-memory record.
-enum ChunkKind : uint32_t { kSkip = 0, kPcm = 1, kSilence = 2 };
+enum ChunkKind : uint32_t { kSkip = 0, kPcm = 1, kSilence = 2, kSilenceConv = 3 /* silence into a converting sink */ };
 
 struct ChunkRec
 {
@@ -104,8 +168,12 @@ struct ChunkRec
     uint32_t ramp_shift;  // ... so that q = umulhi(i*total, magic) >> shift exactly
     uint32_t units;       // ceil(subsamples / 4)
     uint32_t dst_lo, dst_hi;
+    uint32_t frames;
+    uint32_t out_fmt;     // ohp_out_fmt
+    uint32_t aux;         // per-format parameter (ohp_chunk_desc::aux)
+    uint32_t out_bytes;   // bytes the sink receives (== bytes for the packed sinks)
 };
-static_assert(sizeof(ChunkRec) == 64, "ChunkRec is one 64-byte record");
+static_assert(sizeof(ChunkRec) == 80, "ChunkRec is 80 bytes (16-byte multiple)");
 
 constexpr uint32_t kModeRamped = 1u, kModeInLe = 2u, kModeOutLe = 4u, kModeTag6 = 8u, kModeTransform = 16u;
 // how the four subsamples of a unit map to frames
@@ -210,7 +278,7 @@ __device__ __forceinline__ void tma_load(uint32_t dst_smem, const void* src, uin
 // shared -> global bulk copy (TMA), tracked by bulk async-groups.
 __device__ __forceinline__ void tma_store(void* dst, uint32_t src_smem, uint32_t bytes)
 {
-#ifdef OHP_L2_HINT_STORE
+#ifndef OHP_NO_L2_HINT_STORE /* output is written once and never re-read: evict-first keeps it from crowding L2 (+1.5 % on configs[1]) */
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                  :: "l"(dst), "r"(src_smem), "r"(bytes), "l"(l2_evict_first_policy()) : "memory");
 #else
@@ -598,6 +666,157 @@ __device__ __noinline__ void shift_chunk(uint32_t in_addr, uint32_t head, uint32
         }
         __syncwarp();
         if (w < words) sts32(out_addr + 4u * w, __funnelshift_r(a, b, fshift));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The other IPcmProcessor sinks of the reference tree (output size differs from the input size).  One subsample at a
+// time, any alignment: these carry 1 ms flywheel blocks and Songcast frames, not the bulk of the traffic.
+
+// Left-justified big-endian value of the B-byte subsample whose first byte is at shared address a (low bytes zero).
+__device__ __forceinline__ uint32_t load_subsample(uint32_t a, uint32_t B, bool le)
+{
+    const uint32_t aw = a & ~3u;
+    const uint32_t x = __funnelshift_r(lds32(aw), lds32(aw + 4u), (a & 3u) * 8u); // memory order, first byte lowest
+    const uint32_t v = le ? (x << (8u * (4u - B))) : __byte_perm(x, 0u, 0x0123);
+    return v & (0xffffffffu << (8u * (4u - B)));
+}
+
+// MsgPlayablePcm::ReadBlock's arithmetic on one subsample (attenuation, then ramp), on the left-justified value.
+__device__ __forceinline__ uint32_t ramp_subsample(uint32_t v, uint32_t B, const UnitCtx& cx, const RampRegs& rr, uint32_t frame, uint32_t chan)
+{
+    if (B == 2 && cx.attenuation != OHP_UNITY_ATTENUATION) {
+        const uint32_t s = (uint32_t)((int32_t)v >> 16);
+        v = ((s * cx.attenuation) >> 8) << 16;
+    }
+    if (cx.ramped) {
+        const int32_t s16 = (int32_t)v >> 16; // 8-bit: the value's low byte is already zero
+        const uint32_t prod2 = (uint32_t)(s16 * (int32_t)ramp_mult2(rr, frame));
+        v = prod2 & (B == 1 ? 0xff000000u : 0xffff0000u);
+        if (B == 4 && cx.tag6) v |= chan << 4;
+    }
+    return v;
+}
+
+// FlywheelInput::DoProcessFragment (StarvationRamper.cpp:117-186): interleaved -> planar, 4 bytes per subsample,
+// big-endian left-justified, zero padded; channel c's plane starts at dst + c * plane_bytes.  Written straight to global.
+__device__ __noinline__ void convert_planar32(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint8_t* dst, uint32_t plane_bytes, uint32_t lane)
+{
+    UnitCtx cx;
+    RampRegs rr;
+    rr.table = table;
+    load_ctx(cr, cx, rr);
+    const uint32_t B = (cr.variant & 3u) + 1u;
+    const uint32_t ch = cr.channels;
+    const uint32_t frames = cr.frames;
+    const bool words = ((reinterpret_cast<uint64_t>(dst) | plane_bytes) & 3u) == 0;
+    for (uint32_t c = 0; c < ch; c++) {
+        uint8_t* plane = dst + (uint64_t)c * plane_bytes;
+        for (uint32_t f = lane; f < frames; f += 32) {
+            uint32_t v = load_subsample(in_addr + cr.head + (f * ch + c) * B, B, cx.in_le);
+            v = ramp_subsample(v, B, cx, rr, f, c);
+            const uint32_t be = __byte_perm(v, 0u, 0x0123); // most significant byte first in memory
+            if (words) {
+                reinterpret_cast<uint32_t*>(plane)[f] = be;
+            } else {
+                for (uint32_t i = 0; i < 4; i++) plane[4u * f + i] = (uint8_t)(be >> (8u * i));
+            }
+        }
+    }
+}
+
+// RampGenerator::ProcessFragment (StarvationRamper.cpp:281-326): 32-bit big-endian in, the top OB bytes out
+// (32 -> three bytes and a zero).  Contracts in place: unit u (4 subsamples, 16 bytes) -> OB words.
+template <int OB>
+__device__ __noinline__ void convert_from32(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t lane)
+{
+    UnitCtx cx;
+    RampRegs rr;
+    rr.table = table;
+    load_ctx(cr, cx, rr);
+    const uint32_t ch = cr.channels;
+    const uint32_t units = cr.units;
+    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        uint32_t o[4];
+        if (u < units) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t k = 4u * u + j;
+                const uint32_t f = cr.ch_magic ? __umulhi(k, cr.ch_magic) : k; // k / channels
+                uint32_t v = load_subsample(in_addr + cr.head + 4u * k, 4u, cx.in_le);
+                v = ramp_subsample(v, 4u, cx, rr, f, k - f * ch);
+                o[j] = (OB == 4) ? (v & 0xffffff00u) : v;
+            }
+        } else {
+            o[0] = o[1] = o[2] = o[3] = 0;
+        }
+        __syncwarp();
+        if (u < units) {
+            uint32_t w[OB];
+            unit_pack<OB>(o, w, false, false);
+#pragma unroll
+            for (int i = 0; i < OB; i++) sts32(out_addr + u * (4u * OB) + 4u * i, w[i]);
+        }
+    }
+}
+
+// Sender::DoProcessFragment (Av/Songcast/Sender.cpp:356-377): OCH (1 or 2) channels starting at `first`, the top
+// DB = min(B, 3) bytes of each subsample.  Contracts in place: unit u = 4 frames -> OCH * DB words.
+template <int DB, int OCH>
+__device__ __noinline__ void convert_songcast(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t first, uint32_t lane)
+{
+    UnitCtx cx;
+    RampRegs rr;
+    rr.table = table;
+    load_ctx(cr, cx, rr);
+    const uint32_t B = (cr.variant & 3u) + 1u;
+    const uint32_t ch = cr.channels;
+    const uint32_t units = (cr.frames + 3u) >> 2;
+    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        uint32_t o[4 * OCH];
+        if (u < units) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t f = min(4u * u + j, cr.frames - 1u); // surplus frames of the last unit: recomputed, not stored beyond
+#pragma unroll
+                for (int c = 0; c < OCH; c++) {
+                    uint32_t v = load_subsample(in_addr + cr.head + (f * ch + first + c) * B, B, cx.in_le);
+                    o[j * OCH + c] = ramp_subsample(v, B, cx, rr, f, first + c);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4 * OCH; j++) o[j] = 0;
+        }
+        __syncwarp();
+        if (u < units) {
+#pragma unroll
+            for (int h = 0; h < OCH; h++) {
+                const uint32_t (&oh)[4] = reinterpret_cast<const uint32_t (&)[4]>(o[4 * h]);
+                uint32_t w[DB];
+                unit_pack<DB>(oh, w, false, false);
+#pragma unroll
+                for (int i = 0; i < DB; i++) sts32(out_addr + u * (4u * OCH * DB) + (h * DB + i) * 4u, w[i]);
+            }
+        }
+    }
+}
+
+// Fill `bytes` bytes at shared address a (16-byte aligned) with what MsgPlayableSilence::ReadBlock would emit:
+// used when silence goes to a sink that converts it (planar / Songcast).
+__device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint32_t channels, uint32_t lane)
+{
+    const uint32_t vecs = (bytes + 15u) >> 4;
+    for (uint32_t v = lane; v < vecs; v += 32) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        if (channels == 6 && v < 2) {
+            // 00 00 00 c0 with c0 = 0x00,0x10..0x70 over the first 32 bytes (Msg.cpp:2877)
+            const uint32_t c0 = 4u * v;
+            z = make_uint4((c0 << 4) << 24, ((c0 + 1u) << 4) << 24, ((c0 + 2u) << 4) << 24, ((c0 + 3u) << 4) << 24);
+        }
+        sts128(a + 16u * v, z);
     }
 }
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from ohpipeline_b200 import abi, capi, workloads as W
-from util import describe_first_diff, make_desc, pack_chunks
+from util import covered_mask, describe_first_diff, make_desc, pack_chunks
 
 pytestmark = pytest.mark.gpu
 
@@ -341,3 +341,93 @@ def test_cuda_path_reproduces_reference_golden_vectors(ctx, port, path):
         mask[int(d["dst_off"]):int(d["dst_off"]) + int(n)] = True
     out = run_device(ctx, sched.chunks, inp, out_bytes, fill=0)
     assert _hashlib.sha256(out.tobytes()).digest() == g["out_sha256"].tobytes()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the other IPcmProcessor sinks of the reference tree: FlywheelInput, RampGenerator, Songcast Sender
+
+def _compare_whole(ctx, port, descs, inp, out_bytes):
+    rc, want = port.process_chunks(descs, inp, out_bytes)
+    assert rc == 0, "oracle rejected chunk %d" % (-rc - 1)
+    got = run_device(ctx, descs, inp, out_bytes, fill=0)
+    assert np.array_equal(got, want), describe_first_diff(got, want, descs)
+    got = np.zeros(out_bytes, dtype=np.uint8)
+    ctx.process_host(descs, inp, got)
+    m = covered_mask(descs, out_bytes)  # ohp_process_host leaves bytes no chunk covers unspecified
+    assert np.array_equal(got[m], want[m]), "host path differs from the oracle"
+
+
+def test_planar32_sink_flywheel_input(ctx, port):
+    """FlywheelInput (StarvationRamper.cpp:117-186): interleaved -> planar 4-byte BE left-justified, several playables
+    appended into the same planes the way Prepare() reads a queue of messages."""
+    rng = np.random.default_rng(31)
+    descs = []
+    src = dst = 0
+    for bits in (8, 16, 24, 32):
+        b = bits // 8
+        for ch in (1, 2, 3, 6, 8):
+            parts = [int(x) for x in rng.integers(1, 120, 3)]
+            total = sum(parts) + int(rng.integers(0, 5))
+            done = 0
+            for i, frames in enumerate(parts):
+                silence = (i == 1 and ch in (2, 6))
+                d = make_desc(bytes=frames * ch * b, bit_depth=bits, channels=ch, out_fmt=abi.OUT_PLANAR32_BE, aux=total,
+                              flags=(abi.F_SILENCE if silence else (abi.F_IN_LITTLE_ENDIAN if (bits + ch) % 3 == 0 else 0))
+                              | (abi.F_RAMP_ENABLED if i == 2 else 0),
+                              ramp_start=int(rng.integers(0, 16385)), ramp_end=int(rng.integers(0, 16385)),
+                              src_off=src, dst_off=dst + done * 4)
+                descs.append(d[0])
+                if not silence:
+                    src += frames * ch * b + int(rng.integers(0, 3))
+                done += frames
+            dst += ch * total * 4 + 4 * int(rng.integers(0, 3))
+    descs = np.array(descs, dtype=abi.CHUNK_DESC)
+    inp = port.fill_pcm(src + 64, 3131)
+    _compare_whole(ctx, port, descs, inp, dst + 64)
+
+
+def test_from32_sink_ramp_generator(ctx, port):
+    """RampGenerator::ProcessFragment (StarvationRamper.cpp:281-326): 32-bit BE in, packed 8/16/24/32-bit BE out."""
+    rng = np.random.default_rng(32)
+    specs = []
+    for ob in (8, 16, 24, 32):
+        for ch in (1, 2, 5, 6, 8):
+            for frames in (1, 7, 48, 192, 9216 // (4 * ch)):
+                specs.append(dict(bytes=frames * ch * 4, bit_depth=32, channels=ch, out_fmt=abi.OUT_FROM32_BE, aux=ob,
+                                  flags=(abi.F_RAMP_ENABLED if frames % 2 else 0), ramp_start=int(rng.integers(0, 16385)),
+                                  ramp_end=int(rng.integers(0, 16385)), src_pad=int(rng.integers(0, 4)), dst_pad=int(rng.integers(0, 4))))
+    descs, in_bytes, out_bytes = pack_chunks(specs)
+    inp = port.fill_pcm(in_bytes, 3232)
+    _compare_whole(ctx, port, descs, inp, out_bytes)
+
+
+def test_songcast_sink(ctx, port):
+    """Sender::DoProcessFragment (Av/Songcast/Sender.cpp:356-377): two channels from FirstChannelToSend, at most
+    three bytes per subsample; mono sends one; silence goes through the same path."""
+    rng = np.random.default_rng(33)
+    specs = []
+    for bits in (8, 16, 24, 32):
+        b = bits // 8
+        for ch in (1, 2, 3, 6, 8, 10, 12):
+            first = 0 if ch < 10 else 8  # Sender::FirstChannelToSend, Sender.cpp:351-354
+            for frames in (1, 5, 64, 9216 // (ch * b)):
+                kind = int(rng.integers(0, 4))
+                flags = [0, abi.F_RAMP_ENABLED, abi.F_RAMP_ENABLED | abi.F_IN_LITTLE_ENDIAN, abi.F_SILENCE][kind]
+                specs.append(dict(bytes=frames * ch * b, bit_depth=bits, channels=ch, out_fmt=abi.OUT_SONGCAST, aux=first, flags=flags,
+                                  ramp_start=int(rng.integers(0, 16385)), ramp_end=int(rng.integers(0, 16385)),
+                                  src_pad=int(rng.integers(0, 4)), dst_pad=int(rng.integers(0, 4))))
+    descs, in_bytes, out_bytes = pack_chunks(specs)
+    inp = port.fill_pcm(in_bytes, 3333)
+    _compare_whole(ctx, port, descs, inp, out_bytes)
+
+
+def test_converting_sinks_reject_what_the_reference_asserts_on(ctx):
+    bad = [make_desc(bytes=32, bit_depth=16, channels=2, out_fmt=abi.OUT_FROM32_BE, aux=16),       # RampGenerator is fed 32-bit only
+           make_desc(bytes=32, bit_depth=32, channels=2, out_fmt=abi.OUT_FROM32_BE, aux=12),
+           make_desc(bytes=32, bit_depth=32, channels=2, out_fmt=abi.OUT_FROM32_BE, aux=16, flags=abi.F_SILENCE),  # ProcessSilence ASSERTS
+           make_desc(bytes=32, bit_depth=16, channels=2, out_fmt=abi.OUT_PLANAR32_BE, aux=7),      # plane shorter than the playable
+           make_desc(bytes=32, bit_depth=16, channels=2, out_fmt=abi.OUT_SONGCAST, aux=1)]         # first channel + 2 > channels
+    for d in bad:
+        assert capi.validate(d, 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC, d
+        with pytest.raises(capi.OhpError):
+            ctx.process_host(d, np.zeros(64, np.uint8), np.zeros(4096, np.uint8))

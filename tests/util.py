@@ -42,8 +42,27 @@ def pack_chunks(chunk_specs, align=1, rng=None):
         descs[i] = d[0]
         if not (int(d["flags"][0]) & abi.F_SILENCE):
             src += int(d["bytes"][0])
-        dst += int(abi.chunk_out_bytes(d)[0])
+        if int(d["out_fmt"][0]) == abi.OUT_PLANAR32_BE:
+            dst += int(d["channels"][0]) * int(d["aux"][0]) * 4
+        else:
+            dst += int(abi.chunk_out_bytes(d)[0])
         if align > 1:
             src = (src + align - 1) // align * align
             dst = (dst + align - 1) // align * align
     return descs, src + 64, dst + 64
+
+
+def covered_mask(descs, out_bytes):
+    """Boolean mask of the output bytes some chunk writes (planar output is strided per channel)."""
+    mask = np.zeros(out_bytes, dtype=bool)
+    ob = abi.chunk_out_bytes(descs)
+    for d, n in zip(descs, ob):
+        lo = int(d["dst_off"])
+        if int(d["out_fmt"]) == abi.OUT_PLANAR32_BE:
+            frames = int(d["bytes"]) // (int(d["channels"]) * int(d["bit_depth"]) // 8)
+            for c in range(int(d["channels"])):
+                a = lo + c * int(d["aux"]) * 4
+                mask[a:a + frames * 4] = True
+        else:
+            mask[lo:lo + int(n)] = True
+    return mask
