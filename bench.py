@@ -42,6 +42,8 @@ def build_workload(name, streams, seconds):
         return workloads.config5(n_streams=streams or 65536, seconds=seconds or 1.0)
     if name == "config3":
         return workloads.config3(n_streams=streams or 4096, seconds=seconds or 1.0)
+    if name == "config4":
+        return workloads.mixed(n_streams=streams or 16384, seed=4, max_frames=int((seconds or 1.0) * 48000))
     if name == "config1":
         return workloads.config1(seconds or 10.0)
     raise SystemExit("unknown workload %r" % name)

@@ -51,8 +51,9 @@ def cuda_lib():
         L.ohp_ramp_table.restype = C.POINTER(C.c_uint16)
         L.ohp_median_multiplier.restype = C.c_uint32
         L.ohp_median_multiplier.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
-        L.ohp_chunk_out_bytes.restype = C.c_uint32
-        L.ohp_chunk_out_bytes.argtypes = [C.c_void_p]
+        if hasattr(L, "ohp_chunk_out_bytes"):  # absent only from older experiment builds loaded through OHP_LIB_CUDA
+            L.ohp_chunk_out_bytes.restype = C.c_uint32
+            L.ohp_chunk_out_bytes.argtypes = [C.c_void_p]
         L.ohp_validate.restype = C.c_int
         L.ohp_validate.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.POINTER(C.c_size_t)]
         L.ohp_process_device.restype = C.c_int

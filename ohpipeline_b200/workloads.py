@@ -206,8 +206,15 @@ def mixed(n_streams=64, seed=4, max_frames=6000, with_silence=True, p2=True):
                 # keep it audible: ramp down only part of the way by giving it far more time than the stream has
                 op, dur = abi.EV_RAMP_DOWN, (4 * total_j + jps) // q * q + q
             lst.append((at, stage, op, dur if op in (abi.EV_RAMP_DOWN, abi.EV_RAMP_UP) else 0))
+        msg_frames = chunk
         if rng.random() < 0.3:
-            lst.append((0, int(rng.integers(0, 3)), abi.EV_MAX_MSG_JIFFIES, max(jps, int(rng.integers(jps, 5 * MS)) // q * q)))
+            cap = max(jps, int(rng.integers(jps, 5 * MS)) // q * q)
+            lst.append((0, int(rng.integers(0, 3)), abi.EV_MAX_MSG_JIFFIES, cap))
+            msg_frames = max(1, min(chunk, cap // jps))
+        if want_p2 and -(-total // msg_frames) + n_ev > 6000:
+            # Ramp::Set rounds every message's share of the ramp UP (Msg.cpp:606-611), so a long stream of tiny
+            # messages reaches kMin however slow the ramp is -- and then mutes.  Such P2 streams only ramp up.
+            lst = [(at, st, abi.EV_RAMP_UP if op == abi.EV_RAMP_DOWN else op, arg) for (at, st, op, arg) in lst]
         if bits == 16 and rng.random() < 0.5:
             lst.append((int(rng.integers(0, total_j + 1)) // q * q, 3, abi.EV_SET_ATTENUATION, int(rng.integers(0, 512))))
         if use_silence:
