@@ -1,6 +1,7 @@
 // msg_model.cpp -- see msg_model.h.  The arithmetic follows the reference exactly (descriptor parity is
 // checked against the linked reference in tests/test_schedule_parity.py); the code is this repo's own.
 #include "msg_model.h"
+#include "ramp_core.h"
 
 #include <algorithm>
 
@@ -27,124 +28,38 @@ static uint32_t ohp_median_multiplier_host(uint32_t aStart, uint32_t aEnd, uint3
 // ------------------------------------------------------------------------------------------------
 // Ramp
 
-bool Ramp::IsValid() const
+// The arithmetic lives in ramp_core.h (shared with the device-side schedule builder); these wrappers keep the
+// reference's signatures and turn its ASSERTs into AssertionFailed.
+
+static core::RampPod ToPod(const Ramp& aRamp)
 {
-    // Ramp::DoValidate, Msg.cpp:745-782
-    if (iStart > kMax || iEnd > kMax) return false;
-    switch (iDirection) {
-    case ENone: return iStart == iEnd;
-    case EUp:   return iStart < iEnd;
-    case EDown: return iStart > iEnd;
-    case EMute: return iStart == kMin && iEnd == kMin;
-    }
-    return false;
+    const ohp_ramp r = aRamp.ToAbi();
+    return core::RampPod{r.start, r.end, r.direction, r.enabled};
 }
 
-void Ramp::TakeLower(uint32_t aStart, uint32_t aEnd)
+static Ramp FromPod(const core::RampPod& aPod)
 {
-    // two ramps over the same audio: the quieter one wins at both ends (Msg.cpp:721-734)
-    iStart = std::min(iStart, aStart);
-    iEnd = std::min(iEnd, aEnd);
-    iDirection = (iStart == iEnd) ? ENone : (iStart > iEnd ? EDown : EUp);
+    return Ramp::FromAbi(ohp_ramp{aPod.start, aPod.end, aPod.direction, aPod.enabled});
 }
 
 bool Ramp::Set(uint32_t aStart, uint32_t aFragmentSize, uint32_t aRemainingDuration, EDirection aDirection,
                Ramp& aSplit, uint32_t& aSplitPos)
 {
-    OHP_ASSERT(aRemainingDuration >= aFragmentSize); // Msg.cpp:598
-    OHP_ASSERT(aDirection != ENone);                 // Msg.cpp:599
-    OHP_ASSERT(aRemainingDuration != 0);             // the reference divides by it
-    iEnabled = true;
-    aSplit.Reset();
-    aSplitPos = 0xffffffffu;
-
-    // How far this fragment moves the ramp: its share of what is left, rounded UP so that a ramp always
-    // completes within its duration (Msg.cpp:603-605); an overshoot of less than the fragment size is
-    // rounding, anything more is a caller bug (Msg.cpp:611, 620).
-    const uint32_t distance = (aDirection == EDown) ? aStart : kMax - aStart;
-    const uint32_t delta = (uint32_t)((distance * (uint64_t)aFragmentSize + aRemainingDuration - 1) / aRemainingDuration);
-    uint32_t end;
-    if (aDirection == EDown) {
-        if (delta > aStart) {
-            OHP_ASSERT(delta - aStart <= aFragmentSize - 1);
-            end = kMin;
-        }
-        else {
-            end = aStart - delta;
-        }
-    }
-    else {
-        if (aStart + delta > kMax) {
-            OHP_ASSERT(aStart + delta - kMax <= aFragmentSize - 1);
-            end = kMax;
-        }
-        else {
-            end = aStart + delta;
-        }
-    }
-
-    if (iDirection == ENone) {
-        iDirection = aDirection;
-        iStart = aStart;
-        iEnd = end;
-    }
-    else if (iDirection == aDirection) {
-        TakeLower(aStart, end);
-    }
-    else {
-        // Opposite directions.  Treat both as lines over x in [0, aFragmentSize]; (a0,a1) is the one starting
-        // lower.  If they cross strictly inside the fragment, the fragment becomes "rise to the crossing" and
-        // aSplit becomes "fall from the crossing" (Msg.cpp:637-699).  All in 64-bit signed, truncating division.
-        int64_t a0, a1, b0, b1;
-        if (iStart < aStart) { a0 = iStart; a1 = iEnd; b0 = aStart; b1 = end; }
-        else                 { a0 = aStart; a1 = end;  b0 = iStart; b1 = iEnd; }
-        const int64_t slopeDiff = (a1 - a0) - (b1 - b0);
-        bool crossed = false;
-        if (slopeDiff != 0) {
-            const int64_t x = ((int64_t)aFragmentSize * (b0 - a0)) / slopeDiff;
-            const int64_t y = ((a1 - a0) * (b0 - a0)) / slopeDiff + a0;
-            if (x > 0 && (uint32_t)x < aFragmentSize) {
-                crossed = true;
-                aSplitPos = (uint32_t)x;
-                aSplit.iStart = (uint32_t)y;
-                aSplit.iEnd = std::min(iEnd, end);
-                aSplit.iDirection = (aSplit.iStart == aSplit.iEnd) ? ENone : EDown;
-                aSplit.iEnabled = true;
-                const uint32_t first = std::min(iStart, aStart);
-                iStart = first;
-                iEnd = (uint32_t)y;
-                iDirection = (iStart == iEnd) ? ENone : EUp;
-            }
-        }
-        if (!crossed) {
-            TakeLower(aStart, end);
-        }
-    }
-    OHP_ASSERT(IsValid()); // Msg.cpp:701-708
-    return aSplit.IsEnabled();
+    core::RampPod r = ToPod(*this), split;
+    const int rc = core::ramp_set(r, aStart, aFragmentSize, aRemainingDuration, (uint32_t)aDirection, split, aSplitPos);
+    OHP_ASSERT(rc != core::kRampAssert); // Msg.cpp:598-599, 611, 620, 701-708
+    *this = FromPod(r);
+    aSplit = FromPod(split);
+    return rc == 1;
 }
 
 Ramp Ramp::Split(uint32_t aNewSize, uint32_t aCurrentSize)
 {
-    OHP_ASSERT(aCurrentSize != 0);
-    Ramp rest;
-    rest.iEnd = iEnd;
-    rest.iDirection = iDirection;
-    rest.iEnabled = true;
-    // proportional share, truncated; unsigned 32-bit span as in the reference (Msg.cpp:791-798)
-    if (iDirection == EUp) {
-        iEnd = iStart + (uint32_t)(((uint32_t)(iEnd - iStart) * (uint64_t)aNewSize) / aCurrentSize);
-    }
-    else {
-        iEnd = iStart - (uint32_t)(((uint32_t)(iStart - iEnd) * (uint64_t)aNewSize) / aCurrentSize);
-    }
-    if (iStart == iEnd) {
-        iDirection = ENone; // also turns the first part of a muted message into an enabled flat ramp at 0
-    }
-    rest.iStart = iEnd; // no one-step advance (the reference's FIXME, Msg.cpp:802)
-    OHP_ASSERT(IsValid());
-    OHP_ASSERT(rest.IsValid());
-    return rest;
+    core::RampPod r = ToPod(*this), rest;
+    const int rc = core::ramp_split(r, aNewSize, aCurrentSize, rest);
+    OHP_ASSERT(rc != core::kRampAssert);
+    *this = FromPod(r);
+    return FromPod(rest);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -156,9 +156,6 @@ public:
         return r;
     }
 private:
-    void TakeLower(uint32_t aStart, uint32_t aEnd);
-    bool IsValid() const;
-private:
     uint32_t iStart;
     uint32_t iEnd;
     EDirection iDirection;
