@@ -264,7 +264,26 @@ def main():
     g.manual_seed(1234 + rank)
     d_in = torch.randint(0, 256, (w.in_bytes,), dtype=torch.uint8, device="cuda", generator=g)
     d_out = torch.zeros(w.out_bytes, dtype=torch.uint8, device="cuda")
-    d_desc = torch.from_numpy(chunks.view(np.uint8).copy()).cuda()
+    # descriptors are built ON THE GPU from the stream specs and ramp events (ohp_schedule_{count,emit}_device) and
+    # checked against the host model's; the hot path below consumes the device-built array
+    d_specs = torch.from_numpy(w.streams.view(np.uint8).copy()).cuda()
+    d_events = torch.from_numpy(w.events.view(np.uint8).copy()).cuda() if len(w.events) else torch.zeros(32, dtype=torch.uint8, device="cuda")
+    d_begin = torch.zeros(len(w.streams) + 1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    t_dev = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        total = ctx.schedule_count_device(d_specs.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events), d_begin.data_ptr())
+        if _ == 0:
+            d_desc = torch.empty(max(total, 1) * abi.CHUNK_DESC.itemsize, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+        ctx.schedule_emit_device(d_specs.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events), d_begin.data_ptr(),
+                                 d_desc.data_ptr())
+        ctx.sync()
+        t_dev.append(time.perf_counter() - t0)
+    assert total == n_chunks, (total, n_chunks)
+    if not np.array_equal(d_desc.cpu().numpy()[: n_chunks * abi.CHUNK_DESC.itemsize].view(abi.CHUNK_DESC), chunks):
+        raise SystemExit("bench.py: descriptors built on the GPU differ from the host model's")
     # an explicit (non-default) stream: a NULL stream argument would select the context's own stream, and the
     # CUDA events below must sit on the stream the kernels are launched on
     torch.cuda.synchronize()
@@ -370,7 +389,9 @@ def main():
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "ms_per_step": ms}
 
     if rank == 0:
-        cfg.update({"chunks_per_step_per_gpu": n_chunks, "host_schedule_build_s": round(t_sched, 3)})
+        cfg.update({"chunks_per_step_per_gpu": n_chunks, "host_schedule_build_s": round(t_sched, 3),
+                    "device_schedule_build_s": round(min(t_dev), 4),
+                    "descriptors": "built on the GPU (ohp_schedule_count/emit_device), identical to the host model's"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg, "clocks": clocks,

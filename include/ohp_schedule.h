@@ -85,6 +85,11 @@ typedef struct ohp_schedule ohp_schedule;
 int    ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams,
                           const ohp_ramp_event* events, size_t n_events,
                           int threads, ohp_schedule** out);
+/* Same result from the class-free walk the GPU schedule kernels compile (ohpipeline_b200/host/schedule_walk.h;
+ * device entry points in ohp_schedule_device.h): no message objects, two passes (count, emit). */
+int    ohp_schedule_build_walk(const ohp_stream_spec* streams, size_t n_streams,
+                               const ohp_ramp_event* events, size_t n_events,
+                               int threads, ohp_schedule** out);
 size_t ohp_schedule_num_chunks(const ohp_schedule* s);
 const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s);
 const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s);

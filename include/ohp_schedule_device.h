@@ -1,0 +1,47 @@
+/*
+ * ohp_schedule_device.h -- C ABI of the DEVICE-side ramp-schedule builder (exported by libohp_b200.so).
+ *
+ * Same job as ohp_schedule_build (include/ohp_schedule.h) -- per-stream ramp events in, one ohp_chunk_desc per
+ * MsgPlayable out -- but the walk runs on the GPU, one thread per stream, so descriptors are born in HBM next to
+ * the kernel that consumes them (ohp_process_device).  It replaces, for a batch of independent streams,
+ *     Ramper::ProcessAudio            (OpenHome/Media/Pipeline/Ramper.cpp:114-134)
+ *     Muter::ProcessAudio             (Muter.cpp:210-262)
+ *     StarvationRamper::ProcessMsgOut / ApplyRamp (StarvationRamper.cpp:791-832, 579-603)
+ *     MsgAudio::Split / SetRamp / SetMuted        (Msg.cpp:1949-2046)      Ramp::Set / Split (Msg.cpp:590-807)
+ *     MsgAudioPcm::CreatePlayable / MsgSilence::CreatePlayable (Msg.cpp:2234-2262, 2472-2492)
+ *     MsgPlayable::Split              (Msg.cpp:2591-2624)
+ * and produces bit-identical descriptors (tests/test_gpu_schedule.py: against ohp_schedule_build and against the
+ * playables the reference itself produced, tests/golden).
+ *
+ * Two calls, because the caller owns the descriptor array and needs its size first:
+ *   1. ohp_schedule_count_device  walks every stream, counts its playables and output bytes, scans the counts into
+ *                                 d_chunk_begin[0..n_streams] and returns the total (synchronous: it reads the total
+ *                                 and the error status back).  Where the reference would ASSERT on a stream the call
+ *                                 fails with OHP_E_INVALID_DESC, for a spec the message model cannot represent with
+ *                                 OHP_E_INVALID_ARG; ohp_last_error names the stream.
+ *   2. ohp_schedule_emit_device   walks again and writes descriptor k of stream s to d_chunks[d_chunk_begin[s] + k]
+ *                                 (asynchronous on `stream`).
+ * All pointers are DEVICE pointers; d_streams / d_events / d_chunks must be 16-byte aligned.
+ */
+#ifndef OHP_SCHEDULE_DEVICE_H
+#define OHP_SCHEDULE_DEVICE_H
+
+#include "ohp_b200.h"
+#include "ohp_schedule.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                              const ohp_ramp_event* d_events, size_t n_events,
+                              uint64_t* d_chunk_begin /* n_streams + 1 */, uint64_t* d_stream_out_bytes /* n_streams, may be NULL */,
+                              uint64_t* total_chunks /* host, out */, void* stream);
+int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                             const ohp_ramp_event* d_events, size_t n_events, const uint64_t* d_chunk_begin,
+                             ohp_chunk_desc* d_chunks, ohp_chunk_info* d_info /* may be NULL */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OHP_SCHEDULE_DEVICE_H */

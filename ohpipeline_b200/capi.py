@@ -74,6 +74,13 @@ def cuda_lib():
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ohp_launch_count.restype = C.c_uint64
         L.ohp_launch_count.argtypes = [C.c_void_p]
+        if hasattr(L, "ohp_schedule_count_device"):  # include/ohp_schedule_device.h
+            L.ohp_schedule_count_device.restype = C.c_int
+            L.ohp_schedule_count_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                    C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+            L.ohp_schedule_emit_device.restype = C.c_int
+            L.ohp_schedule_emit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]
         L.ohp_set_timing.restype = C.c_int
         L.ohp_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.ohp_last_kernel_ms.restype = C.c_double
@@ -90,6 +97,8 @@ def host_lib():
         L = C.CDLL(LIB_HOST)
         L.ohp_schedule_build.restype = C.c_int
         L.ohp_schedule_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        L.ohp_schedule_build_walk.restype = C.c_int
+        L.ohp_schedule_build_walk.argtypes = L.ohp_schedule_build.argtypes
         L.ohp_schedule_num_chunks.restype = C.c_size_t
         L.ohp_schedule_num_chunks.argtypes = [C.c_void_p]
         for name in ("ohp_schedule_chunks", "ohp_schedule_chunk_info", "ohp_schedule_stream_chunk_begin",
@@ -141,14 +150,16 @@ class Schedule:
         self.stream_out_bytes = out_bytes
 
 
-def schedule_build(streams, events, threads=0):
+def schedule_build(streams, events, threads=0, walk=False):
     """Run the ramp events of every stream through the stage chain; returns a Schedule.
-    Raises OhpError(E_INVALID_DESC) where the reference would ASSERT."""
+    Raises OhpError(E_INVALID_DESC) where the reference would ASSERT.
+    walk=True: the class-free walk (ohp_schedule_build_walk), the source the GPU schedule kernels compile."""
     L = host_lib()
     streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
     events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
     h = C.c_void_p()
-    rc = L.ohp_schedule_build(_ptr(streams), len(streams), _ptr(events), len(events), threads, C.byref(h))
+    build = L.ohp_schedule_build_walk if walk else L.ohp_schedule_build
+    rc = build(_ptr(streams), len(streams), _ptr(events), len(events), threads, C.byref(h))
     if rc != 0:
         raise OhpError(rc, L.ohp_schedule_last_error().decode())
     try:
@@ -269,6 +280,60 @@ class Context:
 
     def launch_count(self):
         return int(self._L.ohp_launch_count(self._h))
+
+    # device-side schedule builder (include/ohp_schedule_device.h); all pointers are raw device addresses
+    def schedule_count_device(self, d_streams, n_streams, d_events, n_events, d_chunk_begin, d_out_bytes=0, stream=None):
+        total = C.c_uint64(0)
+        self._check(self._L.ohp_schedule_count_device(self._h, C.c_void_p(d_streams), n_streams, C.c_void_p(d_events),
+                                                      n_events, C.c_void_p(d_chunk_begin), C.c_void_p(d_out_bytes),
+                                                      C.byref(total), C.c_void_p(stream or 0)))
+        return int(total.value)
+
+    def schedule_emit_device(self, d_streams, n_streams, d_events, n_events, d_chunk_begin, d_chunks, d_info=0, stream=None):
+        self._check(self._L.ohp_schedule_emit_device(self._h, C.c_void_p(d_streams), n_streams, C.c_void_p(d_events),
+                                                     n_events, C.c_void_p(d_chunk_begin), C.c_void_p(d_chunks),
+                                                     C.c_void_p(d_info), C.c_void_p(stream or 0)))
+
+    def schedule_build_device(self, streams, events):
+        """Host-array convenience around the two calls: uploads specs and events, builds the descriptors ON THE GPU
+        and returns a Schedule of host copies (tests); production callers keep everything in HBM."""
+        streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+        events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+        ns, ne = len(streams), len(events)
+        ptrs = []
+
+        def dalloc(nbytes):
+            ptrs.append(self.device_alloc(max(int(nbytes), 16)))
+            return ptrs[-1]
+
+        try:
+            d_streams = dalloc(streams.nbytes)
+            d_events = dalloc(events.nbytes)
+            d_begin = dalloc((ns + 1) * 8)
+            d_outb = dalloc(ns * 8)
+            if ns:
+                self.memcpy_h2d(d_streams, streams.view(np.uint8).reshape(-1))
+            if ne:
+                self.memcpy_h2d(d_events, events.view(np.uint8).reshape(-1))
+            total = self.schedule_count_device(d_streams, ns, d_events, ne, d_begin, d_outb)
+            chunks = np.zeros(total, dtype=abi.CHUNK_DESC)
+            info = np.zeros(total, dtype=abi.CHUNK_INFO)
+            begin = np.zeros(ns + 1, dtype=np.uint64)
+            outb = np.zeros(ns, dtype=np.uint64)
+            d_chunks = dalloc(chunks.nbytes)
+            d_info = dalloc(info.nbytes)
+            self.schedule_emit_device(d_streams, ns, d_events, ne, d_begin, d_chunks, d_info)
+            if total:
+                self.memcpy_d2h(chunks.view(np.uint8).reshape(-1), d_chunks)
+                self.memcpy_d2h(info.view(np.uint8).reshape(-1), d_info)
+            self.memcpy_d2h(begin.view(np.uint8), d_begin)
+            if ns:
+                self.memcpy_d2h(outb.view(np.uint8), d_outb)
+            self.sync()
+        finally:
+            for q in ptrs:
+                self.device_free(q)
+        return Schedule(chunks, info, begin, outb)
 
     def set_timing(self, enabled):
         self._check(self._L.ohp_set_timing(self._h, int(bool(enabled))))

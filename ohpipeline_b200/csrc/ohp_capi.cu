@@ -4,6 +4,8 @@
 // There is no CPU fallback anywhere in this file: without a usable sm_100 device every compute entry
 // point returns OHP_E_NO_DEVICE / OHP_E_CUDA.
 #include "ohp_kernels.cuh"
+#include "ohp_schedule_kernels.cuh"
+#include "../../include/ohp_schedule_device.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -782,6 +784,83 @@ int ohp_memcpy_d2h(ohp_context* ctx, void* hptr, const void* dptr, uint64_t byte
     OHP_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     OHP_CUDA(ctx, cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, st));
+    return OHP_OK;
+}
+
+// Device-side schedule builder (include/ohp_schedule_device.h) -------------------------------------------------
+
+static int schedule_status(ohp_context* ctx, cudaStream_t st)
+{
+    // words [2], [3] of the status block belong to the schedule kernels
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t bits = ctx->h_status[2];
+    if (bits == 0) return OHP_OK;
+    const uint32_t stream_index = 0xffffffffu - ctx->h_status[3];
+    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(uint32_t), st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    char buf[160];
+    if (bits & (1u << sched::kErrSpec)) {
+        std::snprintf(buf, sizeof buf, "stream %u: spec not representable (rate, frame size, chunk size, event slice or sink)", stream_index);
+        return fail(ctx, OHP_E_INVALID_ARG, buf);
+    }
+    if (bits & (1u << sched::kErrAssert)) {
+        std::snprintf(buf, sizeof buf, "stream %u: the reference would ASSERT on this schedule", stream_index);
+        return fail(ctx, OHP_E_INVALID_DESC, buf);
+    }
+    std::snprintf(buf, sizeof buf, "stream %u: more than %d pending message splits in one stage", stream_index, sched::kStackDepth);
+    return fail(ctx, OHP_E_NO_MEMORY, buf);
+}
+
+int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                              const ohp_ramp_event* d_events, size_t n_events, uint64_t* d_chunk_begin,
+                              uint64_t* d_stream_out_bytes, uint64_t* total_chunks, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (!total_chunks) return fail(ctx, OHP_E_INVALID_ARG, "null total_chunks");
+    *total_chunks = 0;
+    if (!d_chunk_begin || (n_streams && !d_streams) || (n_events && !d_events)) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    sched::ScheduleParams p{};
+    p.streams = d_streams; p.n_streams = n_streams; p.events = d_events; p.n_events = n_events;
+    p.chunk_count = d_chunk_begin; p.out_bytes = d_stream_out_bytes;
+    p.status = ctx->d_status + 2;
+    if (n_streams) {
+        sched::schedule_kernel<false><<<(unsigned)((n_streams + 31) / 32), 32, 0, st>>>(p);
+        OHP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    sched::scan_kernel<<<1, 1024, 0, st>>>(d_chunk_begin, n_streams);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    uint64_t* h_total = reinterpret_cast<uint64_t*>(ctx->h_status + 14); // 8-byte aligned tail of the pinned status block
+    OHP_CUDA(ctx, cudaMemcpyAsync(h_total, d_chunk_begin + n_streams, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t total = *h_total;
+    const int rc = schedule_status(ctx, st);
+    if (rc != OHP_OK) return rc;
+    *total_chunks = total;
+    return OHP_OK;
+}
+
+int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                             const ohp_ramp_event* d_events, size_t n_events, const uint64_t* d_chunk_begin,
+                             ohp_chunk_desc* d_chunks, ohp_chunk_info* d_info, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (n_streams == 0) return OHP_OK;
+    if (!d_streams || !d_chunk_begin || !d_chunks || (n_events && !d_events)) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    if (reinterpret_cast<uint64_t>(d_chunks) & 15u) return fail(ctx, OHP_E_INVALID_ARG, "descriptor array must be 16-byte aligned");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    sched::ScheduleParams p{};
+    p.streams = d_streams; p.n_streams = n_streams; p.events = d_events; p.n_events = n_events;
+    p.chunk_begin = d_chunk_begin; p.descs = d_chunks; p.info = d_info;
+    p.status = ctx->d_status + 2;
+    sched::schedule_kernel<true><<<(unsigned)((n_streams + 31) / 32), 32, 0, st>>>(p);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
     return OHP_OK;
 }
 

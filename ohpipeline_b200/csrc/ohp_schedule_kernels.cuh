@@ -1,0 +1,90 @@
+// ohp_schedule_kernels.cuh -- device-side ramp-schedule builder: per-stream ramp events -> chunk
+// descriptors, on the GPU, so that the only host-serial step in front of ramp_convert_kernel disappears.
+//
+// ONE THREAD WALKS ONE STREAM (host/schedule_walk.h, which also compiles for the host so the CPU suite can test it).
+// A stream is strictly sequential -- every message's ramp starts where the previous one ended -- and streams are
+// independent, so the parallelism is across streams.  Two passes over the same walk: COUNT (chunks and
+// output bytes per stream), an exclusive scan, then EMIT (descriptors written at each stream's offset).  All integer;
+// the result is bit-identical to ohp_schedule_build (host) and to the reference's playables (tests/golden).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../host/schedule_walk.h"
+
+namespace ohp {
+namespace sched {
+
+struct ScheduleParams
+{
+    const ohp_stream_spec* streams;
+    uint64_t n_streams;
+    const ohp_ramp_event* events;
+    uint64_t n_events;
+    uint64_t* chunk_count;     // COUNT: [n_streams] chunks per stream (scanned in place into chunk_begin afterwards)
+    uint64_t* out_bytes;       // COUNT: [n_streams] output bytes per stream (may be null)
+    const uint64_t* chunk_begin; // EMIT: [n_streams + 1]
+    ohp_chunk_desc* descs;     // EMIT
+    ohp_chunk_info* info;      // EMIT, may be null
+    uint32_t* status;          // [0] error bits (1 << code), [1] 0xffffffff - lowest failing stream (atomicMax; 0 = none)
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(32) schedule_kernel(const ScheduleParams p)
+{
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n_streams) return;
+    const ohp_stream_spec sp = p.streams[s];
+    uint64_t nChunks, outBytes;
+    ohp_chunk_desc* descs = EMIT ? p.descs + p.chunk_begin[s] : nullptr;
+    ohp_chunk_info* info = (EMIT && p.info) ? p.info + p.chunk_begin[s] : nullptr;
+    const uint32_t rc = run_stream<EMIT>(sp, p.events, p.n_events, descs, info, nChunks, outBytes);
+    if (rc != kOk) {
+        atomicOr(&p.status[0], 1u << rc);
+        atomicMax(&p.status[1], 0xffffffffu - (uint32_t)(s > 0xfffffffeull ? 0xfffffffeull : s));
+    }
+    if (!EMIT) {
+        p.chunk_count[s] = nChunks;
+        if (p.out_bytes) p.out_bytes[s] = outBytes;
+    }
+}
+
+// In-place exclusive scan of counts[0..n) into begin[0..n] (begin has n+1 entries; begin[n] = total).  One CTA.
+__global__ void __launch_bounds__(1024) scan_kernel(uint64_t* begin, uint64_t n)
+{
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < n ? begin[i] : 0;
+        uint64_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= (uint32_t)o) w += y;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t before = carry + (warp ? warp_sum[warp - 1] : 0) + (x - v);
+        if (i < n) begin[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) begin[n] = carry;
+}
+
+} // namespace sched
+} // namespace ohp

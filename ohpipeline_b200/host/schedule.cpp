@@ -5,6 +5,7 @@
 // independent, so no synchronisation beyond the final gather.
 #include "msg_model.h"
 #include "stage_chain.h"
+#include "schedule_walk.h"
 
 #include <string>
 #include <thread>
@@ -156,6 +157,68 @@ int ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams, const o
         std::vector<ohp_chunk_info>().swap(recs[s].info);
     }
     sch->chunkBegin[n_streams] = sch->chunks.size();
+    *out = sch;
+    return OHP_OK;
+}
+
+// The class-free walk (schedule_walk.h) on host threads: the same source the GPU schedule kernels compile, so the CPU
+// suite can pin it against the class-based model above (and against the reference's playables) without a GPU.
+int ohp_schedule_build_walk(const ohp_stream_spec* streams, size_t n_streams, const ohp_ramp_event* events, size_t n_events,
+                            int threads, ohp_schedule** out)
+{
+    if (!out || (!streams && n_streams) || (!events && n_events)) {
+        g_error = "null argument";
+        return OHP_E_INVALID_ARG;
+    }
+    *out = nullptr;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if ((size_t)threads > n_streams) threads = (int)(n_streams ? n_streams : 1);
+    ohp_schedule* sch = new ohp_schedule();
+    sch->chunkBegin.assign(n_streams + 1, 0);
+    sch->outBytes.assign(n_streams, 0);
+    std::vector<uint32_t> rcs(n_streams, 0);
+    auto run = [&](bool emit) {
+        auto worker = [&](int t) {
+            const size_t lo = n_streams * (size_t)t / (size_t)threads;
+            const size_t hi = n_streams * (size_t)(t + 1) / (size_t)threads;
+            for (size_t s = lo; s < hi; s++) {
+                uint64_t n = 0, bytes = 0;
+                if (emit) {
+                    rcs[s] = sched::run_stream<true>(streams[s], events, n_events, sch->chunks.data() + sch->chunkBegin[s],
+                                                     sch->info.data() + sch->chunkBegin[s], n, bytes);
+                }
+                else {
+                    rcs[s] = sched::run_stream<false>(streams[s], events, n_events, nullptr, nullptr, n, bytes);
+                    sch->chunkBegin[s + 1] = n; // scanned below
+                    sch->outBytes[s] = bytes;
+                }
+            }
+        };
+        if (threads == 1) {
+            worker(0);
+        }
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+            for (auto& th : pool) th.join();
+        }
+    };
+    run(false);
+    for (size_t s = 0; s < n_streams; s++) {
+        if (rcs[s] != sched::kOk) {
+            g_error = "stream " + std::to_string(s) + (rcs[s] == sched::kErrAssert ? ": the reference would ASSERT on this schedule"
+                                                        : rcs[s] == sched::kErrSpec ? ": spec not representable"
+                                                                                    : ": too many pending message splits");
+            const int rc = rcs[s] == sched::kErrAssert ? OHP_E_INVALID_DESC : (rcs[s] == sched::kErrSpec ? OHP_E_INVALID_ARG : OHP_E_NO_MEMORY);
+            delete sch;
+            return rc;
+        }
+    }
+    for (size_t s = 0; s < n_streams; s++) sch->chunkBegin[s + 1] += sch->chunkBegin[s];
+    sch->chunks.resize(sch->chunkBegin[n_streams]);
+    sch->info.resize(sch->chunkBegin[n_streams]);
+    run(true);
     *out = sch;
     return OHP_OK;
 }

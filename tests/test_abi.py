@@ -25,6 +25,14 @@ def test_cuda_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
 
 
+def test_cuda_library_exports_the_device_schedule_builder():
+    lib = capi.cuda_lib()
+    names = declared_functions("ohp_schedule_device.h")
+    assert names == ["ohp_schedule_count_device", "ohp_schedule_emit_device"]
+    for n in names:
+        assert hasattr(lib, n), n
+
+
 def test_host_library_exports_every_declared_symbol():
     lib = capi.host_lib()
     names = declared_functions("ohp_schedule.h")

@@ -1,0 +1,161 @@
+"""Device-side schedule builder (include/ohp_schedule_device.h) against
+  * the playables the REFERENCE produced (tests/golden/*.npz, recorded from oracle/_ref), and
+  * the host message model (ohp_schedule_build), on the BASELINE configs and on randomized mixed workloads:
+descriptors, chunk info (direction, jiffies), per-stream chunk ranges and output sizes must be identical.
+Then the descriptors built on the GPU drive the hot path and the bytes are checked against the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from ohpipeline_b200 import abi, capi, workloads
+from util import covered_mask
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(g for g in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not g.endswith("ramp_algebra.npz"))
+
+
+def same_schedule(dev, host):
+    assert len(dev.chunks) == len(host.chunks)
+    assert np.array_equal(dev.stream_chunk_begin, host.stream_chunk_begin)
+    assert np.array_equal(dev.stream_out_bytes, host.stream_out_bytes)
+    if not np.array_equal(dev.chunks, host.chunks):
+        i = int(np.nonzero(dev.chunks != host.chunks)[0][0])
+        raise AssertionError("descriptor %d differs: device %s host %s" % (i, dev.chunks[i], host.chunks[i]))
+    assert np.array_equal(dev.info, host.info)
+
+
+def check_both(ctx, w):
+    """Device walk vs host model: identical schedules, or the same refusal where the reference would ASSERT."""
+    try:
+        host = capi.schedule_build(w.streams, w.events)
+    except capi.OhpError as eh:
+        with pytest.raises(capi.OhpError) as ed:
+            ctx.schedule_build_device(w.streams, w.events)
+        assert ed.value.status == eh.status
+        return None
+    same_schedule(ctx.schedule_build_device(w.streams, w.events), host)
+    return host
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_device_schedule_reproduces_reference_playables(ctx, path):
+    g = np.load(path)
+    dev = ctx.schedule_build_device(g["streams"], g["events"])
+    assert np.array_equal(dev.chunks, g["chunks"]), "descriptors differ from the reference's playables"
+    assert np.array_equal(dev.info, g["info"])
+
+
+@pytest.mark.parametrize("make", [
+    lambda: workloads.config1(6.2),
+    lambda: workloads.config2(n_streams=40, seconds=0.5),
+    lambda: workloads.config3(n_streams=70, seconds=1.0),
+    lambda: workloads.config5(n_streams=100, seconds=0.25),
+], ids=["config1", "config2", "config3", "config5"])
+def test_device_schedule_matches_host_on_baseline_configs(ctx, make):
+    assert check_both(ctx, make()) is not None
+
+
+@pytest.mark.parametrize("seed", [4, 11, 12, 13, 14, 15, 16, 17])
+def test_device_schedule_matches_host_on_mixed_workloads(ctx, seed):
+    assert check_both(ctx, workloads.mixed(n_streams=96, seed=seed, max_frames=5000)) is not None
+
+
+def test_device_schedule_many_streams(ctx):
+    """More streams than one wave of threads; ragged event slices; one partial warp."""
+    assert check_both(ctx, workloads.mixed(n_streams=3001, seed=22, max_frames=700)) is not None
+    # seed 21 holds a stream on which the reference ASSERTs (a MsgSilence split below one sample): same refusal
+    assert check_both(ctx, workloads.mixed(n_streams=3001, seed=21, max_frames=700)) is None
+
+
+def test_device_schedule_empty_and_degenerate(ctx):
+    none = ctx.schedule_build_device(np.zeros(0, dtype=abi.STREAM_SPEC), np.zeros(0, dtype=abi.RAMP_EVENT))
+    assert len(none.chunks) == 0 and list(none.stream_chunk_begin) == [0]
+    # a stream without audio produces nothing; its neighbours are unaffected
+    w = workloads.config5(n_streams=3, seconds=0.02)
+    w.streams["total_frames"][1] = 0
+    same_schedule(ctx.schedule_build_device(w.streams, w.events), capi.schedule_build(w.streams, w.events))
+
+
+def test_device_schedule_fails_where_the_host_model_fails(ctx):
+    w = workloads.config5(n_streams=4, seconds=0.02)
+    # unsupported sample rate: Jiffies::PerSample throws SampleRateInvalid (Msg.cpp:424-470) -> not representable
+    bad = w.streams.copy()
+    bad["sample_rate"][2] = 12345
+    with pytest.raises(capi.OhpError) as e:
+        ctx.schedule_build_device(bad, w.events)
+    assert e.value.status == abi.E_INVALID_ARG and "stream 2" in str(e.value)
+    with pytest.raises(capi.OhpError) as eh:
+        capi.schedule_build(bad, w.events)
+    assert eh.value.status == abi.E_INVALID_ARG
+    # bit depth the reference ASSERTs on (DecodedAudio::ConstructPcm, Msg.cpp:349-366)
+    bad = w.streams.copy()
+    bad["bit_depth"][1] = 20
+    with pytest.raises(capi.OhpError) as e:
+        ctx.schedule_build_device(bad, w.events)
+    with pytest.raises(capi.OhpError) as eh:
+        capi.schedule_build(bad, w.events)
+    assert e.value.status == eh.value.status
+    # a converting sink is not a schedule output
+    bad = w.streams.copy()
+    bad["out_fmt"][0] = abi.OUT_PLANAR32_BE
+    with pytest.raises(capi.OhpError) as e:
+        ctx.schedule_build_device(bad, w.events)
+    assert e.value.status == abi.E_INVALID_ARG
+    # event slice outside the events array
+    bad = w.streams.copy()
+    bad["first_event"][3] = len(w.events)
+    bad["num_events"][3] = 1
+    with pytest.raises(capi.OhpError) as e:
+        ctx.schedule_build_device(bad, w.events)
+    assert e.value.status == abi.E_INVALID_ARG
+    # the context is still usable afterwards
+    same_schedule(ctx.schedule_build_device(w.streams, w.events), capi.schedule_build(w.streams, w.events))
+
+
+def test_silence_split_below_one_sample_asserts_on_both(ctx):
+    """A MsgSilence split below one sample leaves a zero-length first part on which Ramp::Set ASSERTs (DESIGN.md
+    'reference behaviours' #5): host model and device walk must both report it."""
+    rate = 44100
+    jps = abi.jiffies_per_sample(rate)
+    s = np.zeros(1, dtype=abi.STREAM_SPEC)
+    s[0]["sample_rate"] = rate; s[0]["bit_depth"] = 16; s[0]["channels"] = 2; s[0]["chunk_frames"] = 100
+    s[0]["total_frames"] = 400; s[0]["num_events"] = 2
+    ev = np.zeros(2, dtype=abi.RAMP_EVENT)
+    ev[0] = (0, 0, abi.EV_INSERT_SILENCE, 10 * jps, 0)
+    ev[1] = (0, 0, abi.EV_RAMP_DOWN, jps // 2, 0)     # remaining < one sample: Split(remaining) on silence
+    with pytest.raises(capi.OhpError) as eh:
+        capi.schedule_build(s, ev)
+    with pytest.raises(capi.OhpError) as ed:
+        ctx.schedule_build_device(s, ev)
+    assert ed.value.status == eh.value.status == abi.E_INVALID_DESC
+
+
+def test_descriptors_built_on_the_gpu_drive_the_hot_path(ctx, port):
+    """events -> (GPU) descriptors -> (GPU) ramp + convert, nothing but specs and PCM crossing PCIe; bytes vs oracle."""
+    import torch
+    w = workloads.mixed(n_streams=64, seed=31, max_frames=4000)
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    rc, want, chunks, _ = port.run(w.streams, w.events, inp, w.out_bytes)
+    assert rc == 0
+    d_streams = torch.from_numpy(w.streams.view(np.uint8).copy()).cuda()
+    d_events = torch.from_numpy(w.events.view(np.uint8).copy()).cuda()
+    d_begin = torch.zeros(len(w.streams) + 1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()  # the context's stream does not order against torch's
+    total = ctx.schedule_count_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events),
+                                      d_begin.data_ptr())
+    assert total == len(chunks)
+    d_desc = torch.zeros(total * abi.CHUNK_DESC.itemsize, dtype=torch.uint8, device="cuda")
+    ctx.schedule_emit_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events),
+                             d_begin.data_ptr(), d_desc.data_ptr())
+    d_in = torch.from_numpy(inp).cuda()
+    d_out = torch.zeros(w.out_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.process_device(d_desc.data_ptr(), total, d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes)
+    ctx.sync()
+    got = d_out.cpu().numpy()
+    mask = covered_mask(chunks, w.out_bytes)
+    assert np.array_equal(got[mask], want[mask])
