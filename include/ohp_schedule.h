@@ -19,6 +19,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "ohp_b200.h"
+#include "ohp_flywheel.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -99,6 +100,17 @@ const uint64_t* ohp_schedule_stream_chunk_begin(const ohp_schedule* s);
 const uint64_t* ohp_schedule_stream_out_bytes(const ohp_schedule* s);
 const char* ohp_schedule_last_error(void);
 void   ohp_schedule_free(ohp_schedule* s);
+
+/*
+ * RampGenerator::Start + EndBlock (Media/Pipeline/StarvationRamper.cpp:235-247, 351-364): the generated flywheel audio
+ * of `job` (ohp_flywheel.h), resident at [src_off, ...) of the ramp pass's input arena, leaves as one MsgAudioPcm per
+ * 1 ms block, ramped down from current_ramp over the whole generated length (SetMuted once the ramp has reached
+ * Ramp::kMin).  Writes one descriptor per block to out[0..cap) with dst_off advancing from `dst_off`; returns their
+ * number, or a negative ohp_status (-OHP_E_INVALID_DESC where the reference would ASSERT, -OHP_E_NO_MEMORY when cap is
+ * too small).  *final_ramp (may be NULL) = RampGenerator::iCurrentRampValue afterwards.
+ */
+int    ohp_flywheel_ramp_chunks(const ohp_flywheel_job* job, uint32_t current_ramp, uint64_t src_off, uint64_t dst_off,
+                                ohp_chunk_desc* out, size_t cap, uint32_t* final_ramp);
 
 /* Scalar helpers mirroring the reference (exported for binding-level tests) ------------------- */
 /* Jiffies::PerSample (Msg.cpp:424-470); 0 for an unsupported rate (the reference throws SampleRateInvalid). */

@@ -52,6 +52,16 @@ assert CHUNK_DESC.itemsize == 32
 
 CHUNK_INFO = np.dtype([("direction", "<u4"), ("jiffies", "<u4")])
 
+# include/ohp_flywheel.h
+FLYWHEEL_JOB = np.dtype([
+    ("src_off", "<u8"), ("dst_off", "<u8"), ("sample_rate", "<u4"), ("out_frames", "<u4"),
+    ("train_frames", "<u2"), ("channels", "u1"), ("bit_depth", "u1"), ("reserved", "<u4"),
+])
+assert FLYWHEEL_JOB.itemsize == 32
+FLYWHEEL_DEGREE = 3
+FLYWHEEL_TRAINING_JIFFIES = 56448      # StarvationRamper::kTrainingJiffies (StarvationRamper.cpp:374)
+FLYWHEEL_RAMP_JIFFIES = 20 * 56448     # StarvationRamper::kRampDownJiffies (StarvationRamper.cpp:375)
+
 RAMP_EVENT = np.dtype([
     ("at_jiffies", "<u8"), ("stage", "<u4"), ("op", "<u4"), ("arg", "<u4"), ("reserved", "<u4"),
 ])

@@ -74,6 +74,14 @@ def cuda_lib():
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ohp_launch_count.restype = C.c_uint64
         L.ohp_launch_count.argtypes = [C.c_void_p]
+        if hasattr(L, "ohp_flywheel_device"):  # include/ohp_flywheel.h
+            L.ohp_flywheel_out_bytes.restype = C.c_uint32
+            L.ohp_flywheel_out_bytes.argtypes = [C.c_void_p]
+            L.ohp_flywheel_validate.restype = C.c_int
+            L.ohp_flywheel_validate.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.POINTER(C.c_size_t)]
+            L.ohp_flywheel_device.restype = C.c_int
+            L.ohp_flywheel_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                              C.c_void_p]
         if hasattr(L, "ohp_schedule_count_device"):  # include/ohp_schedule_device.h
             L.ohp_schedule_count_device.restype = C.c_int
             L.ohp_schedule_count_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
@@ -99,6 +107,9 @@ def host_lib():
         L.ohp_schedule_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
         L.ohp_schedule_build_walk.restype = C.c_int
         L.ohp_schedule_build_walk.argtypes = L.ohp_schedule_build.argtypes
+        L.ohp_flywheel_ramp_chunks.restype = C.c_int
+        L.ohp_flywheel_ramp_chunks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t,
+                                               C.POINTER(C.c_uint32)]
         L.ohp_schedule_num_chunks.restype = C.c_size_t
         L.ohp_schedule_num_chunks.argtypes = [C.c_void_p]
         for name in ("ohp_schedule_chunks", "ohp_schedule_chunk_info", "ohp_schedule_stream_chunk_begin",
@@ -138,6 +149,34 @@ def ramp_split(ramp, new_size, current_size):
     rem = np.zeros(1, dtype=abi.RAMP)
     rc = host_lib().ohp_ramp_split(_ptr(r), new_size, current_size, _ptr(rem))
     return rc, tuple(int(x) for x in r[0]), tuple(int(x) for x in rem[0])
+
+
+def flywheel_ramp_chunks(job, current_ramp, src_off, dst_off):
+    """RampGenerator::Start/EndBlock for one flywheel job: (descriptors, final ramp value).
+    Raises OhpError where the reference would ASSERT."""
+    job = np.ascontiguousarray(job, dtype=abi.FLYWHEEL_JOB).reshape(1)
+    descs = np.zeros(64, dtype=abi.CHUNK_DESC)
+    final = C.c_uint32(0)
+    n = host_lib().ohp_flywheel_ramp_chunks(_ptr(job), current_ramp, src_off, dst_off, _ptr(descs), len(descs), C.byref(final))
+    if n < 0:
+        raise OhpError(-n, host_lib().ohp_schedule_last_error().decode())
+    return descs[:n].copy(), int(final.value)
+
+
+def flywheel_validate(jobs, in_bytes, out_bytes):
+    """ohp_flywheel_validate; returns (status, bad_index)."""
+    jobs = np.ascontiguousarray(jobs, dtype=abi.FLYWHEEL_JOB)
+    bad = C.c_size_t(0)
+    rc = cuda_lib().ohp_flywheel_validate(_ptr(jobs), len(jobs), in_bytes, out_bytes, C.byref(bad))
+    return int(rc), int(bad.value)
+
+
+def flywheel_job(rate, channels, bits, src_off=0, dst_off=0):
+    """A job shaped like StarvationRamper's: 1 ms of training, 20 ms of generated audio."""
+    jps = abi.jiffies_per_sample(rate)
+    j = np.zeros(1, dtype=abi.FLYWHEEL_JOB)
+    j[0] = (src_off, dst_off, rate, abi.FLYWHEEL_RAMP_JIFFIES // jps, abi.FLYWHEEL_TRAINING_JIFFIES // jps, channels, bits, 0)
+    return j
 
 
 class Schedule:
@@ -280,6 +319,11 @@ class Context:
 
     def launch_count(self):
         return int(self._L.ohp_launch_count(self._h))
+
+    def flywheel_device(self, d_jobs, n, d_in, in_bytes, d_out, out_bytes, stream=None):
+        """Asynchronous: FlywheelRamperManager::Ramp + RampGenerator::ProcessFragment for n jobs (device pointers)."""
+        self._check(self._L.ohp_flywheel_device(self._h, C.c_void_p(d_jobs), n, C.c_void_p(d_in), in_bytes,
+                                                C.c_void_p(d_out), out_bytes, C.c_void_p(stream or 0)))
 
     # device-side schedule builder (include/ohp_schedule_device.h); all pointers are raw device addresses
     def schedule_count_device(self, d_streams, n_streams, d_events, n_events, d_chunk_begin, d_out_bytes=0, stream=None):

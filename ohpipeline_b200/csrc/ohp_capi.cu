@@ -5,6 +5,7 @@
 // point returns OHP_E_NO_DEVICE / OHP_E_CUDA.
 #include "ohp_kernels.cuh"
 #include "ohp_schedule_kernels.cuh"
+#include "ohp_flywheel_kernels.cuh"
 #include "../../include/ohp_schedule_device.h"
 
 #include <cstdio>
@@ -465,6 +466,16 @@ static int read_status(ohp_context* ctx, cudaStream_t st)
 {
     OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t fly_bits = ctx->h_status[12];
+    if (fly_bits != 0) {
+        // words [12], [13] belong to the flywheel kernel
+        const uint32_t job = ctx->h_status[13];
+        OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status + 12, 0, 2 * sizeof(uint32_t), st));
+        OHP_CUDA(ctx, cudaStreamSynchronize(st));
+        char fbuf[128];
+        std::snprintf(fbuf, sizeof fbuf, "device rejected flywheel job %u (%s)", job - 1, (fly_bits & 1u) ? "invalid" : "out of range");
+        return fail(ctx, (fly_bits & 1u) ? OHP_E_INVALID_DESC : OHP_E_OUT_OF_RANGE, fbuf);
+    }
     const uint32_t bits = ctx->h_status[0];
     if (bits == 0) return OHP_OK;
     const uint32_t first = ctx->h_status[1];
@@ -859,6 +870,46 @@ int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams,
     p.chunk_begin = d_chunk_begin; p.descs = d_chunks; p.info = d_info;
     p.status = ctx->d_status + 2;
     sched::schedule_kernel<true><<<(unsigned)((n_streams + 31) / 32), 32, 0, st>>>(p);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return OHP_OK;
+}
+
+// Flywheel ramp generator (include/ohp_flywheel.h) ---------------------------------------------------------------
+
+uint32_t ohp_flywheel_out_bytes(const ohp_flywheel_job* job)
+{
+    if (!job) return 0;
+    return job->out_frames * job->channels * (job->bit_depth / 8u);
+}
+
+int ohp_flywheel_validate(const ohp_flywheel_job* jobs, size_t n, uint64_t in_bytes, uint64_t out_bytes, size_t* bad_index)
+{
+    if (!jobs && n) return OHP_E_INVALID_ARG;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t err = fly::check_job(jobs[i], in_bytes, out_bytes);
+        if (err) {
+            if (bad_index) *bad_index = i;
+            return err == 1u ? OHP_E_INVALID_DESC : OHP_E_OUT_OF_RANGE;
+        }
+    }
+    return OHP_OK;
+}
+
+int ohp_flywheel_device(ohp_context* ctx, const ohp_flywheel_job* d_jobs, size_t n, const uint8_t* d_in, uint64_t in_bytes,
+                        uint8_t* d_out, uint64_t out_bytes, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (n == 0) return OHP_OK;
+    if (!d_jobs || !d_in || !d_out) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    if (reinterpret_cast<uint64_t>(d_jobs) & 15u) return fail(ctx, OHP_E_INVALID_ARG, "job array must be 16-byte aligned");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    fly::FlywheelParams p;
+    p.jobs = d_jobs; p.n = n; p.in = d_in; p.in_bytes = in_bytes; p.out = d_out; p.out_bytes = out_bytes;
+    p.status = ctx->d_status + 12;
+    const uint64_t grid = (n + fly::kWarpsPerCta - 1) / fly::kWarpsPerCta;
+    fly::flywheel_kernel<<<(unsigned)grid, fly::kWarpsPerCta * 32, 0, st>>>(p);
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return OHP_OK;

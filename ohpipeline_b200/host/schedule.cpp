@@ -231,6 +231,53 @@ const uint64_t* ohp_schedule_stream_out_bytes(const ohp_schedule* s) { return s 
 const char* ohp_schedule_last_error(void) { return g_error.c_str(); }
 void ohp_schedule_free(ohp_schedule* s) { delete s; }
 
+int ohp_flywheel_ramp_chunks(const ohp_flywheel_job* job, uint32_t current_ramp, uint64_t src_off, uint64_t dst_off,
+                             ohp_chunk_desc* out, size_t cap, uint32_t* final_ramp)
+{
+    if (!job || (!out && cap)) return -OHP_E_INVALID_ARG;
+    try {
+        // RampGenerator::Start (StarvationRamper.cpp:235-247)
+        const uint32_t jps = Jiffies::PerSample(job->sample_rate);
+        const uint32_t frameBytes = job->channels * (job->bit_depth / 8u);
+        const uint32_t blockFrames = OHP_FLYWHEEL_BLOCK_JIFFIES / jps;
+        uint32_t remainingRamp = jps * job->out_frames;
+        uint32_t remaining = job->out_frames;
+        MsgFactory factory;
+        size_t n = 0;
+        while (remaining > 0) {
+            const uint32_t frames = remaining > blockFrames ? blockFrames : remaining;
+            remaining -= frames;
+            if (n == cap) return -OHP_E_NO_MEMORY;
+            // RampGenerator::EndBlock (StarvationRamper.cpp:351-364)
+            MsgAudioPcm* audio = factory.CreateMsgAudioPcm(src_off, frames * frameBytes, job->channels, job->sample_rate,
+                                                           job->bit_depth, AudioDataEndian::Big, MsgAudioPcm::kTrackOffsetInvalid);
+            if (current_ramp == Ramp::kMin) {
+                audio->SetMuted();
+            }
+            else {
+                MsgAudio* split = nullptr;
+                current_ramp = audio->SetRamp(current_ramp, remainingRamp, Ramp::EDown, split);
+                if (split != nullptr) {
+                    split->RemoveRef();
+                    audio->RemoveRef();
+                    OHP_ASSERT(false); // ASSERT(split == nullptr), StarvationRamper.cpp:359
+                }
+            }
+            MsgPlayable* playable = audio->CreatePlayable();
+            out[n++] = playable->Descriptor(dst_off, OHP_OUT_PACKED_BE);
+            src_off += playable->Bytes();
+            dst_off += playable->Bytes();
+            playable->RemoveRef();
+        }
+        if (final_ramp) *final_ramp = current_ramp;
+        return (int)n;
+    }
+    catch (const std::exception& e) {
+        g_error = e.what();
+        return -OHP_E_INVALID_DESC;
+    }
+}
+
 uint32_t ohp_jiffies_per_sample(uint32_t sample_rate) { return Jiffies::PerSampleOrZero(sample_rate); }
 
 int ohp_ramp_set(ohp_ramp* ramp, uint32_t start, uint32_t fragment_size, uint32_t remaining_duration, uint32_t direction,

@@ -917,3 +917,261 @@ void ohpo_fill_pcm(uint8_t* dst, uint64_t bytes, uint64_t seed)
         for (int k = 0; k < 8 && i < bytes; k++, i++) dst[i] = (uint8_t)(z >> (8 * k));
     }
 }
+
+/* ==================================================================================================================
+ * Flywheel ramp generator: Media/FlywheelRamper.cpp + RampGenerator (Media/Pipeline/StarvationRamper.cpp).
+ * The reference computes in TInt16 / TInt32 with wrap-around on overflow (two's complement on every target it
+ * builds for); the sums below are done in unsigned arithmetic and cast back so that C leaves nothing undefined. */
+
+static int16_t wrap16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
+static int32_t mul32(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+
+void ohpo_burgs_method(const int16_t* samples, uint32_t n, uint32_t degree, int16_t* output, int16_t* h,
+                       int16_t* per, int16_t* pef)
+{
+    /* FlywheelRamper::BurgsMethod, FlywheelRamper.cpp:253-328; kBurgScaleShift = 16 - kBurgOutputFormat = 13 (:11-12) */
+    const uint32_t shift = 13;
+    uint32_t limit1 = n - 1;
+    uint32_t limit2 = limit1;
+    for (uint32_t k = 0; k < degree; k++) {
+        uint32_t sn = 0, sd = 0; /* TInt32 accumulators, :260-261 */
+        for (uint32_t j = 0; j < limit1; j++) {
+            const int16_t t1 = wrap16((int32_t)samples[j + k + 1] + pef[j]); /* :265 */
+            const int16_t t2 = wrap16((int32_t)samples[j] + per[j]);         /* :266 */
+            const int32_t t1t1 = (int32_t)t1 * t1;
+            const int32_t t2t2 = (int32_t)t2 * t2;
+            const int32_t t1t2 = (int32_t)t1 * t2;
+            sn -= 2u * (uint32_t)t1t2;                     /* :270 */
+            sd += (uint32_t)t1t1 + (uint32_t)t2t2;         /* :271 */
+        }
+        limit1--;
+        int16_t t3 = 0;
+        if ((int32_t)sn != 0) {
+            /* :278-282.  sd == 0 with sn != 0 needs the accumulator to wrap to exactly zero; the reference would
+             * divide by zero there -- t3 stays 0 in this restatement (documented deviation). */
+            if ((int32_t)sd != 0) {
+                const int64_t ratio = (int64_t)((uint64_t)(int64_t)(int32_t)sn << shift) / (int64_t)(int32_t)sd;
+                t3 = (int16_t)(uint16_t)(uint64_t)ratio;
+            }
+        }
+        output[k] = t3;
+        if (k > 0) {
+            for (uint32_t j = 0; j < k; j++) {
+                const int32_t prod = (int32_t)t3 * output[k - j - 1];              /* :290 */
+                h[j] = wrap16(prod >> shift);                                       /* :291 */
+                h[j] = wrap16((int32_t)h[j] + output[j]);                           /* :292 */
+            }
+            for (uint32_t j = 0; j < k; j++) output[j] = h[j];
+            limit2--;
+        }
+        if (k == degree - 1) break;
+        for (uint32_t j = 0; j < limit2; j++) {
+            const uint32_t i = j + 1;
+            int32_t p = (int32_t)pef[j] + samples[i + k];                           /* :312 */
+            p = mul32(p, t3);
+            per[j] = wrap16((int32_t)per[j] + wrap16(p >> shift));                  /* :314 */
+            int32_t f = (int32_t)per[i] + samples[i];                               /* :316 */
+            f = mul32(f, t3);
+            pef[j] = wrap16(f >> shift);                                            /* :318 */
+            pef[j] = wrap16((int32_t)pef[j] + pef[i]);                              /* :319 */
+        }
+    }
+}
+
+int16_t ohpo_coeff_overflow(const int16_t* coeffs, uint32_t count, uint32_t format)
+{
+    /* FlywheelRamper::CoeffOverflow, FlywheelRamper.cpp:355-388 */
+    const int16_t one = (int16_t)(1 << (16 - format));
+    int16_t total = 0;
+    for (uint32_t j = 0; j < count; j++) total = wrap16((int32_t)total + coeffs[j]);
+    if (total <= one && total >= -one) return 0;
+    if (total & 0x8000) return wrap16((int32_t)total + one);
+    return wrap16((int32_t)total - one);
+}
+
+void ohpo_feedback_init(ohpo_feedback* f, uint32_t state_count, uint32_t descale_bits, uint32_t coeff_format,
+                        uint32_t data_format, uint32_t output_format, int32_t* coeffs, int32_t* samples)
+{
+    /* FeedbackModel::FeedbackModel + Initialise, FlywheelRamper.cpp:420-445 */
+    f->coeffs = coeffs;
+    f->samples = samples;
+    f->state_count = state_count;
+    f->descale_bits = descale_bits;
+    f->coeff_format = coeff_format;
+    f->scale_shift_for_output = (int32_t)(data_format + descale_bits) - (int32_t)output_format;
+    for (uint32_t j = 0; j < state_count; j++) samples[j] >>= descale_bits;
+}
+
+int32_t ohpo_feedback_next(ohpo_feedback* f)
+{
+    /* FeedbackModel::NextSample, FlywheelRamper.cpp:447-487 */
+    uint32_t sum = 0;
+    for (uint32_t j = 0; j < f->state_count; j++) {
+        const int64_t product = (int64_t)f->samples[j] * (int64_t)f->coeffs[j];
+        sum += (uint32_t)(int32_t)(product >> 32);
+    }
+    for (uint32_t j = f->state_count - 1; j > 0; j--) f->samples[j] = f->samples[j - 1];
+    sum <<= f->coeff_format;
+    f->samples[0] = (int32_t)sum;
+    int32_t out = (int32_t)sum;
+    if (f->scale_shift_for_output < 0) out >>= -f->scale_shift_for_output;
+    else out = (int32_t)((uint32_t)out << f->scale_shift_for_output);
+    return out;
+}
+
+uint32_t ohpo_decimation_factor(uint32_t rate)
+{
+    /* FlywheelRamper::DecimationFactor, FlywheelRamper.cpp:330-345 */
+    if (rate == 192000 || rate == 176400) return 4;
+    if (rate == 88200 || rate == 96000) return 2;
+    return 1;
+}
+
+uint32_t ohpo_flywheel_out_bytes(const ohp_flywheel_job* job)
+{
+    return job->out_frames * job->channels * (job->bit_depth / 8u);
+}
+
+static int flywheel_job_ok(const ohp_flywheel_job* job, uint64_t in_bytes, uint64_t out_bytes)
+{
+    const uint32_t jps = ohpo_jiffies_per_sample(job->sample_rate);
+    if (jps == 0) return 0;
+    if (!(job->bit_depth == 8 || job->bit_depth == 16 || job->bit_depth == 24 || job->bit_depth == 32)) return 0; /* StarvationRamper.cpp:322-324 */
+    if (job->channels < 1 || job->channels > OHP_FLYWHEEL_MAX_CHANNELS) return 0;
+    /* FlywheelRamper::Initialise wants exactly the training length (FlywheelRamper.cpp:180-195; with more it reads
+     * past its channel's block) */
+    if (job->train_frames != OHP_FLYWHEEL_TRAINING_JIFFIES / jps) return 0;
+    if (job->train_frames / ohpo_decimation_factor(job->sample_rate) < OHP_FLYWHEEL_DEGREE + 1u) return 0;
+    if ((uint32_t)job->train_frames * 4u * job->channels > OHP_FLYWHEEL_MAX_INPUT_BYTES) return 0;
+    const uint32_t block_frames = OHP_FLYWHEEL_BLOCK_JIFFIES / jps;
+    if (block_frames * job->channels * (job->bit_depth / 8u) > OHP_FLYWHEEL_MAX_BLOCK_BYTES) return 0; /* Bwh capacity ASSERT */
+    if (block_frames * job->channels * 4u > 384u * 10u * 4u) return 0; /* FlywheelRamperManager::iOutBuf, FlywheelRamper.cpp:28 */
+    const uint64_t in_need = (uint64_t)job->train_frames * 4u * job->channels;
+    if (job->src_off > in_bytes || in_need > in_bytes - job->src_off) return 0;
+    const uint64_t out_need = ohpo_flywheel_out_bytes(job);
+    if (job->dst_off > out_bytes || out_need > out_bytes - job->dst_off) return 0;
+    return 1;
+}
+
+int64_t ohpo_flywheel(const ohp_flywheel_job* jobs, size_t n, const uint8_t* in, uint64_t in_bytes,
+                      uint8_t* out, uint64_t out_bytes)
+{
+    for (size_t q = 0; q < n; q++) {
+        const ohp_flywheel_job* job = &jobs[q];
+        if (!flywheel_job_ok(job, in_bytes, out_bytes)) return -(int64_t)(q + 1);
+        const uint32_t ch = job->channels;
+        const uint32_t dec = ohpo_decimation_factor(job->sample_rate);
+        const uint32_t jps = ohpo_jiffies_per_sample(job->sample_rate);
+        const uint32_t bytes_per_chan = (uint32_t)job->train_frames * 4u;
+        const uint32_t ob = job->bit_depth / 8u;
+        int16_t input[OHP_FLYWHEEL_MAX_TRAIN_FRAMES], per[OHP_FLYWHEEL_MAX_TRAIN_FRAMES], pef[OHP_FLYWHEEL_MAX_TRAIN_FRAMES];
+        int16_t burg[OHP_FLYWHEEL_DEGREE], h[OHP_FLYWHEEL_DEGREE];
+        int32_t fb_samples[OHP_FLYWHEEL_MAX_CHANNELS][OHP_FLYWHEEL_DEGREE], fb_coeffs[OHP_FLYWHEEL_MAX_CHANNELS][OHP_FLYWHEEL_DEGREE];
+        ohpo_feedback fb[OHP_FLYWHEEL_MAX_CHANNELS];
+        /* FlywheelRamperManager::InitChannels (FlywheelRamper.cpp:70-83) -> FlywheelRamper::Initialise (:178-231) */
+        for (uint32_t c = 0; c < ch; c++) {
+            const uint8_t* p = in + job->src_off + (uint64_t)c * bytes_per_chan;
+            const uint32_t count = bytes_per_chan / (4u * dec);
+            memset(per, 0, sizeof per);
+            memset(pef, 0, sizeof pef);
+            for (uint32_t i = 0; i < count; i++) {
+                const uint32_t hi = ((uint32_t)p[0] << 8) + p[1];
+                const int16_t s16 = (int16_t)(uint16_t)hi;
+                const uint32_t full = (hi << 16) + ((uint32_t)p[2] << 8) + p[3];
+                p += 4u * dec;
+                if (i >= count - OHP_FLYWHEEL_DEGREE) fb_samples[c][count - i - 1] = (int32_t)full; /* reverse order, :214-218 */
+                input[i] = (int16_t)(s16 >> 1); /* kBurgDataDescaleBitCount = 1, :220 */
+            }
+            ohpo_burgs_method(input, count, OHP_FLYWHEEL_DEGREE, burg, h, per, pef);
+            const int16_t excess = ohpo_coeff_overflow(burg, OHP_FLYWHEEL_DEGREE, 3); /* CorrectBurgCoeffs, :347-353 */
+            if (excess != 0) burg[0] = wrap16((int32_t)burg[0] - (int32_t)excess * 2);
+            for (uint32_t i = 0; i < OHP_FLYWHEEL_DEGREE; i++) {
+                fb_coeffs[c][i] = (int32_t)(0u - ((uint32_t)(int32_t)burg[i] << 16)); /* PrepareFeedbackCoeffs, :233-240 */
+            }
+            /* FeedbackModel(iDegree, 0, kBurgOutputFormat = 3, kFeedbackDataFormat = 1, 1), :150 */
+            ohpo_feedback_init(&fb[c], OHP_FLYWHEEL_DEGREE, 0, 3, 1, 1, fb_coeffs[c], fb_samples[c]);
+        }
+        /* FlywheelRamperManager::Ramp (:46-68): 1 ms blocks through RenderChannels (:85-135), each delivered to
+         * RampGenerator::ProcessFragment (StarvationRamper.cpp:281-326) */
+        const uint32_t block_frames = OHP_FLYWHEEL_BLOCK_JIFFIES / jps;
+        uint32_t remaining = job->out_frames;
+        uint8_t* dst = out + job->dst_off;
+        int32_t prev[OHP_FLYWHEEL_MAX_CHANNELS];
+        while (remaining > 0) {
+            const uint32_t frames = remaining > block_frames ? block_frames : remaining;
+            remaining -= frames;
+            uint32_t hold = 0; /* restarts with every block, :89 */
+            for (uint32_t j = 0; j < frames; j++) {
+                for (uint32_t c = 0; c < ch; c++) {
+                    int32_t sample;
+                    if (hold == 0) {
+                        sample = ohpo_feedback_next(&fb[c]);
+                        prev[c] = sample;
+                    } else {
+                        sample = prev[c];
+                    }
+                    const uint32_t u = (uint32_t)sample;
+                    const uint8_t b[4] = {(uint8_t)(u >> 24), (uint8_t)(u >> 16), (uint8_t)(u >> 8), (uint8_t)u};
+                    switch (ob) {
+                    case 1: *dst++ = b[0]; break;
+                    case 2: *dst++ = b[0]; *dst++ = b[1]; break;
+                    case 3: *dst++ = b[0]; *dst++ = b[1]; *dst++ = b[2]; break;
+                    default: *dst++ = b[0]; *dst++ = b[1]; *dst++ = b[2]; *dst++ = 0; break; /* :313-321 */
+                    }
+                }
+                if (++hold == dec) hold = 0;
+            }
+        }
+    }
+    return 0;
+}
+
+int ohpo_flywheel_ramp_chunks(const ohp_flywheel_job* job, uint32_t current_ramp, uint64_t src_off, uint64_t dst_off,
+                              ohp_chunk_desc* out, uint32_t cap, uint32_t* final_ramp)
+{
+    /* RampGenerator::Start (StarvationRamper.cpp:235-247) */
+    const uint32_t jps = ohpo_jiffies_per_sample(job->sample_rate);
+    if (jps == 0) return -1;
+    const uint32_t frame_bytes = job->channels * (job->bit_depth / 8u);
+    const uint32_t block_frames = OHP_FLYWHEEL_BLOCK_JIFFIES / jps;
+    uint32_t remaining_ramp = jps * job->out_frames;
+    uint32_t remaining = job->out_frames;
+    uint32_t n = 0;
+    while (remaining > 0) {
+        const uint32_t frames = remaining > block_frames ? block_frames : remaining;
+        remaining -= frames;
+        if (n == cap) return -1;
+        /* RampGenerator::EndBlock (StarvationRamper.cpp:351-364) on a fresh MsgAudioPcm, then CreatePlayable
+         * (Msg.cpp:2234-2262) */
+        ohp_chunk_desc* d = &out[n++];
+        memset(d, 0, sizeof *d);
+        d->dst_off = dst_off;
+        d->bytes = frames * frame_bytes;
+        d->attenuation = OHP_UNITY_ATTENUATION;
+        d->bit_depth = job->bit_depth;
+        d->channels = job->channels;
+        d->out_fmt = OHP_OUT_PACKED_BE;
+        if (current_ramp == KMIN) {
+            /* SetMuted -> CreatePlayable hands out silence with no ramp */
+            d->flags = OHP_F_SILENCE;
+            d->ramp_start = d->ramp_end = KMAX;
+        } else {
+            ohp_ramp r, split;
+            uint32_t split_pos;
+            ramp_reset(&r);
+            const int rc = ohpo_ramp_set(&r, current_ramp, frames * jps, remaining_ramp, OHP_DIR_DOWN, &split, &split_pos);
+            if (rc != 0) return -1; /* ASSERT(split == nullptr), :359 */
+            remaining_ramp -= frames * jps;
+            if (r.end == KMIN) remaining_ramp = 0;
+            current_ramp = r.end;
+            d->src_off = src_off;
+            d->flags = OHP_F_RAMP_ENABLED;
+            d->ramp_start = (uint16_t)r.start;
+            d->ramp_end = (uint16_t)r.end;
+        }
+        src_off += d->bytes;
+        dst_off += d->bytes;
+    }
+    if (final_ramp) *final_ramp = current_ramp;
+    return (int)n;
+}

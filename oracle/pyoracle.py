@@ -81,6 +81,20 @@ class _Lib:
             _ptr(descs), len(descs), _ptr(inp), inp.size, _ptr(out), out.size)
         return int(rc), out
 
+    # ---- flywheel ramp generator (both libraries export burgs_method / feedback_model) ----
+    def burgs_method(self, samples, degree):
+        """FlywheelRamper::BurgsMethod on int16 samples; returns the `degree` coefficients."""
+        samples = np.ascontiguousarray(samples, dtype=np.int16)
+        out = np.zeros(degree, dtype=np.int16)
+        h = np.zeros(degree, dtype=np.int16)
+        per = np.zeros(len(samples), dtype=np.int16)
+        pef = np.zeros(len(samples), dtype=np.int16)
+        f = getattr(self.lib, self.prefix + "burgs_method")
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        f(_ptr(samples), len(samples), degree, _ptr(out), _ptr(h), _ptr(per), _ptr(pef))
+        return out
+
     def _collect(self, res, n_streams, free):
         n = res.num_chunks
         chunks = np.zeros(n, dtype=abi.CHUNK_DESC)
@@ -111,6 +125,46 @@ class Port(_Lib):
         L.ohpo_chunk_out_bytes.restype = C.c_uint32
         L.ohpo_chunk_out_bytes.argtypes = [C.c_void_p]
         self.ramp_array = np.ctypeslib.as_array((C.c_uint32 * 512).in_dll(L, "ohpo_ramp_array")).copy()
+
+    def feedback_model(self, descale, coeff_format, data_format, out_format, coeffs, samples, count):
+        """FeedbackModel: `count` outputs from the coefficients and initial states (int32 arrays)."""
+        coeffs = np.array(coeffs, dtype=np.int64).astype(np.uint32).view(np.int32).copy()
+        samples = np.array(samples, dtype=np.int64).astype(np.uint32).view(np.int32).copy()
+
+        class FB(C.Structure):
+            _fields_ = [("coeffs", C.c_void_p), ("samples", C.c_void_p), ("state_count", C.c_uint32),
+                        ("descale_bits", C.c_uint32), ("coeff_format", C.c_uint32), ("shift", C.c_int32)]
+        fb = FB()
+        L = self.lib
+        L.ohpo_feedback_init.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.ohpo_feedback_next.restype = C.c_int32
+        L.ohpo_feedback_next.argtypes = [C.c_void_p]
+        L.ohpo_feedback_init(C.byref(fb), len(coeffs), descale, coeff_format, data_format, out_format, _ptr(coeffs), _ptr(samples))
+        return np.array([L.ohpo_feedback_next(C.byref(fb)) for _ in range(count)], dtype=np.int32)
+
+    def flywheel(self, jobs, inp, out_bytes):
+        """FlywheelRamperManager::Ramp + RampGenerator::ProcessFragment per job; returns (rc, out)."""
+        jobs = np.ascontiguousarray(jobs, dtype=abi.FLYWHEEL_JOB)
+        inp = np.ascontiguousarray(inp, dtype=np.uint8)
+        out = np.zeros(int(out_bytes), dtype=np.uint8)
+        L = self.lib
+        L.ohpo_flywheel.restype = C.c_int64
+        L.ohpo_flywheel.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        rc = L.ohpo_flywheel(_ptr(jobs), len(jobs), _ptr(inp), inp.size, _ptr(out), out.size)
+        return int(rc), out
+
+    def flywheel_ramp_chunks(self, job, current_ramp, src_off, dst_off):
+        """RampGenerator::Start/EndBlock: (descs, final_ramp) or (None, None) where the reference would ASSERT."""
+        job = np.ascontiguousarray(job, dtype=abi.FLYWHEEL_JOB).reshape(1)
+        descs = np.zeros(64, dtype=abi.CHUNK_DESC)
+        final = C.c_uint32(0)
+        L = self.lib
+        L.ohpo_flywheel_ramp_chunks.restype = C.c_int
+        L.ohpo_flywheel_ramp_chunks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        n = L.ohpo_flywheel_ramp_chunks(_ptr(job), current_ramp, src_off, dst_off, _ptr(descs), len(descs), C.byref(final))
+        if n < 0:
+            return None, None
+        return descs[:n].copy(), int(final.value)
 
     def schedule_run(self, streams, events):
         """Message-model restatement: returns (rc, chunks, info, stream_chunk_begin, stream_out_bytes)."""
@@ -168,6 +222,47 @@ class Ref(_Lib):
         self._libc_free.argtypes = [C.c_void_p]
         n = L.ref_ramp_array_count()
         self.ramp_array = np.array([L.ref_ramp_array()[i] for i in range(n)], dtype=np.uint32)
+
+    def feedback_model(self, descale, coeff_format, data_format, out_format, coeffs, samples, count):
+        coeffs = np.array(coeffs, dtype=np.int64).astype(np.uint32).view(np.int32).copy()
+        samples = np.array(samples, dtype=np.int64).astype(np.uint32).view(np.int32).copy()
+        out = np.zeros(count, dtype=np.int32)
+        f = self.lib.ref_feedback_model
+        f.restype = None
+        f.argtypes = [C.c_uint32] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        f(len(coeffs), descale, coeff_format, data_format, out_format, _ptr(coeffs), _ptr(samples), _ptr(out), count)
+        return out
+
+    def flywheel(self, rate, channels, bits, current_ramp, training):
+        """The real RampGenerator.  Returns (rc, raw, ramped, descs, info, final_ramp)."""
+        training = np.ascontiguousarray(training, dtype=np.uint8)
+        cap = 20 * 400 * channels * 4 + 64
+        raw = np.zeros(cap, dtype=np.uint8)
+        ramped = np.zeros(cap, dtype=np.uint8)
+        descs = np.zeros(64, dtype=abi.CHUNK_DESC)
+        info = np.zeros(64, dtype=abi.CHUNK_INFO)
+        nbytes, nd, final = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        f = self.lib.ref_flywheel
+        f.restype = C.c_int
+        f.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                      C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        rc = f(rate, channels, bits, current_ramp, _ptr(training), training.size, _ptr(raw), _ptr(ramped), cap,
+               C.byref(nbytes), _ptr(descs), _ptr(info), len(descs), C.byref(nd), C.byref(final))
+        if rc != 0:
+            return rc, None, None, None, None, None
+        return 0, raw[:nbytes.value].copy(), ramped[:nbytes.value].copy(), descs[:nd.value].copy(), info[:nd.value].copy(), int(final.value)
+
+    def flywheel_input(self, descs, inp, rate, jiffies):
+        """The real FlywheelInput::Prepare over messages made from `descs`.  Returns (rc, planar bytes)."""
+        descs = np.ascontiguousarray(descs, dtype=abi.CHUNK_DESC)
+        inp = np.ascontiguousarray(inp, dtype=np.uint8)
+        planar = np.zeros(16384, dtype=np.uint8)
+        n = C.c_uint32(0)
+        f = self.lib.ref_flywheel_input
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        rc = f(_ptr(descs), len(descs), _ptr(inp), rate, jiffies, _ptr(planar), planar.size, C.byref(n))
+        return rc, planar[:n.value].copy()
 
     def _free_result(self, res_ref):
         res = res_ref._obj

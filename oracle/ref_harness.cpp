@@ -3,6 +3,8 @@
 // Compiled together with the reference's own, unmodified sources
 //     /root/reference/OpenHome/Media/Pipeline/Msg.cpp
 //     /root/reference/OpenHome/Media/Utils/ProcessorAudioUtils.cpp
+//     /root/reference/OpenHome/Media/FlywheelRamper.cpp
+//     /root/reference/OpenHome/Media/Pipeline/StarvationRamper.cpp   (for FlywheelInput and RampGenerator)
 // (against the ohNet header shim in oracle/shim/) into oracle/_ref/libohref.so by oracle/Makefile.
 // It calls the reference's public API the way the reference's own unit tests do
 // (Media/Tests/TestMsg.cpp SuiteRamp / SuiteMsgPlayable): MsgFactory::CreateMsgAudioPcm ->
@@ -16,6 +18,8 @@
 #include <OpenHome/Media/Pipeline/Msg.h>
 #include <OpenHome/Media/Utils/ProcessorAudioUtils.h>
 #include <OpenHome/Media/Pipeline/RampArray.h>
+#include <OpenHome/Media/Pipeline/StarvationRamper.h>
+#include <OpenHome/Media/FlywheelRamper.h>
 
 #include <cstring>
 #include <cstdlib>
@@ -376,6 +380,122 @@ int ref_schedule_run(const ohp_stream_spec* streams, size_t n_streams,
         res->num_chunks = k;
     }
     return 0;
+}
+
+// ---- flywheel ramp generator ---------------------------------------------------------------------------------------
+
+// FlywheelRamper::BurgsMethod as the reference's own Test6 calls it (TestFlywheelRamper.cpp:568-608).
+void ref_burgs_method(const int16_t* samples, uint32_t n, uint32_t degree, int16_t* output, int16_t* h, int16_t* per, int16_t* pef)
+{
+    FlywheelRamper::BurgsMethod(const_cast<TInt16*>(samples), n, degree, output, h, per, pef);
+}
+
+// FeedbackModel as the reference's Test1-Test5 use it: `count` outputs from the given coefficients and initial states.
+void ref_feedback_model(uint32_t states, uint32_t descale, uint32_t coeffFormat, uint32_t dataFormat, uint32_t outFormat,
+                        int32_t* coeffs, int32_t* samples, int32_t* out, uint32_t count)
+{
+    FeedbackModel fb(states, descale, coeffFormat, dataFormat, outFormat);
+    fb.Initialise(coeffs, samples);
+    for (uint32_t i = 0; i < count; i++) out[i] = fb.NextSample();
+}
+
+// FlywheelInput::Prepare (StarvationRamper.cpp:90-111) over a queue of real messages made from `descs`
+// (unramped PCM or silence chunks of one stream).  planar receives channels * (jiffies / jps) * 4 bytes.
+int ref_flywheel_input(const ohp_chunk_desc* descs, size_t n, const uint8_t* in, uint32_t rate, uint32_t jiffies,
+                       uint8_t* planar, uint32_t cap, uint32_t* planarBytes)
+{
+    RefFactory* f = new RefFactory();
+    try {
+        MsgQueueLite queue;
+        uint32_t bits = 16, ch = 2;
+        for (size_t k = 0; k < n; k++) {
+            const ohp_chunk_desc& d = descs[k];
+            bits = d.bit_depth; ch = d.channels;
+            if (d.flags & OHP_F_SILENCE) {
+                TUint j = (d.bytes / (d.channels * (d.bit_depth / 8u))) * Jiffies::PerSample(rate);
+                queue.Enqueue(f->factory->CreateMsgSilence(j, rate, d.bit_depth, d.channels));
+            }
+            else {
+                queue.Enqueue(f->factory->CreateMsgAudioPcm(Brn(in + d.src_off, d.bytes), d.channels, rate, d.bit_depth,
+                              (d.flags & OHP_F_IN_LITTLE_ENDIAN) ? AudioDataEndian::Little : AudioDataEndian::Big, 0));
+            }
+        }
+        FlywheelInput input(OHP_FLYWHEEL_TRAINING_JIFFIES);
+        const Brx& buf = input.Prepare(queue, jiffies, rate, bits, ch);
+        if (buf.Bytes() > cap) { delete f; return -2; }
+        std::memcpy(planar, buf.Ptr(), buf.Bytes());
+        *planarBytes = buf.Bytes();
+        delete f;
+        return 0;
+    }
+    catch (AssertionFailed&) {
+        return -1;
+    }
+}
+
+// The real RampGenerator (StarvationRamper.cpp:196-371): Start() on a training block in FlywheelInput's layout, then
+// every MsgAudioPcm it produces.  raw = the messages' payloads (what FlywheelRamperManager generated, repacked by
+// RampGenerator::ProcessFragment); ramped = the same messages through CreatePlayable -> Read(ProcessorPcmBufTest) with
+// the ramp RampGenerator::EndBlock set; descs = one per message (src_off / dst_off = offset in raw / ramped).
+// Callers keep to jobs ohp_flywheel_validate accepts: an ASSERT on the generator's own thread cannot be caught here.
+int ref_flywheel(uint32_t rate, uint32_t channels, uint32_t bits, uint32_t currentRamp,
+                 const uint8_t* training, uint32_t trainingBytes,
+                 uint8_t* raw, uint8_t* ramped, uint32_t cap, uint32_t* outBytes,
+                 ohp_chunk_desc* descs, ohp_chunk_info* info, uint32_t descCap, uint32_t* numDescs, uint32_t* finalRamp)
+{
+    RefFactory* f = new RefFactory();
+    int rc = 0;
+    uint32_t bytes = 0, nd = 0;
+    try {
+        RampGenerator gen(*f->factory, OHP_FLYWHEEL_TRAINING_JIFFIES, OHP_FLYWHEEL_RAMP_JIFFIES, kPriorityNormal);
+        Brn recent(training, trainingBytes);
+        gen.Start(recent, rate, channels, bits, currentRamp);
+        ProcessorPcmBufTest proc;
+        Msg* m = nullptr;
+        while (gen.TryGetAudio(m)) {
+            MsgAudioPcm* pcm = static_cast<MsgAudioPcm*>(m);
+            MsgAudioPcm* clone = static_cast<MsgAudioPcm*>(pcm->Clone());
+            clone->ClearRamp();
+            MsgPlayable* rawPlayable = clone->CreatePlayable();
+            rawPlayable->Read(proc);
+            const uint32_t n = proc.Buf().Bytes();
+            if (bytes + n > cap || nd == descCap) { rc = -2; rawPlayable->RemoveRef(); pcm->RemoveRef(); continue; }
+            std::memcpy(raw + bytes, proc.Ptr(), n);
+            rawPlayable->RemoveRef();
+            const Ramp ramp = pcm->Ramp();
+            const uint32_t jiffies = pcm->Jiffies();
+            MsgPlayable* playable = pcm->CreatePlayable();
+            playable->Read(proc);
+            if (proc.Buf().Bytes() != n) rc = -3;
+            else std::memcpy(ramped + bytes, proc.Ptr(), n);
+            ohp_chunk_desc& d = descs[nd];
+            std::memset(&d, 0, sizeof d);
+            const bool silence = dynamic_cast<MsgPlayablePcm*>(playable) == nullptr;
+            d.src_off = silence ? 0 : bytes;
+            d.dst_off = bytes;
+            d.bytes = n;
+            d.ramp_start = (uint16_t)playable->Ramp().Start();
+            d.ramp_end = (uint16_t)playable->Ramp().End();
+            d.attenuation = OHP_UNITY_ATTENUATION;
+            d.bit_depth = (uint8_t)bits;
+            d.channels = (uint8_t)channels;
+            d.flags = (playable->Ramp().IsEnabled() ? OHP_F_RAMP_ENABLED : 0) | (silence ? OHP_F_SILENCE : 0);
+            d.out_fmt = OHP_OUT_PACKED_BE;
+            info[nd].direction = (uint32_t)ramp.Direction();
+            info[nd].jiffies = jiffies;
+            nd++;
+            bytes += n;
+            playable->RemoveRef();
+        }
+        *finalRamp = gen.iCurrentRampValue;
+    }
+    catch (AssertionFailed&) {
+        return -1; // the factory is leaked on purpose (see RunStream)
+    }
+    *outBytes = bytes;
+    *numDescs = nd;
+    delete f;
+    return rc;
 }
 
 int ref_hardware_threads(void)

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <chrono>
+#include <thread>
 
 namespace OpenHome {
 
@@ -95,11 +96,64 @@ private:
     Semaphore& iSem;
 };
 
-class Thread
+// ohNet's Thread: Start() launches Run(); Wait() blocks the thread itself until Signal() (a counting semaphore) and
+// throws ThreadKill once Kill() was called; the destructor kills and joins.  (StarvationRamper.cpp's RampGenerator runs
+// FlywheelRamperManager::Ramp on such a thread.)
+class Thread : private INonCopyable
 {
 public:
+    static const TUint kDefaultStackBytes = 32 * 1024;
     static const TChar* CurrentThreadName() { return "oracle"; }
     static void Sleep(TUint /*aMilliSecs*/) {}
+    virtual ~Thread() { Kill(); Join(); }
+    void Start() { iThread = std::thread([this] { try { Run(); } catch (ThreadKill&) {} }); }
+    void Wait()
+    {
+        std::unique_lock<std::mutex> lock(iMutex);
+        iCv.wait(lock, [this] { return iCount > 0 || iKill; });
+        if (iKill) THROW(ThreadKill);
+        --iCount;
+    }
+    TBool TryWait()
+    {
+        std::lock_guard<std::mutex> lock(iMutex);
+        if (iKill) THROW(ThreadKill);
+        if (iCount == 0) return false;
+        --iCount;
+        return true;
+    }
+    void Signal()
+    {
+        { std::lock_guard<std::mutex> lock(iMutex); ++iCount; }
+        iCv.notify_all();
+    }
+    void Kill()
+    {
+        { std::lock_guard<std::mutex> lock(iMutex); iKill = true; }
+        iCv.notify_all();
+    }
+    void CheckForKill() const { if (iKill) THROW(ThreadKill); }
+    void Join() { if (iThread.joinable()) iThread.join(); }
+protected:
+    Thread(const TChar* /*aName*/, TUint /*aPriority*/ = kPriorityNormal, TUint /*aStackBytes*/ = kDefaultStackBytes) {}
+    virtual void Run() = 0;
+private:
+    std::thread iThread;
+    std::mutex iMutex;
+    std::condition_variable iCv;
+    TUint iCount = 0;
+    bool iKill = false;
+};
+
+class ThreadFunctor : public Thread
+{
+public:
+    ThreadFunctor(const TChar* aName, Functor aFunctor, TUint aPriority = kPriorityNormal, TUint aStackBytes = kDefaultStackBytes)
+        : Thread(aName, aPriority, aStackBytes), iFunctor(aFunctor) {}
+    ~ThreadFunctor() { Kill(); Join(); }
+private:
+    void Run() override { iFunctor(); }
+    Functor iFunctor;
 };
 
 } // namespace OpenHome

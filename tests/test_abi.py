@@ -33,6 +33,14 @@ def test_cuda_library_exports_the_device_schedule_builder():
         assert hasattr(lib, n), n
 
 
+def test_cuda_library_exports_the_flywheel_generator():
+    lib = capi.cuda_lib()
+    names = declared_functions("ohp_flywheel.h")
+    assert names == ["ohp_flywheel_device", "ohp_flywheel_out_bytes", "ohp_flywheel_validate"]
+    for n in names:
+        assert hasattr(lib, n), n
+
+
 def test_host_library_exports_every_declared_symbol():
     lib = capi.host_lib()
     names = declared_functions("ohp_schedule.h")

@@ -1,0 +1,137 @@
+"""Flywheel ramp generator, CPU side: the C oracle (oracle/ohp_oracle.c) and the host RampGenerator mirror
+(ohp_flywheel_ramp_chunks) against
+  * the known answers of the reference's own tests (Media/Tests/TestFlywheelRamper.cpp Test1-Test6),
+  * the reference itself: FlywheelRamper.cpp + StarvationRamper.cpp linked into oracle/_ref (where it was built),
+  * tests/golden/flywheel.npz, recorded from oracle/_ref by tests/golden/make_golden_flywheel.py."""
+import os
+
+import numpy as np
+import pytest
+
+from ohpipeline_b200 import abi, capi
+from flywheel_util import SHAPES, training_block, train_frames
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "flywheel.npz")
+
+# TestFlywheelRamper.cpp:492-518
+BURG_IN_1 = [111411200, 110362624, 108855296, 107937792, 108265472, 108462080, 108199936, 108527616, 107479040, 105578496,
+             102170624, 97845248, 93257728, 88342528, 83034112, 77004800, 70844416, 63963136, 56885248, 51183616, 46399488,
+             41418752, 36306944, 31457280, 27000832, 21430272, 15597568, 10027008, 4521984, 196608, -5439488, -10420224,
+             -15335424, -20905984, -26083328, -32112640, -37552128, -42270720, -47251456, -52232192, -55836672, -59834368,
+             -63700992, -67960832]
+BURG_IN_2 = [80150528, 78249984, 75628544, 74055680, 73924608, 73924608, 73400320, 72744960, 72351744, 70189056, 67174400,
+             64225280, 60948480, 57999360, 53673984, 49676288, 46596096, 42598400, 38731776, 36044800, 34144256, 31588352,
+             28966912, 26673152, 24838144, 21889024, 18087936, 14548992, 9961472, 7208960, 3735552, 131072, -3342336,
+             -7602176, -10616832, -14417920, -18546688, -21626880, -25296896, -28901376, -32505856, -35913728, -38731776,
+             -42401792]
+
+
+def libs(port):
+    from oracle import pyoracle
+    out = [port]
+    if pyoracle.Ref.available():
+        out.append(pyoracle.Ref())
+    return out
+
+
+def test_burg_known_answers(port):
+    """SuiteFlywheelRamper::Test6 (TestFlywheelRamper.cpp:568-608)."""
+    for lib in libs(port):
+        for data, want in ((BURG_IN_1, [-16619, 8835, -374]), (BURG_IN_2, [-14748, 5235, 1360])):
+            s = (np.array(data, dtype=np.int64) >> 16).astype(np.int16)
+            assert list(lib.burgs_method(s, 3)) == want
+
+
+def test_feedback_model_known_answers(port):
+    """SuiteFlywheelRamper::Test1, Test2, Test5 (TestFlywheelRamper.cpp:111-262, 395-556)."""
+    for lib in libs(port):
+        v = [0x01000000, 0x02000000, 0x04000000, 0x08000000]
+        got = lib.feedback_model(8, 1, 1, 1, v, v, 4)
+        assert [int(x) for x in got] == [0x00aa0000, 0x00555400, 0x002b5200, 0x0016fa00]
+        # Test2: scaling by coefficient / data / output format, two states
+        table = {(1, 1, 1): (0x20000, 0x400), (2, 1, 1): (0x40000, 0x1000), (3, 1, 1): (0x80000, 0x4000),
+                 (4, 1, 1): (0x100000, 0x10000), (1, 2, 1): (0x40000, 0x800), (1, 3, 1): (0x80000, 0x1000),
+                 (1, 4, 1): (0x100000, 0x2000), (1, 1, 2): (0x10000, 0x200), (1, 1, 3): (0x8000, 0x100),
+                 (1, 1, 4): (0x4000, 0x80), (2, 2, 2): (0x40000, 0x1000)}
+        fixtures = _test2_inputs()
+        for fmt, want in table.items():
+            got = lib.feedback_model(fixtures["descale"], fmt[0], fmt[1], fmt[2], fixtures["coeffs"], fixtures["samples"], 2)
+            assert tuple(int(x) for x in got) == want, fmt
+        # Test5: an oscillator -- one coefficient of -1 (2.30) at position k gives period 2(k+1)
+        for k, want in ((0, [0xc0000000, 0x40000000] * 3),
+                        (1, [0, 0xc0000000, 0, 0x40000000, 0, 0xc0000000]),
+                        (2, [0, 0, 0xc0000000, 0, 0, 0x40000000, 0, 0, 0xc0000000, 0, 0, 0x40000000])):
+            coeffs = [0] * 6
+            coeffs[k] = 0xc0000000
+            got = lib.feedback_model(8, 2, 2, 2, coeffs, [0x40000000, 0, 0, 0, 0, 0], len(want))
+            assert [int(x) & 0xffffffff for x in got] == want, k
+
+
+def _test2_inputs():
+    # TestFlywheelRamper.cpp:159-174: kDataInDescaleBits = 8, coeffs {0x01000000, 0}, samples {0x01000000, 0}
+    return {"descale": 8, "coeffs": [0x01000000, 0], "samples": [0x01000000, 0]}
+
+
+@pytest.mark.parametrize("kind", ["tone", "noise", "dc", "zero", "step", "max"])
+def test_oracle_matches_linked_reference(port, ref, kind):
+    """The real RampGenerator (FlywheelRamperManager::Ramp on its own thread, ProcessFragment, EndBlock) vs the port:
+    generated audio, per-block ramp descriptors, final ramp value, and the ramped bytes a driver would read."""
+    for n, (rate, ch, bits) in enumerate(SHAPES):
+        for start in (abi.RAMP_MAX, 9000, 1, 0):
+            training = training_block(rate, ch, kind, seed=100 + n)
+            rc, raw, ramped, descs, info, final = ref.flywheel(rate, ch, bits, start, training)
+            assert rc == 0
+            job = capi.flywheel_job(rate, ch, bits)
+            rc2, out = port.flywheel(job, training, raw.size)
+            assert rc2 == 0
+            assert np.array_equal(out, raw), (rate, ch, bits, kind)
+            pd, pfinal = port.flywheel_ramp_chunks(job, start, 0, 0)
+            assert np.array_equal(pd, descs), (rate, ch, bits, start)
+            assert pfinal == final
+            rc3, pr = port.process_chunks(pd, out, out.size)
+            assert rc3 == 0 and np.array_equal(pr, ramped)
+
+
+def test_host_ramp_chunks_match_oracle(port):
+    """ohp_flywheel_ramp_chunks (product, host message model) vs the oracle's RampGenerator::EndBlock restatement."""
+    for rate, ch, bits in SHAPES:
+        job = capi.flywheel_job(rate, ch, bits, src_off=4096, dst_off=123)
+        for start in (abi.RAMP_MAX, 16383, 12345, 4097, 100, 1, 0):
+            want, wfinal = port.flywheel_ramp_chunks(job, start, 4096, 123)
+            got, gfinal = capi.flywheel_ramp_chunks(job, start, 4096, 123)
+            assert np.array_equal(got, want), (rate, ch, bits, start)
+            assert gfinal == wfinal
+            assert int(abi.chunk_out_bytes(got).sum()) == int(job["out_frames"][0]) * ch * bits // 8
+
+
+def test_golden_flywheel_vectors(port):
+    g = np.load(GOLDEN)
+    jobs, starts = g["jobs"], g["starts"]
+    for k in range(len(jobs)):
+        job = jobs[k:k + 1].copy()
+        training = g["training_%d" % k]
+        rc, out = port.flywheel(job, training, int(g["raw_%d" % k].size))
+        assert rc == 0
+        assert np.array_equal(out, g["raw_%d" % k]), k
+        descs, final = capi.flywheel_ramp_chunks(job, int(starts[k]), 0, 0)
+        assert np.array_equal(descs, g["descs_%d" % k]), k
+        assert final == int(g["finals"][k])
+        rc, ramped = port.process_chunks(descs, out, out.size)
+        assert rc == 0 and np.array_equal(ramped, g["ramped_%d" % k]), k
+
+
+def test_validate_refuses_what_the_reference_cannot_hold():
+    ok = capi.flywheel_job(48000, 2, 24)
+    assert capi.flywheel_validate(ok, 1 << 20, 1 << 20) == (abi.OK, 0)
+    for field, value in (("sample_rate", 12345), ("bit_depth", 20), ("channels", 0), ("channels", 9), ("train_frames", 47)):
+        bad = ok.copy()
+        bad[field] = value
+        assert capi.flywheel_validate(bad, 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC, field
+    # 384 kHz x 8 channels x 32 bit: one 1 ms block (12288 B) overruns RampGenerator's 6144-byte buffer
+    assert capi.flywheel_validate(capi.flywheel_job(384000, 8, 32), 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC
+    # 384 kHz x 6 channels: the training block (9216 B) overruns FlywheelInput's 7680-byte buffer
+    assert capi.flywheel_validate(capi.flywheel_job(384000, 6, 8), 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC
+    assert capi.flywheel_validate(ok, 100, 1 << 20)[0] == abi.E_OUT_OF_RANGE
+    assert capi.flywheel_validate(ok, 1 << 20, 100)[0] == abi.E_OUT_OF_RANGE
+    both = np.concatenate([ok, capi.flywheel_job(48000, 2, 20)])
+    assert capi.flywheel_validate(both, 1 << 20, 1 << 20) == (abi.E_INVALID_DESC, 1)
