@@ -41,7 +41,8 @@ def build_workload(name, streams, seconds):
     if name == "config5":
         return workloads.config5(n_streams=streams or 65536, seconds=seconds or 1.0)
     if name == "config3":
-        return workloads.config3(n_streams=streams or 4096, seconds=seconds or 1.0)
+        return workloads.config3(n_streams=streams or 4096, seconds=seconds or 1.0,
+                                 n_events=int(os.environ.get("OHP_C3_EVENTS", "8")))  # experiment knob: 0 = no ramps, uniform chunks
     if name == "config4":
         return workloads.mixed(n_streams=streams or 16384, seed=4, max_frames=int((seconds or 1.0) * 48000))
     if name == "config1":
@@ -200,6 +201,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 5)")
+    ap.add_argument("--chunk-frames", type=int, default=0, help="experiment: override the workload's frames per message")
+    ap.add_argument("--pad-mb", type=float, default=0.0, help="experiment: spacer allocated between the input and output arenas")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -209,6 +212,8 @@ def main():
         args.warmup = 3
 
     w = build_workload(args.workload, args.streams, args.seconds)
+    if args.chunk_frames:
+        w.streams["chunk_frames"] = args.chunk_frames
     frames_per_step = w.total_frames
     subsamples_per_step = w.total_subsamples
     cfg = {"workload": w.name, "streams_per_gpu": int(len(w.streams)), "frames_per_step_per_gpu": frames_per_step,
@@ -263,6 +268,7 @@ def main():
     g = torch.Generator(device="cuda")
     g.manual_seed(1234 + rank)
     d_in = torch.randint(0, 256, (w.in_bytes,), dtype=torch.uint8, device="cuda", generator=g)
+    d_pad = torch.zeros(int(args.pad_mb * (1 << 20)) + 1, dtype=torch.uint8, device="cuda")  # noqa: F841 (address spacer)
     d_out = torch.zeros(w.out_bytes, dtype=torch.uint8, device="cuda")
     # descriptors are built ON THE GPU from the stream specs and ramp events (ohp_schedule_{count,emit}_device) and
     # checked against the host model's; the hot path below consumes the device-built array

@@ -95,7 +95,8 @@ __device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uin
 #endif
 
 // Persistent, warp-specialised CTAs (see ohp_kernels.cuh): chunks are dealt block-cyclically to the CTAs; inside the
-// CTA the chunk with ordinal k belongs to consumer warp k % kConsumerWarps and to ring slot k % kRingSlots.
+// CTA the chunk with ordinal k belongs to consumer team k % kTeams (kWarpsPerChunk warps that split an aligned chunk
+// between them) and to ring slot k % kRingSlots.
 __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kRingSlots; s++) {
             mbar_init(smem_u32(&sm.full[s]), 1);
-            mbar_init(smem_u32(&sm.empty[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), kWarpsPerChunk);
         }
         fence_mbar_init();
     }
@@ -127,6 +128,17 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
         uint32_t wr = 0;              // next free byte of the ring
         uint32_t free_bytes = kRingBytes;
         uint64_t rd = 0;              // oldest chunk whose slot has not been reclaimed yet
+        uint32_t my_slot_bytes = 0;   // lane s: bytes to give back when ring slot s (barrier pair s) is released
+        // The whole warp walks the issue loop in lockstep (warp-uniform control flow) and lane 0 performs the side
+        // effects: what the loop needs of chunk j lives in lane j's registers and arrives by shuffle, so issuing a chunk
+        // costs a few dozen ALU cycles instead of a chain of dependent shared-memory reads.  The descriptors of the NEXT
+        // batch are fetched before the loop, so their global-memory latency hides behind it.
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        if (lane < my_n) {
+            const uint64_t c = cta_chunk_index(lane, blockIdx.x, gridDim.x);
+            d0 = __ldg(dp + 2 * c);
+            d1 = __ldg(dp + 2 * c + 1);
+        }
         for (uint64_t base = 0; base < my_n; base += 32) {
             // all lanes: decode 32 descriptors into the record table (the half the consumers are done with:
             // at most kRingSlots <= 32 chunks are ever in flight)
@@ -135,53 +147,134 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
             r.kind = kSkip;
             uint64_t src_al = 0;
             if (k < my_n) {
-                const uint64_t c = cta_chunk_index(k, blockIdx.x, gridDim.x);
-                const uint4 d0 = __ldg(dp + 2 * c);
-                const uint4 d1 = __ldg(dp + 2 * c + 1);
                 uint64_t src_off;
                 const uint32_t err = decode_chunk(p, d0, d1, r, src_off);
-                if (err) report(p, err, c);
+                if (err) report(p, err, cta_chunk_index(k, blockIdx.x, gridDim.x));
                 src_al = reinterpret_cast<uint64_t>(p.in) + src_off - r.head;
             }
-            const uint32_t rslot = (uint32_t)(k & (kRecSlots - 1));
-            sm.rec[rslot] = r;
-            sm.load_src[rslot] = src_al;
+            if (k + 32 < my_n) {
+                const uint64_t c = cta_chunk_index(k + 32, blockIdx.x, gridDim.x);
+                d0 = __ldg(dp + 2 * c);
+                d1 = __ldg(dp + 2 * c + 1);
+            }
+            sm.rec[(uint32_t)(k & (kRecSlots - 1))] = r;
+            const uint32_t my_kind = r.kind;
+            uint32_t my_span = 0;
+            if (my_kind == kPcm || my_kind == kSilenceConv) my_span = (r.head + r.bytes + 15u) & ~15u;
             __syncwarp();
-            // one lane: carve slots out of the ring and start the loads, in order
-            if (lane == 0) {
-                const uint32_t count = (uint32_t)(my_n - base < 32 ? my_n - base : 32);
-                for (uint32_t j = 0; j < count; j++) {
-                    const uint64_t it = base + j;
-                    const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
-                    const uint32_t bs = (uint32_t)(it & (kRingSlots - 1));
-                    const uint32_t kind = sm.rec[sl].kind;
-                    const bool pcm = kind == kPcm;
-                    uint32_t span = 0, need = 0;
-                    if (pcm || kind == kSilenceConv) {
-                        span = (sm.rec[sl].head + sm.rec[sl].bytes + 15u) & ~15u;
-                        need = kSlotFront + span + kSlotBack;
+            const uint32_t count = (uint32_t)(my_n - base < 32 ? my_n - base : 32);
+            [[maybe_unused]] const uint32_t my_need = my_span ? kSlotFront + my_span + kSlotBack : 0u;
+#if OHP_LOADER == 1
+            uint32_t j = 0;
+            while (j < count) {
+                const uint64_t it0 = base + j;
+                // (1) sweep the slots in flight, oldest first, without blocking: lane l tests slot rd + l
+                {
+                    const uint32_t inflight = (uint32_t)(it0 - rd); // <= kRingSlots <= 32
+                    const uint64_t r = rd + lane;
+                    const uint32_t rs = (uint32_t)(r % kRingSlots);
+                    const bool released = lane < inflight && mbar_test(smem_u32(&sm.empty[rs]), (uint32_t)(r / kRingSlots) & 1u);
+                    const uint32_t mask = __ballot_sync(0xffffffffu, released);
+                    const uint32_t nrel = mask == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~mask) - 1u; // reclaim is in order
+                    uint32_t bytes = __shfl_sync(0xffffffffu, my_slot_bytes, rs);
+                    bytes = lane < nrel ? bytes : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+                    free_bytes += bytes;
+                    rd += nrel;
+                }
+                // (2) place as many of the next chunks as fit right now (warp-uniform; lane g keeps chunk j + g's offset)
+                uint32_t fit = 0, my_wr = 0;
+                {
+                    uint32_t wr_s = wr, free_s = free_bytes;
+                    for (uint32_t g = 0; g < kIssueWidth && j + g < count; g++) {
+                        const uint32_t need = __shfl_sync(0xffffffffu, my_need, j + g);
+                        const bool wrap = wr_s + need > kRingBytes;       // the slot must be contiguous: skip the end of the ring
+                        const uint32_t waste = wrap ? kRingBytes - wr_s : 0u;
+                        if (free_s < need + waste || it0 + g - rd >= kRingSlots) break;
+                        if (wrap) wr_s = 0;
+                        if (lane == g) my_wr = wr_s;
+                        if (lane == (uint32_t)((it0 + g) % kRingSlots)) my_slot_bytes = need + waste;
+                        free_s -= need + waste;
+                        wr_s += need;
+                        fit++;
                     }
-                    uint32_t waste = 0;
-                    const bool wrap = wr + need > kRingBytes;           // the slot must be contiguous: skip the end of the ring
-                    if (wrap) waste = kRingBytes - wr;
-                    // reclaim, oldest first, until the slot fits and its barrier pair is free
-                    while (free_bytes < need + waste || it - rd >= kRingSlots) {
-                        const uint32_t os = (uint32_t)(rd & (kRingSlots - 1));
-                        OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[os]), (uint32_t)(rd / kRingSlots) & 1u, p.status));
-                        free_bytes += sm.slot_bytes[os];
-                        rd++;
+                    if (fit == 0) {
+                        // ring full: block on the oldest slot (one lane polls), then sweep again
+                        const uint32_t os = (uint32_t)(rd % kRingSlots);
+                        if (lane == 0) OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[os]), (uint32_t)(rd / kRingSlots) & 1u, p.status));
+                        __syncwarp();
+                        continue;
                     }
-                    if (wrap) wr = 0;
-                    sm.slot_bytes[bs] = need + waste;
-                    free_bytes -= need + waste;
+                    wr = wr_s;
+                    free_bytes = free_s;
+                }
+                // (3) lanes 0..fit-1 start chunk j + lane
+                {
+                    const uint32_t from = (j + lane) & 31u;
+                    const uint32_t kind = __shfl_sync(0xffffffffu, my_kind, from);
+                    uint32_t span = __shfl_sync(0xffffffffu, my_span, from);
+                    const uint64_t src = ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(src_al >> 32), from) << 32)
+                                       | __shfl_sync(0xffffffffu, (uint32_t)src_al, from);
+                    if (lane < fit) {
+                        const uint64_t it = it0 + lane;
+                        sm.ring_off[(uint32_t)(it & (kRecSlots - 1))] = my_wr;
+                        const uint32_t full = smem_u32(&sm.full[(uint32_t)(it % kRingSlots)]);
+                        if (kind == kPcm) {
+                            const uint8_t* al = reinterpret_cast<const uint8_t*>(src);
+                            const uint32_t dst_smem = ring + my_wr + kSlotFront;
+                            const uint64_t room = (uint64_t)(p.in + p.in_bytes - al);
+                            if (span > room) {
+                                // last 16-byte word of the arena is partial: fetch its bytes one by one
+                                const uint32_t whole = (uint32_t)(room & ~15ull);
+                                for (uint32_t i = whole; i < (uint32_t)room; i++) sm.ring[my_wr + kSlotFront + i] = al[i];
+                                span = whole;
+                            }
+                            if (span != 0) {
+                                mbar_arrive_expect_tx(full, span);
+                                tma_load(dst_smem, al, span, full);
+                            } else {
+                                mbar_arrive(full);
+                            }
+                        } else {
+                            mbar_arrive(full); // nothing to load (silence; a converting sink still gets its slot)
+                        }
+                    }
+                }
+                j += fit;
+            }
+#else
+            for (uint32_t j = 0; j < count; j++) {
+                const uint64_t it = base + j;
+                const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
+                const uint32_t bs = (uint32_t)(it % kRingSlots);
+                const uint32_t kind = __shfl_sync(0xffffffffu, my_kind, j);
+                uint32_t span = __shfl_sync(0xffffffffu, my_span, j);
+                const uint64_t src = ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(src_al >> 32), j) << 32)
+                                   | __shfl_sync(0xffffffffu, (uint32_t)src_al, j);
+                const uint32_t need = span ? kSlotFront + span + kSlotBack : 0u;
+                const bool wrap = wr + need > kRingBytes;           // the slot must be contiguous: skip the end of the ring
+                const uint32_t waste = wrap ? kRingBytes - wr : 0u;
+                // reclaim, oldest first, until the slot fits and its barrier pair is free
+                while (free_bytes < need + waste || it - rd >= kRingSlots) {
+                    const uint32_t os = (uint32_t)(rd % kRingSlots);
+                    // one lane polls (32 lanes hammering the same mbarrier slow the SM's barrier unit down measurably)
+                    if (lane == 0) OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[os]), (uint32_t)(rd / kRingSlots) & 1u, p.status));
+                    __syncwarp();
+                    free_bytes += __shfl_sync(0xffffffffu, my_slot_bytes, os);
+                    rd++;
+                }
+                if (wrap) wr = 0;
+                if (lane == bs) my_slot_bytes = need + waste;
+                free_bytes -= need + waste;
+                if (lane == 0) {
                     sm.ring_off[sl] = wr;
                     const uint32_t full = smem_u32(&sm.full[bs]);
-                    if (pcm) {
-                        const uint8_t* al = reinterpret_cast<const uint8_t*>(sm.load_src[sl]);
+                    if (kind == kPcm) {
+                        const uint8_t* al = reinterpret_cast<const uint8_t*>(src);
                         const uint32_t dst_smem = ring + wr + kSlotFront;
                         const uint64_t room = (uint64_t)(p.in + p.in_bytes - al);
                         if (span > room) {
-                            // last 16-byte word of the arena is partial: fetch its bytes one by one
                             const uint32_t whole = (uint32_t)(room & ~15ull);
                             for (uint32_t i = whole; i < (uint32_t)room; i++) sm.ring[wr + kSlotFront + i] = al[i];
                             span = whole;
@@ -192,13 +285,13 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                         } else {
                             mbar_arrive(full);
                         }
-                        wr += need;
                     } else {
-                        mbar_arrive(full); // nothing to load (silence; a converting sink still gets its slot)
-                        wr += need;
+                        mbar_arrive(full);
                     }
                 }
+                wr += need;
             }
+#endif
             __syncwarp();
         }
         if (lane == 0) {
@@ -208,17 +301,32 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
         }
     } else {
-        // ------------------------------------------------------------------ consumers: one warp per chunk
+        // ------------------------------------------------------------------ consumers: a team of kWarpsPerChunk warps per chunk
         const uint32_t cw = warp - 1;
+        const uint32_t team = cw / kWarpsPerChunk;
+        const uint32_t member = cw % kWarpsPerChunk; // member 0 leads: it does whatever is not split
         const uint32_t table = smem_u32(&sm.table2[0]);
-        for (uint64_t it = cw; it < my_n; it += kConsumerWarps) {
-            const uint32_t bs = (uint32_t)(it & (kRingSlots - 1));
+        for (uint64_t it = team; it < my_n; it += kTeams) {
+            const uint32_t bs = (uint32_t)(it % kRingSlots);
             const uint32_t ph = (uint32_t)(it / kRingSlots) & 1u;
+            // every lane looks once (the data is usually there); if not, one lane polls and the warp barrier hands what
+            // it observed to the others -- 32 lanes spinning on one mbarrier slow the SM's barrier unit down measurably
+#if OHP_CONSUMER_POLL == 0
             OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
+#elif OHP_CONSUMER_POLL == 1
+            if (lane == 0) OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
+            __syncwarp();
+#else
+            if (!__all_sync(0xffffffffu, mbar_test(smem_u32(&sm.full[bs]), ph))) {
+                if (lane == 0) OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
+                __syncwarp();
+            }
+#endif
             const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
             const ChunkRec& cr = sm.rec[sl];
             const uint32_t kind = cr.kind;
-            if (kind == kPcm || kind == kSilenceConv) {
+            const bool split = chunk_splits(cr);
+            if ((kind == kPcm || kind == kSilenceConv) && (member == 0 || split)) {
                 uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
                 const uint32_t head = cr.head;
                 const uint32_t in_addr = ring + sm.ring_off[sl] + kSlotFront;          // 16-byte aligned; image at +head
@@ -226,6 +334,15 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 const uint32_t image = in_addr + head - ((head - cr.dst_lo) & 15u);
                 const uint32_t out_addr = image & ~3u;                                 // word stores; == image unless dst is odd
                 const uint32_t fmt = cr.out_fmt;
+                // this warp's share: groups [g_begin, g_end) = bytes [b_begin, b_end) of the image
+                const uint32_t B = (cr.variant & 3u) + 1u;
+                const uint32_t groups = (cr.units + 3u) >> 2;
+                uint32_t g_begin = 0, g_end = groups, b_begin = 0, b_end = cr.out_bytes;
+                if (split) {
+                    const uint32_t g_mid = (groups + 1u) >> 1;
+                    if (member == 0) { g_end = g_mid; b_end = min(g_mid * 16u * B, cr.out_bytes); }
+                    else { g_begin = g_mid; b_begin = min(g_mid * 16u * B, cr.out_bytes); }
+                }
                 if (kind == kSilenceConv) {
                     silence_to_smem(in_addr, cr.bytes, cr.channels, lane);
                     __syncwarp();
@@ -235,11 +352,13 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
                 if (fmt <= OHP_OUT_PACKED_LE) {
                     if (cr.mode & kModeTransform) {
-                        switch (cr.variant & 3u) {
-                        case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, lane); break;
-                        case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, lane); break;
-                        case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, lane); break;
-                        default: transform_dispatch<4>(cr, table, in_addr, out_addr, lane); break;
+                        if (g_begin < g_end) {
+                            switch (cr.variant & 3u) {
+                            case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
+                            case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
+                            case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
+                            default: transform_dispatch<4>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
+                            }
                         }
                     } else if (out_addr != in_addr + head) {
                         shift_chunk(in_addr, head, out_addr, cr.bytes, lane);
@@ -254,7 +373,6 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     default: convert_from32<4>(cr, table, in_addr, out_addr, lane); break;
                     }
                 } else {
-                    const uint32_t B = (cr.variant & 3u) + 1u;
                     const uint32_t db = B < 3 ? B : 3u;
                     if (cr.channels >= 2) {
                         if (db == 1) convert_songcast<1, 2>(cr, table, in_addr, out_addr, cr.aux, lane);
@@ -278,8 +396,10 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
                 // the finished image sits at out_addr: one TMA bulk store for its 16-byte aligned interior when out_addr is
                 // congruent to dst mod 16, a register funnel otherwise (destination not 4-byte aligned).  The planar sink
-                // has already written global memory itself.
-                if (fmt != OHP_OUT_PLANAR32_BE) store_image_warp(out_addr, dst, cr.out_bytes, lane);
+                // has already written global memory itself.  (A split chunk is aligned: each half is a bulk store.)
+                if (fmt != OHP_OUT_PLANAR32_BE && b_begin < b_end) {
+                    store_image_warp(out_addr + b_begin, dst + b_begin, b_end - b_begin, lane);
+                }
                 __syncwarp();
                 if (lane == 0) {
                     tma_commit();
@@ -295,12 +415,12 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 }
                 __syncwarp();
             } else {
-                if (kind == kSilence) {
+                if (kind == kSilence && member == 0) {
                     uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
                     write_silence(dst, cr.bytes, cr.channels, (cr.variant & 3u) + 1u, lane);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs]));
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs])); // every member arrives: the slot's barrier counts the team
             }
         }
         if (lane == 0) {

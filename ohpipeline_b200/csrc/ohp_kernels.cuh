@@ -50,13 +50,34 @@ namespace ohp {
 #ifndef OHP_CHUNK_BLOCK
 #define OHP_CHUNK_BLOCK 16
 #endif
+#ifndef OHP_LOADER
+#define OHP_LOADER 1        /* 1: place and start up to OHP_ISSUE_WIDTH chunks per round; 0: one chunk at a time */
+#endif
+#ifndef OHP_CONSUMER_POLL
+#define OHP_CONSUMER_POLL 2 /* 0: every lane waits on the barrier; 1: lane 0 waits, __syncwarp; 2: one look by all, then 1 */
+#endif
+#ifndef OHP_ISSUE_WIDTH
+#define OHP_ISSUE_WIDTH 8
+#endif
 #ifndef OHP_GROUPS_PER_STEP
 #define OHP_GROUPS_PER_STEP 1
 #endif
+#ifndef OHP_WARPS_PER_CHUNK
+#define OHP_WARPS_PER_CHUNK 1
+#endif
+// consumer warps that share one chunk (1 or 2): with 2, an aligned chunk's groups are split between the two warps of a
+// "team", halving the time a ring slot spends in the consumer stage.  Measured (profiles/README.md): no gain on
+// configs[1] (0.893 vs 0.890 of peak) and a loss on small chunks (0.68 vs 0.94 on configs[4]'s 2880-byte chunks:
+// twice the per-chunk barrier traffic), so one warp per chunk ships; the team path stays for experiments.
+constexpr int kWarpsPerChunk = OHP_WARPS_PER_CHUNK;
+constexpr uint32_t kIssueWidth = OHP_ISSUE_WIDTH;     // chunks the loader warp can place and start in one round (one per lane)
 constexpr int kGroupsPerStep = OHP_GROUPS_PER_STEP; // independent 16-subsample groups a lane works on at once
 constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of this many consecutive chunks
 constexpr int kConsumerWarps = OHP_CONSUMER_WARPS;
 constexpr int kThreads = 32 + kConsumerWarps * 32; // loader warp + consumer warps
+constexpr int kTeams = kConsumerWarps / kWarpsPerChunk;
+static_assert(kWarpsPerChunk == 1 || kWarpsPerChunk == 2, "one or two warps per chunk");
+static_assert(kConsumerWarps % kWarpsPerChunk == 0, "consumer warps come in teams");
 constexpr int kRecSlots = 64;                      // two batches of 32 decoded chunk records
 constexpr uint32_t kRingSlots = OHP_RING_SLOTS;    // chunks in flight per CTA (barrier pairs); <= 32
 constexpr uint32_t kRingBytes = OHP_RING_BYTES;    // shared-memory byte ring the chunk slots are carved from
@@ -64,7 +85,12 @@ constexpr uint32_t kMaxChunk = OHP_MAX_PCM_CHUNK_BYTES;
 constexpr uint32_t kSlotFront = 16;                // the output image may start up to 15 bytes before the input image
 constexpr uint32_t kSlotBack = 80;                 // over-read / over-write of the last 16-subsample group + funnel word
 static_assert(kRingBytes % 16 == 0 && kRingBytes >= 2 * (kSlotFront + kMaxChunk + 16 + kSlotBack), "ring too small");
-static_assert(kRingSlots <= 32 && (kRingSlots & (kRingSlots - 1)) == 0, "ring slots: power of two, at most one decode batch");
+static_assert(kRingSlots <= 32, "ring slots: at most one decode batch");
+// A barrier pair is waited on by parity, which only tells "the previous phase is over" from "it is not": every phase
+// of one pair must therefore be consumed by the SAME warp (it finishes phase p before it waits for p + 1).  Chunk k
+// uses pair k % kRingSlots and team k % kTeams, so the slot count has to be a multiple of the team count -- with 16
+// pairs and 5 or 6 teams a warp could wait two phases ahead of a load still in flight and be let through.
+static_assert(kRingSlots % kTeams == 0, "ring slots must be a multiple of the consumer team count");
 
 // device status word bits (OR-ed by the kernel, read back by ohp_sync)
 constexpr uint32_t kErrInvalidDesc = 1u;
@@ -183,9 +209,7 @@ struct __align__(128) SharedStorage
 {
     uint8_t ring[kRingBytes];
     ChunkRec rec[kRecSlots];          // indexed by (chunk ordinal & (kRecSlots-1)); decoded 32 at a time
-    uint64_t load_src[kRecSlots];     // loader's own notes: 16-byte aligned source of the chunk's span
     uint32_t ring_off[kRecSlots];     // where the chunk's slot starts in the ring (written when the load is issued)
-    uint32_t slot_bytes[kRingSlots];  // loader's own notes: bytes to reclaim when the slot is released
     uint16_t table2[OHP_RAMP_TABLE_ENTRIES];
     uint64_t full[kRingSlots];
     uint64_t empty[kRingSlots];
@@ -237,6 +261,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
@@ -597,17 +629,18 @@ __device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, u
 
 // Fast path: the image starts on a 16-byte boundary and the output goes back to the same bytes.  Each lane takes
 // groups of four units (16 subsamples = B x 16 bytes) with 128-bit shared-memory loads and stores.
+// g_begin..g_end: the groups this warp takes (a team of two warps splits the chunk).
 template <int B, uint32_t CHM>
-__device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+__device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t,
+                                               uint32_t g_begin, uint32_t groups)
 {
     UnitCtx cx;
     RampRegs rr;
     rr.table = table;
     load_ctx(cr, cx, rr);
-    const uint32_t groups = (cr.units + 3u) >> 2;
     // kGroupsPerStep independent groups per lane per step: one basic block, so their dependency chains interleave
     // (a lone warp per chunk has no other warp to hide LDS / IMAD latency behind)
-    for (uint32_t gb = 0; gb < groups; gb += 32u * kGroupsPerStep) { // warp-uniform trip count (the step synchronises the warp)
+    for (uint32_t gb = g_begin; gb < groups; gb += 32u * kGroupsPerStep) { // warp-uniform trip count (the step synchronises the warp)
         const uint32_t g0 = gb + t;
         uint32_t r[kGroupsPerStep][4 * B + 1];
         uint32_t w[kGroupsPerStep][4 * B];
@@ -820,13 +853,23 @@ __device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint
     }
 }
 
+// True when a team of two warps may split this chunk: the aligned in-place path (disjoint group ranges never touch
+// each other's bytes; the general path slides the image down by up to 15 bytes, so its halves would race).
+__device__ __forceinline__ bool chunk_splits(const ChunkRec& cr)
+{
+    const uint32_t chm = (cr.variant >> 2) & 3u;
+    return kWarpsPerChunk == 2 && cr.kind == kPcm && cr.out_fmt <= OHP_OUT_PACKED_LE && (cr.mode & kModeTransform) != 0
+        && (cr.variant & 16u) != 0 && (chm == kChmStereo || chm == kChmMul4);
+}
+
 template <int B>
-__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t)
+__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t,
+                                                   uint32_t g_begin, uint32_t g_end)
 {
     const uint32_t chm = (cr.variant >> 2) & 3u;
     const bool aligned = (cr.variant & 16u) != 0;
-    if (aligned && chm == kChmStereo) transform_aligned<B, kChmStereo>(cr, table, in_addr, out_addr, t);
-    else if (aligned && chm == kChmMul4) transform_aligned<B, kChmMul4>(cr, table, in_addr, out_addr, t);
+    if (aligned && chm == kChmStereo) transform_aligned<B, kChmStereo>(cr, table, in_addr, out_addr, t, g_begin, g_end);
+    else if (aligned && chm == kChmMul4) transform_aligned<B, kChmMul4>(cr, table, in_addr, out_addr, t, g_begin, g_end);
     else if (chm == kChmStereo) transform_any<B, kChmStereo>(cr, table, in_addr, out_addr, t);
     else if (chm == kChmMul4) transform_any<B, kChmMul4>(cr, table, in_addr, out_addr, t);
     else if (chm == kChmMono) transform_any<B, kChmMono>(cr, table, in_addr, out_addr, t);

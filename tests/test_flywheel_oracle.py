@@ -10,6 +10,7 @@ import pytest
 
 from ohpipeline_b200 import abi, capi
 from flywheel_util import SHAPES, training_block, train_frames
+from util import make_desc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "flywheel.npz")
 
@@ -135,3 +136,31 @@ def test_validate_refuses_what_the_reference_cannot_hold():
     assert capi.flywheel_validate(ok, 1 << 20, 100)[0] == abi.E_OUT_OF_RANGE
     both = np.concatenate([ok, capi.flywheel_job(48000, 2, 20)])
     assert capi.flywheel_validate(both, 1 << 20, 1 << 20) == (abi.E_INVALID_DESC, 1)
+
+
+def test_planar_sink_matches_the_real_flywheel_input(port, ref):
+    """FlywheelInput::Prepare (StarvationRamper.cpp:90-186) over real messages vs the oracle's OHP_OUT_PLANAR32_BE sink:
+    the last millisecond of a stream as 1-3 messages of any depth / endianness, plus leading silence."""
+    rng = np.random.default_rng(5)
+    for rate, ch, bits in [(44100, 2, 16), (48000, 2, 24), (96000, 6, 32), (192000, 8, 24), (48000, 1, 8), (88200, 3, 32)]:
+        for le in (False, True):
+            for with_silence in (False, True):
+                T = train_frames(rate)
+                fb = ch * bits // 8
+                pieces = sorted(set(int(x) for x in rng.integers(1, T, 2))) + [T]
+                wire = rng.integers(0, 256, T * fb, dtype=np.uint8)
+                descs = []
+                first = 0
+                for k, upto in enumerate(pieces):
+                    silence = with_silence and k == 0
+                    d = make_desc(src_off=0 if silence else first * fb, dst_off=first * 4, bytes=(upto - first) * fb,
+                                  bit_depth=bits, channels=ch, out_fmt=abi.OUT_PLANAR32_BE, aux=T,
+                                  flags=(abi.F_SILENCE if silence else (abi.F_IN_LITTLE_ENDIAN if le and bits > 8 else 0)))
+                    descs.append(d)
+                    first = upto
+                descs = np.concatenate(descs)
+                rc, want = ref.flywheel_input(descs, wire, rate, T * abi.jiffies_per_sample(rate))
+                assert rc == 0 and want.size == T * 4 * ch
+                rc, got = port.process_chunks(descs, wire, want.size)
+                assert rc == 0
+                assert np.array_equal(got, want), (rate, ch, bits, le, with_silence)
