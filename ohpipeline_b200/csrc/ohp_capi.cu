@@ -95,8 +95,9 @@ __device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uin
 #endif
 
 // Persistent, warp-specialised CTAs (see ohp_kernels.cuh): chunks are dealt block-cyclically to the CTAs; inside the
-// CTA the chunk with ordinal k belongs to consumer team k % kTeams (kWarpsPerChunk warps that split an aligned chunk
-// between them) and to ring slot k % kRingSlots.
+// CTA the chunk with ordinal k uses barrier pair k % kBarPairs and is transformed by whichever consumer warp draws
+// ticket k (OHP_DYNAMIC) -- so a warp that met a run of expensive chunks does not hold the in-order ring up while
+// its neighbours idle -- or by warp k % kConsumerWarps (static).
 __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -105,10 +106,11 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     const uint32_t lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < kRingSlots; s++) {
+        for (uint32_t s = 0; s < kBarPairs; s++) {
             mbar_init(smem_u32(&sm.full[s]), 1);
-            mbar_init(smem_u32(&sm.empty[s]), kWarpsPerChunk);
+            mbar_init(smem_u32(&sm.empty[s]), 1);
         }
+        sm.next_ticket = 0;
         fence_mbar_init();
     }
     for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) sm.table2[i] = p.table2[i];
@@ -172,8 +174,9 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 {
                     const uint32_t inflight = (uint32_t)(it0 - rd); // <= kRingSlots <= 32
                     const uint64_t r = rd + lane;
-                    const uint32_t rs = (uint32_t)(r % kRingSlots);
-                    const bool released = lane < inflight && mbar_test(smem_u32(&sm.empty[rs]), (uint32_t)(r / kRingSlots) & 1u);
+                    const uint32_t rs = (uint32_t)(r % kRingSlots); // lane rs remembers what the slot holds
+                    const bool released = lane < inflight
+                        && mbar_test(smem_u32(&sm.empty[(uint32_t)(r % kBarPairs)]), (uint32_t)(r / kBarPairs) & 1u);
                     const uint32_t mask = __ballot_sync(0xffffffffu, released);
                     const uint32_t nrel = mask == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~mask) - 1u; // reclaim is in order
                     uint32_t bytes = __shfl_sync(0xffffffffu, my_slot_bytes, rs);
@@ -201,8 +204,9 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     }
                     if (fit == 0) {
                         // ring full: block on the oldest slot (one lane polls), then sweep again
-                        const uint32_t os = (uint32_t)(rd % kRingSlots);
-                        if (lane == 0) OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[os]), (uint32_t)(rd / kRingSlots) & 1u, p.status));
+                        if (lane == 0) {
+                            OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[(uint32_t)(rd % kBarPairs)]), (uint32_t)(rd / kBarPairs) & 1u, p.status));
+                        }
                         __syncwarp();
                         continue;
                     }
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     if (lane < fit) {
                         const uint64_t it = it0 + lane;
                         sm.ring_off[(uint32_t)(it & (kRecSlots - 1))] = my_wr;
-                        const uint32_t full = smem_u32(&sm.full[(uint32_t)(it % kRingSlots)]);
+                        const uint32_t full = smem_u32(&sm.full[(uint32_t)(it % kBarPairs)]);
                         if (kind == kPcm) {
                             const uint8_t* al = reinterpret_cast<const uint8_t*>(src);
                             const uint32_t dst_smem = ring + my_wr + kSlotFront;
@@ -257,11 +261,12 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 const uint32_t waste = wrap ? kRingBytes - wr : 0u;
                 // reclaim, oldest first, until the slot fits and its barrier pair is free
                 while (free_bytes < need + waste || it - rd >= kRingSlots) {
-                    const uint32_t os = (uint32_t)(rd % kRingSlots);
                     // one lane polls (32 lanes hammering the same mbarrier slow the SM's barrier unit down measurably)
-                    if (lane == 0) OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[os]), (uint32_t)(rd / kRingSlots) & 1u, p.status));
+                    if (lane == 0) {
+                        OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[(uint32_t)(rd % kBarPairs)]), (uint32_t)(rd / kBarPairs) & 1u, p.status));
+                    }
                     __syncwarp();
-                    free_bytes += __shfl_sync(0xffffffffu, my_slot_bytes, os);
+                    free_bytes += __shfl_sync(0xffffffffu, my_slot_bytes, (uint32_t)(rd % kRingSlots));
                     rd++;
                 }
                 if (wrap) wr = 0;
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 free_bytes -= need + waste;
                 if (lane == 0) {
                     sm.ring_off[sl] = wr;
-                    const uint32_t full = smem_u32(&sm.full[bs]);
+                    const uint32_t full = smem_u32(&sm.full[(uint32_t)(it % kBarPairs)]);
                     if (kind == kPcm) {
                         const uint8_t* al = reinterpret_cast<const uint8_t*>(src);
                         const uint32_t dst_smem = ring + wr + kSlotFront;
@@ -301,16 +306,20 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
         }
     } else {
-        // ------------------------------------------------------------------ consumers: a team of kWarpsPerChunk warps per chunk
+        // ------------------------------------------------------------------ consumers: one warp per chunk
         const uint32_t cw = warp - 1;
-        const uint32_t team = cw / kWarpsPerChunk;
-        const uint32_t member = cw % kWarpsPerChunk; // member 0 leads: it does whatever is not split
         const uint32_t table = smem_u32(&sm.table2[0]);
-        for (uint64_t it = team; it < my_n; it += kTeams) {
-            const uint32_t bs = (uint32_t)(it % kRingSlots);
-            const uint32_t ph = (uint32_t)(it / kRingSlots) & 1u;
-            // every lane looks once (the data is usually there); if not, one lane polls and the warp barrier hands what
-            // it observed to the others -- 32 lanes spinning on one mbarrier slow the SM's barrier unit down measurably
+#if OHP_DYNAMIC
+        for (;;) {
+            unsigned long long ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&sm.next_ticket, 1ull);
+            const uint64_t it = __shfl_sync(0xffffffffu, ticket, 0);
+            if (it >= my_n) break;
+#else
+        for (uint64_t it = cw; it < my_n; it += kConsumerWarps) {
+#endif
+            const uint32_t bs = (uint32_t)(it % kBarPairs);
+            const uint32_t ph = (uint32_t)(it / kBarPairs) & 1u;
 #if OHP_CONSUMER_POLL == 0
             OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
 #elif OHP_CONSUMER_POLL == 1
@@ -325,8 +334,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
             const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
             const ChunkRec& cr = sm.rec[sl];
             const uint32_t kind = cr.kind;
-            const bool split = chunk_splits(cr);
-            if ((kind == kPcm || kind == kSilenceConv) && (member == 0 || split)) {
+            if (kind == kPcm || kind == kSilenceConv) {
                 uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
                 const uint32_t head = cr.head;
                 const uint32_t in_addr = ring + sm.ring_off[sl] + kSlotFront;          // 16-byte aligned; image at +head
@@ -334,15 +342,8 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 const uint32_t image = in_addr + head - ((head - cr.dst_lo) & 15u);
                 const uint32_t out_addr = image & ~3u;                                 // word stores; == image unless dst is odd
                 const uint32_t fmt = cr.out_fmt;
-                // this warp's share: groups [g_begin, g_end) = bytes [b_begin, b_end) of the image
                 const uint32_t B = (cr.variant & 3u) + 1u;
-                const uint32_t groups = (cr.units + 3u) >> 2;
-                uint32_t g_begin = 0, g_end = groups, b_begin = 0, b_end = cr.out_bytes;
-                if (split) {
-                    const uint32_t g_mid = (groups + 1u) >> 1;
-                    if (member == 0) { g_end = g_mid; b_end = min(g_mid * 16u * B, cr.out_bytes); }
-                    else { g_begin = g_mid; b_begin = min(g_mid * 16u * B, cr.out_bytes); }
-                }
+                const uint32_t g_begin = 0, g_end = (cr.units + 3u) >> 2, b_begin = 0, b_end = cr.out_bytes;
                 if (kind == kSilenceConv) {
                     silence_to_smem(in_addr, cr.bytes, cr.channels, lane);
                     __syncwarp();
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
                 // the finished image sits at out_addr: one TMA bulk store for its 16-byte aligned interior when out_addr is
                 // congruent to dst mod 16, a register funnel otherwise (destination not 4-byte aligned).  The planar sink
-                // has already written global memory itself.  (A split chunk is aligned: each half is a bulk store.)
+                // has already written global memory itself.
                 if (fmt != OHP_OUT_PLANAR32_BE && b_begin < b_end) {
                     store_image_warp(out_addr + b_begin, dst + b_begin, b_end - b_begin, lane);
                 }
@@ -415,12 +416,12 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 }
                 __syncwarp();
             } else {
-                if (kind == kSilence && member == 0) {
+                if (kind == kSilence) {
                     uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
                     write_silence(dst, cr.bytes, cr.channels, (cr.variant & 3u) + 1u, lane);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs])); // every member arrives: the slot's barrier counts the team
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs]));
             }
         }
         if (lane == 0) {

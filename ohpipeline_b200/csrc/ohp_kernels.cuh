@@ -1,26 +1,34 @@
 // ohp_kernels.cuh -- device code of the fused ramp + format-convert path (sm_100a).
 //
-// One MsgPlayable ("chunk") is the unit of work.  The kernel is persistent and warp-specialised; every CTA runs
+// One MsgPlayable ("chunk") is the unit of work.  The kernel is persistent and warp-specialised; two CTAs per SM,
+// each with a 103 KB shared-memory BYTE RING, one loader warp and eight consumer warps:
 //
-//   loader  (warp 0)            walks this CTA's chunks: its 32 lanes fetch and decode 32 descriptors at a time
-//                               (restating the reference's ASSERTs and precomputing the per-chunk ramp constants),
-//                               then one lane carves, chunk by chunk, a slot out of a shared-memory BYTE RING and
-//                               pulls the 16-byte-aligned span that covers the chunk's source bytes into it with ONE
-//                               TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on an mbarrier);
-//   consumers (kConsumerWarps)  each warp owns every kConsumerWarps-th chunk from start to finish: it waits on the
-//                               slot's "full" mbarrier, transforms the chunk IN PLACE in "units" of four subsamples
-//                               held in registers -- unpack (BE or LE wire order: DecodedAudio::CopyToBigEndian*,
-//                               Msg.cpp:380-408), attenuate (MsgPlayablePcm::ApplyAttenuation, Msg.cpp:2736-2751),
-//                               ramp (RampApplicator::GetNextSample, Msg.cpp:832-899), repack for the IPcmProcessor
-//                               sink (packed BE / packed LE); byte shuffles are PRMT, the ramp one IMAD per subsample
-//                               -- then writes it out itself: the 16-byte-aligned interior of the destination with
-//                               ONE TMA bulk store (cp.async.bulk.global.shared::cta), the ragged head/tail (chunks
-//                               start at arbitrary byte offsets: a 24-bit stereo frame is 6 bytes, a split playable
-//                               starts wherever the ramp ended) with byte stores, and hands the slot back.
+//   loader  (warp 0)    walks this CTA's chunks: its 32 lanes fetch and decode 32 descriptors at a time (restating the
+//                       reference's ASSERTs and precomputing the per-chunk ramp constants; the next batch's descriptors
+//                       are already in flight), then the whole warp runs the issue loop in lockstep, everything it
+//                       needs of chunk j arriving by shuffle from lane j:  (1) lanes test the "empty" barriers of all
+//                       slots in flight at once and reclaim, in order, what has been released;  (2) as many of the next
+//                       chunks as fit are given contiguous slots in the ring;  (3) one lane per placed chunk starts ONE
+//                       TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on the slot's "full" mbarrier)
+//                       of the 16-byte-aligned span covering the chunk's source bytes.  When the consumers keep up the
+//                       ring is full and the loader places one chunk per released slot; when the loader is what limits
+//                       (small chunks) there is room, and it places up to OHP_ISSUE_WIDTH per round;
+//   consumers           take chunks by TICKET (a shared-memory counter), first come first served, so a warp that met
+//                       a run of expensive chunks does not hold up the in-order ring while its neighbours idle.  The
+//                       warp waits on the chunk's "full" mbarrier, transforms the chunk IN PLACE in "units" of four
+//                       subsamples held in registers -- unpack (BE or LE wire order: DecodedAudio::CopyToBigEndian*,
+//                       Msg.cpp:380-408), attenuate (MsgPlayablePcm::ApplyAttenuation, Msg.cpp:2736-2751), ramp
+//                       (RampApplicator::GetNextSample, Msg.cpp:832-899), repack for the IPcmProcessor sink; byte
+//                       shuffles are PRMT, the ramp one IMAD per subsample -- then writes it out itself: the
+//                       16-byte-aligned interior of the destination with ONE TMA bulk store
+//                       (cp.async.bulk.global.shared::cta), the ragged head/tail (chunks start at arbitrary byte
+//                       offsets: a 24-bit stereo frame is 6 bytes, a split playable starts wherever the ramp ended)
+//                       with byte stores, and hands the slot back ("empty" mbarrier) once the store has read it.
 //
 // In place means a chunk in flight costs one buffer, not two, so the 227 KB of an SM hold twice as many chunks between
 // "load issued" and "store drained" -- that, not arithmetic, is what bounds an HBM-bound kernel.  A warp per chunk means
-// no cross-warp synchronisation on the data path and one setup per chunk.
+// no cross-warp synchronisation on the data path and one setup per chunk.  (profiles/README.md has the measurements
+// behind the shape: CTAs per SM, ring size, warps, issue width, polling discipline.)
 //
 // The 512-entry ramp curve sits in shared memory as 2*multiplier, so that the high half of the 16x16 product is
 // the reference's (s16 * mult) >> 15; the per-frame ramp position trunc(i*total/(N-1)) is an exact multiply-high by
@@ -39,13 +47,13 @@ namespace ohp {
 
 // Tunables (overridable with -D for experiments; the defaults are what ships)
 #ifndef OHP_CONSUMER_WARPS
-#define OHP_CONSUMER_WARPS 4
+#define OHP_CONSUMER_WARPS 8
 #endif
 #ifndef OHP_RING_BYTES
-#define OHP_RING_BYTES 47104
+#define OHP_RING_BYTES 105472
 #endif
 #ifndef OHP_RING_SLOTS
-#define OHP_RING_SLOTS 16
+#define OHP_RING_SLOTS 32
 #endif
 #ifndef OHP_CHUNK_BLOCK
 #define OHP_CHUNK_BLOCK 16
@@ -54,7 +62,7 @@ namespace ohp {
 #define OHP_LOADER 1        /* 1: place and start up to OHP_ISSUE_WIDTH chunks per round; 0: one chunk at a time */
 #endif
 #ifndef OHP_CONSUMER_POLL
-#define OHP_CONSUMER_POLL 2 /* 0: every lane waits on the barrier; 1: lane 0 waits, __syncwarp; 2: one look by all, then 1 */
+#define OHP_CONSUMER_POLL 0 /* 0: every lane waits on the barrier; 1: lane 0 waits, __syncwarp; 2: one look by all, then 1 */
 #endif
 #ifndef OHP_ISSUE_WIDTH
 #define OHP_ISSUE_WIDTH 8
@@ -62,22 +70,14 @@ namespace ohp {
 #ifndef OHP_GROUPS_PER_STEP
 #define OHP_GROUPS_PER_STEP 1
 #endif
-#ifndef OHP_WARPS_PER_CHUNK
-#define OHP_WARPS_PER_CHUNK 1
+#ifndef OHP_DYNAMIC
+#define OHP_DYNAMIC 1       /* 1: consumer warps take chunks by ticket (first come, first served); 0: chunk k -> warp k % warps */
 #endif
-// consumer warps that share one chunk (1 or 2): with 2, an aligned chunk's groups are split between the two warps of a
-// "team", halving the time a ring slot spends in the consumer stage.  Measured (profiles/README.md): no gain on
-// configs[1] (0.893 vs 0.890 of peak) and a loss on small chunks (0.68 vs 0.94 on configs[4]'s 2880-byte chunks:
-// twice the per-chunk barrier traffic), so one warp per chunk ships; the team path stays for experiments.
-constexpr int kWarpsPerChunk = OHP_WARPS_PER_CHUNK;
 constexpr uint32_t kIssueWidth = OHP_ISSUE_WIDTH;     // chunks the loader warp can place and start in one round (one per lane)
 constexpr int kGroupsPerStep = OHP_GROUPS_PER_STEP; // independent 16-subsample groups a lane works on at once
 constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of this many consecutive chunks
 constexpr int kConsumerWarps = OHP_CONSUMER_WARPS;
 constexpr int kThreads = 32 + kConsumerWarps * 32; // loader warp + consumer warps
-constexpr int kTeams = kConsumerWarps / kWarpsPerChunk;
-static_assert(kWarpsPerChunk == 1 || kWarpsPerChunk == 2, "one or two warps per chunk");
-static_assert(kConsumerWarps % kWarpsPerChunk == 0, "consumer warps come in teams");
 constexpr int kRecSlots = 64;                      // two batches of 32 decoded chunk records
 constexpr uint32_t kRingSlots = OHP_RING_SLOTS;    // chunks in flight per CTA (barrier pairs); <= 32
 constexpr uint32_t kRingBytes = OHP_RING_BYTES;    // shared-memory byte ring the chunk slots are carved from
@@ -86,11 +86,21 @@ constexpr uint32_t kSlotFront = 16;                // the output image may start
 constexpr uint32_t kSlotBack = 80;                 // over-read / over-write of the last 16-subsample group + funnel word
 static_assert(kRingBytes % 16 == 0 && kRingBytes >= 2 * (kSlotFront + kMaxChunk + 16 + kSlotBack), "ring too small");
 static_assert(kRingSlots <= 32, "ring slots: at most one decode batch");
-// A barrier pair is waited on by parity, which only tells "the previous phase is over" from "it is not": every phase
-// of one pair must therefore be consumed by the SAME warp (it finishes phase p before it waits for p + 1).  Chunk k
-// uses pair k % kRingSlots and team k % kTeams, so the slot count has to be a multiple of the team count -- with 16
-// pairs and 5 or 6 teams a warp could wait two phases ahead of a load still in flight and be let through.
-static_assert(kRingSlots % kTeams == 0, "ring slots must be a multiple of the consumer team count");
+// A barrier pair is waited on by parity, which only tells "the previous phase is over" from "it is not": whoever waits
+// for phase q of a pair must know that phase q - 1 has completed.
+//   * static assignment (chunk k -> warp k % warps, pair k % kRingSlots): every phase of one pair must be consumed by
+//     the SAME warp (it finishes phase q - 1 before it waits for q), so the slot count is a multiple of the warp count;
+//   * ticket assignment (OHP_DYNAMIC): any warp may hold any ticket, and a warp can be handed a ticket whose chunk has
+//     not even been started.  With S = kRingSlots chunks in flight at most and W <= S warps, a ticket y is never more
+//     than S + W ahead of the oldest chunk o still loading (finished and running tickets are loaded, hence < o + S;
+//     at most W tickets are blocked), so with 2 S pairs the previous user of y's pair, chunk y - 2 S < o, has landed.
+#if OHP_DYNAMIC
+constexpr uint32_t kBarPairs = 2u * kRingSlots;
+static_assert((uint32_t)kConsumerWarps <= kRingSlots, "ticket assignment needs at most one warp per ring slot");
+#else
+constexpr uint32_t kBarPairs = kRingSlots;
+static_assert(kRingSlots % kConsumerWarps == 0, "ring slots must be a multiple of the consumer warp count");
+#endif
 
 // device status word bits (OR-ed by the kernel, read back by ohp_sync)
 constexpr uint32_t kErrInvalidDesc = 1u;
@@ -211,8 +221,9 @@ struct __align__(128) SharedStorage
     ChunkRec rec[kRecSlots];          // indexed by (chunk ordinal & (kRecSlots-1)); decoded 32 at a time
     uint32_t ring_off[kRecSlots];     // where the chunk's slot starts in the ring (written when the load is issued)
     uint16_t table2[OHP_RAMP_TABLE_ENTRIES];
-    uint64_t full[kRingSlots];
-    uint64_t empty[kRingSlots];
+    uint64_t full[kBarPairs];
+    uint64_t empty[kBarPairs];
+    unsigned long long next_ticket;   // OHP_DYNAMIC: ordinal of the next chunk a consumer warp will take
 };
 
 // Work distribution: chunks are dealt to the CTAs block-cyclically, kChunkBlock consecutive chunks at a time, so that
@@ -629,7 +640,7 @@ __device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, u
 
 // Fast path: the image starts on a 16-byte boundary and the output goes back to the same bytes.  Each lane takes
 // groups of four units (16 subsamples = B x 16 bytes) with 128-bit shared-memory loads and stores.
-// g_begin..g_end: the groups this warp takes (a team of two warps splits the chunk).
+// g_begin..groups: the groups to transform (the whole chunk in the shipped kernel).
 template <int B, uint32_t CHM>
 __device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t,
                                                uint32_t g_begin, uint32_t groups)
@@ -851,15 +862,6 @@ __device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint
         }
         sts128(a + 16u * v, z);
     }
-}
-
-// True when a team of two warps may split this chunk: the aligned in-place path (disjoint group ranges never touch
-// each other's bytes; the general path slides the image down by up to 15 bytes, so its halves would race).
-__device__ __forceinline__ bool chunk_splits(const ChunkRec& cr)
-{
-    const uint32_t chm = (cr.variant >> 2) & 3u;
-    return kWarpsPerChunk == 2 && cr.kind == kPcm && cr.out_fmt <= OHP_OUT_PACKED_LE && (cr.mode & kModeTransform) != 0
-        && (cr.variant & 16u) != 0 && (chm == kChmStereo || chm == kChmMul4);
 }
 
 template <int B>
