@@ -247,6 +247,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # the image's default prints a version banner on stdout, next to the JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -348,6 +349,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or min(args.steps, 5)
+        # every rank pins its whole batch (in + out) in host memory: refuse loudly rather than drive the box out of memory
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+            need = (w.in_bytes + w.out_bytes) * world
+            if need > 0.7 * avail:
+                raise SystemExit("bench.py: e2e needs %.0f GB of pinned host memory over %d ranks, %.0f GB available"
+                                 % (need / 1e9, world, avail / 1e9))
+        except ImportError:
+            pass
         h_in, h_in_ptr = ctx.host_alloc(w.in_bytes)
         h_out, h_out_ptr = ctx.host_alloc(w.out_bytes)
         ctx.memcpy_d2h(h_in, d_in.data_ptr(), st)

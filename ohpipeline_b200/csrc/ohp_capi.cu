@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cctype>
 #include <mutex>
+#include <sched.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -506,6 +508,8 @@ struct ohp_context
     bool timed = false;
     uint64_t launches = 0;
     std::vector<cudaEvent_t> slice_events; // ohp_process_host pipeline, reused across calls
+    cpu_set_t local_cpus;                  // cores of the NUMA node this GPU hangs off (empty set: unknown)
+    bool have_local_cpus = false;
     std::string error;
 };
 
@@ -568,6 +572,46 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
     }
     ctx->launches++;
     return OHP_OK;
+}
+
+// Cores of the NUMA node the device's PCIe root port belongs to (sysfs).  Pinned buffers are allocated from a thread
+// bound to them, so that DMA between host memory and this GPU does not cross the socket interconnect: with one
+// process per GPU on a two-socket box that is the difference between every rank hammering socket 0's memory and each
+// rank using its own.
+static bool device_local_cpus(int device, cpu_set_t* out)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    for (char* c = bus; *c; c++) *c = (char)std::tolower((unsigned char)*c);
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = std::fscanf(f, "%d", &node);
+    std::fclose(f);
+    if (got != 1 || node < 0) return false;
+    std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = std::fopen(path, "r");
+    if (!f) return false;
+    char list[1024] = {0};
+    const bool ok = std::fgets(list, (int)sizeof list, f) != nullptr;
+    std::fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(out);
+    int count = 0;
+    for (const char* c = list; *c;) {
+        if (!std::isdigit((unsigned char)*c)) { c++; continue; }
+        char* end = nullptr;
+        long lo = std::strtol(c, &end, 10), hi = lo;
+        if (*end == '-') hi = std::strtol(end + 1, &end, 10);
+        for (long k = lo; k <= hi && k < CPU_SETSIZE; k++) { CPU_SET((int)k, out); count++; }
+        c = end;
+    }
+    return count > 0;
 }
 
 template <class T>
@@ -683,6 +727,7 @@ int ohp_create(int device, ohp_context** out_ctx)
     if (!ctx) return fail(nullptr, OHP_E_NO_MEMORY, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->have_local_cpus = device_local_cpus(device, &ctx->local_cpus);
 #define OHP_CREATE(call)                                                          \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -890,7 +935,13 @@ int ohp_host_alloc(ohp_context* ctx, uint64_t bytes, void** out_hptr)
 {
     if (!ctx || !out_hptr) return OHP_E_INVALID_ARG;
     OHP_CUDA(ctx, cudaSetDevice(ctx->device));
-    OHP_CUDA(ctx, cudaMallocHost(out_hptr, bytes ? bytes : 1));
+    // allocate (and thereby touch and pin) the pages from a thread bound to the GPU's NUMA node
+    cpu_set_t saved;
+    const bool rebind = ctx->have_local_cpus && sched_getaffinity(0, sizeof saved, &saved) == 0
+                        && sched_setaffinity(0, sizeof ctx->local_cpus, &ctx->local_cpus) == 0;
+    const cudaError_t e = cudaMallocHost(out_hptr, bytes ? bytes : 1);
+    if (rebind) (void)sched_setaffinity(0, sizeof saved, &saved);
+    if (e != cudaSuccess) return fail(ctx, OHP_E_CUDA, "cudaMallocHost", e);
     return OHP_OK;
 }
 
