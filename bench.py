@@ -323,6 +323,7 @@ def main():
     ctx.sync(st)
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
+    inflight_cap = ctx.inflight_cap()
     if dist is not None:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -408,6 +409,7 @@ def main():
     if rank == 0:
         cfg.update({"chunks_per_step_per_gpu": n_chunks, "host_schedule_build_s": round(t_sched, 3),
                     "device_schedule_build_s": round(min(t_dev), 4),
+                    "inflight_chunks_per_cta": inflight_cap,
                     "descriptors": "built on the GPU (ohp_schedule_count/emit_device), identical to the host model's"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

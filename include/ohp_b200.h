@@ -160,6 +160,11 @@ int         ohp_memcpy_d2h(ohp_context* ctx, void* hptr, const void* dptr, uint6
 /* Instrumentation ----------------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t    ohp_launch_count(const ohp_context* ctx);
+/* Chunks per thread block the most recent ohp_process_device launch kept in flight.  Large batches are tuned: the first
+ * few launches of a batch shape (same n, in_bytes, out_bytes) each try a candidate between CUDA events on the caller's
+ * stream, later ones use the fastest (OHP_AUTOTUNE=0 or OHP_CAP_CHUNKS=<k> in the environment switch that off).
+ * The value never changes results. */
+uint32_t    ohp_inflight_cap(const ohp_context* ctx);
 /* Device time, in ms, of the most recent ohp_process_device kernel(s), measured with CUDA events
  * on the launching stream; blocks until they finish.  -1 when timing is disabled. */
 int         ohp_set_timing(ohp_context* ctx, int enabled);

@@ -74,6 +74,9 @@ def cuda_lib():
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ohp_launch_count.restype = C.c_uint64
         L.ohp_launch_count.argtypes = [C.c_void_p]
+        if hasattr(L, "ohp_inflight_cap"):
+            L.ohp_inflight_cap.restype = C.c_uint32
+            L.ohp_inflight_cap.argtypes = [C.c_void_p]
         if hasattr(L, "ohp_flywheel_device"):  # include/ohp_flywheel.h
             L.ohp_flywheel_out_bytes.restype = C.c_uint32
             L.ohp_flywheel_out_bytes.argtypes = [C.c_void_p]
@@ -319,6 +322,9 @@ class Context:
 
     def launch_count(self):
         return int(self._L.ohp_launch_count(self._h))
+
+    def inflight_cap(self):
+        return int(self._L.ohp_inflight_cap(self._h))
 
     def flywheel_device(self, d_jobs, n, d_in, in_bytes, d_out, out_bytes, stream=None):
         """Asynchronous: FlywheelRamperManager::Ramp + RampGenerator::ProcessFragment for n jobs (device pointers)."""

@@ -123,14 +123,14 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     const long long t_begin = clock64();
 #endif
     // chunks of this CTA: ordinal k <-> chunk cta_chunk_index(k)
-    const uint64_t my_n = cta_chunk_count(p.n, blockIdx.x, gridDim.x);
+    const uint64_t my_n = cta_chunk_count(p.n, blockIdx.x, gridDim.x, p.chunk_block);
     const uint32_t ring = smem_u32(&sm.ring[0]);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader
         const uint4* dp = reinterpret_cast<const uint4*>(p.descs);
         uint32_t wr = 0;              // next free byte of the ring
-        uint32_t free_bytes = kRingBytes;
+        uint32_t free_bytes = p.cap_bytes;
         uint64_t rd = 0;              // oldest chunk whose slot has not been reclaimed yet
         uint32_t my_slot_bytes = 0;   // lane s: bytes to give back when ring slot s (barrier pair s) is released
         // The whole warp walks the issue loop in lockstep (warp-uniform control flow) and lane 0 performs the side
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
         // batch are fetched before the loop, so their global-memory latency hides behind it.
         uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
         if (lane < my_n) {
-            const uint64_t c = cta_chunk_index(lane, blockIdx.x, gridDim.x);
+            const uint64_t c = cta_chunk_index(lane, blockIdx.x, gridDim.x, p.chunk_block);
             d0 = __ldg(dp + 2 * c);
             d1 = __ldg(dp + 2 * c + 1);
         }
@@ -153,11 +153,11 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
             if (k < my_n) {
                 uint64_t src_off;
                 const uint32_t err = decode_chunk(p, d0, d1, r, src_off);
-                if (err) report(p, err, cta_chunk_index(k, blockIdx.x, gridDim.x));
+                if (err) report(p, err, cta_chunk_index(k, blockIdx.x, gridDim.x, p.chunk_block));
                 src_al = reinterpret_cast<uint64_t>(p.in) + src_off - r.head;
             }
             if (k + 32 < my_n) {
-                const uint64_t c = cta_chunk_index(k + 32, blockIdx.x, gridDim.x);
+                const uint64_t c = cta_chunk_index(k + 32, blockIdx.x, gridDim.x, p.chunk_block);
                 d0 = __ldg(dp + 2 * c);
                 d1 = __ldg(dp + 2 * c + 1);
             }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                         const uint32_t need = __shfl_sync(0xffffffffu, my_need, j + g);
                         const bool wrap = wr_s + need > kRingBytes;       // the slot must be contiguous: skip the end of the ring
                         const uint32_t waste = wrap ? kRingBytes - wr_s : 0u;
-                        if (free_s < need + waste || it0 + g - rd >= kRingSlots) break;
+                        if (free_s < need + waste || it0 + g - rd >= p.cap_chunks) break;
                         if (wrap) wr_s = 0;
                         if (lane == g) my_wr = wr_s;
                         if (lane == (uint32_t)((it0 + g) % kRingSlots)) my_slot_bytes = need + waste;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 const bool wrap = wr + need > kRingBytes;           // the slot must be contiguous: skip the end of the ring
                 const uint32_t waste = wrap ? kRingBytes - wr : 0u;
                 // reclaim, oldest first, until the slot fits and its barrier pair is free
-                while (free_bytes < need + waste || it - rd >= kRingSlots) {
+                while (free_bytes < need + waste || it - rd >= p.cap_chunks) {
                     // one lane polls (32 lanes hammering the same mbarrier slow the SM's barrier unit down measurably)
                     if (lane == 0) {
                         OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[(uint32_t)(rd % kBarPairs)]), (uint32_t)(rd / kBarPairs) & 1u, p.status));
@@ -486,6 +486,26 @@ static const uint16_t kRampTable[OHP_RAMP_TABLE_ENTRIES] = {
 
 static thread_local std::string g_create_error;
 
+// In-flight tuning.  How many chunks a CTA should keep in flight is the one knob whose best value depends on the batch
+// in a way the shape cannot settle: configs[1] (uniform 5760-byte chunks) peaks sharply at 12 (0.985 of the copy peak
+// against 0.895 at 16 and above, 0.945 at 10), configs[2] and small chunks want everything the ring holds
+// (profiles/README.md).  So a context learns it per batch signature: the first launches of a signature each run with a
+// different candidate between CUDA events on the caller's stream, later launches read the finished timings and use the
+// fastest.  Results never depend on the cap; only large batches are tuned.
+constexpr int kTuneCandidates = 3;  // three, so that a benchmark's customary three warm-up launches do all the exploring
+static const uint32_t kTuneCaps[kTuneCandidates] = {kRingSlots, 12u, 18u};
+constexpr uint64_t kTuneMinBytes = 256ull << 20; // batches below this are launch-latency territory: not worth tuning
+constexpr uint64_t kTuneMinChunks = 65536;
+struct TuneEntry
+{
+    uint64_t n = 0, in_bytes = 0, out_bytes = 0;
+    int launched = 0;                 // candidates started so far
+    bool have[kTuneCandidates] = {};
+    float ms[kTuneCandidates] = {};
+    cudaEvent_t ev[kTuneCandidates][2] = {};
+    uint64_t last_use = 0;
+};
+
 } // namespace ohp
 
 struct ohp_context
@@ -508,6 +528,13 @@ struct ohp_context
     bool timed = false;
     uint64_t launches = 0;
     std::vector<cudaEvent_t> slice_events; // ohp_process_host pipeline, reused across calls
+    uint32_t cap_bytes = ohp::kRingBytes;   // in-flight limits per CTA (experiments: OHP_CAP_BYTES / OHP_CAP_CHUNKS)
+    uint32_t cap_chunks = ohp::kRingSlots;
+    uint32_t chunk_block = ohp::kChunkBlock;
+    bool cap_pinned = false;               // OHP_CAP_CHUNKS / OHP_CAP_BYTES given: no tuning
+    bool autotune = true;                  // OHP_AUTOTUNE=0 turns it off
+    std::vector<ohp::TuneEntry> tune;      // one entry per batch signature seen (a few)
+    uint32_t last_cap_chunks = ohp::kRingSlots; // what the most recent launch used (ohp_inflight_cap)
     cpu_set_t local_cpus;                  // cores of the NUMA node this GPU hangs off (empty set: unknown)
     bool have_local_cpus = false;
     std::string error;
@@ -560,12 +587,65 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
     p.out_bytes = out_bytes;
     p.table2 = ctx->d_table2;
     p.status = ctx->d_status;
+    p.cap_bytes = ctx->cap_bytes;
+    p.cap_chunks = ctx->cap_chunks;
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctx->ctas_per_sm;
-    const uint64_t blocks = (n + kChunkBlock - 1) / kChunkBlock; // chunks are dealt kChunkBlock at a time
+    // chunks are dealt in runs of chunk_block: long runs keep what a CTA has in flight inside one stretch of each arena,
+    // short ones keep every CTA busy when the batch is small (at least ~8 runs per CTA)
+    uint64_t chunk_block = ctx->chunk_block;
+    while (chunk_block > kMinChunkBlock && n / chunk_block < grid * 8) chunk_block >>= 1;
+    p.chunk_block = (uint32_t)chunk_block;
+    const uint64_t blocks = (n + chunk_block - 1) / chunk_block;
     if (grid > blocks) grid = blocks;
+    // in-flight tuning (see TuneEntry)
+    TuneEntry* tune = nullptr;
+    int trial = -1;
+    if (ctx->autotune && !ctx->cap_pinned && in_bytes + out_bytes >= kTuneMinBytes && n >= kTuneMinChunks) {
+        static uint64_t use_clock = 0;
+        for (TuneEntry& t : ctx->tune) {
+            if (t.n == n && t.in_bytes == in_bytes && t.out_bytes == out_bytes) tune = &t;
+        }
+        if (!tune) {
+            if (ctx->tune.size() < 8) {
+                ctx->tune.emplace_back();
+                tune = &ctx->tune.back();
+            } else {
+                tune = &ctx->tune[0];
+                for (TuneEntry& t : ctx->tune) if (t.last_use < tune->last_use) tune = &t;
+                for (int c = 0; c < kTuneCandidates; c++) { tune->have[c] = false; }
+                tune->launched = 0;
+            }
+            tune->n = n; tune->in_bytes = in_bytes; tune->out_bytes = out_bytes;
+        }
+        tune->last_use = ++use_clock;
+        int best = -1;
+        for (int c = 0; c < tune->launched; c++) {
+            if (!tune->have[c] && cudaEventQuery(tune->ev[c][1]) == cudaSuccess) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, tune->ev[c][0], tune->ev[c][1]) == cudaSuccess) { tune->ms[c] = ms; tune->have[c] = true; }
+            }
+            if (tune->have[c] && (best < 0 || tune->ms[c] < tune->ms[best])) best = c;
+        }
+        (void)cudaGetLastError(); // cudaErrorNotReady from the query is not an error
+        if (tune->launched < kTuneCandidates) {
+            trial = tune->launched;
+            for (int k = 0; k < 2; k++) {
+                if (!tune->ev[trial][k]) OHP_CUDA(ctx, cudaEventCreate(&tune->ev[trial][k]));
+            }
+            p.cap_chunks = kTuneCaps[trial];
+        } else if (best >= 0) {
+            p.cap_chunks = kTuneCaps[best];
+        }
+    }
+    ctx->last_cap_chunks = p.cap_chunks;
     if (ctx->timing) OHP_CUDA(ctx, cudaEventRecord(ctx->ev_start, st));
+    if (trial >= 0) OHP_CUDA(ctx, cudaEventRecord(tune->ev[trial][0], st));
     ramp_convert_kernel<<<(unsigned)grid, kThreads, sizeof(SharedStorage), st>>>(p);
     OHP_CUDA(ctx, cudaGetLastError());
+    if (trial >= 0) {
+        OHP_CUDA(ctx, cudaEventRecord(tune->ev[trial][1], st));
+        tune->launched = trial + 1;
+    }
     if (ctx->timing) {
         OHP_CUDA(ctx, cudaEventRecord(ctx->ev_stop, st));
         ctx->timed = true;
@@ -728,6 +808,19 @@ int ohp_create(int device, ohp_context** out_ctx)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->have_local_cpus = device_local_cpus(device, &ctx->local_cpus);
+    if (const char* e = std::getenv("OHP_CAP_BYTES")) {
+        const long v = std::atol(e);
+        if (v >= (long)(2 * (kSlotFront + kMaxChunk + 16 + kSlotBack)) && v <= (long)kRingBytes) { ctx->cap_bytes = (uint32_t)v; ctx->cap_pinned = true; }
+    }
+    if (const char* e = std::getenv("OHP_AUTOTUNE")) ctx->autotune = std::atoi(e) != 0;
+    if (const char* e = std::getenv("OHP_CHUNK_BLOCK")) {
+        const long v = std::atol(e);
+        if (v >= 1 && v <= 65536) ctx->chunk_block = (uint32_t)v;
+    }
+    if (const char* e = std::getenv("OHP_CAP_CHUNKS")) {
+        const long v = std::atol(e);
+        if (v >= 1 && v <= (long)kRingSlots) { ctx->cap_chunks = (uint32_t)v; ctx->cap_pinned = true; }
+    }
 #define OHP_CREATE(call)                                                          \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -781,6 +874,12 @@ int ohp_destroy(ohp_context* ctx)
     if (ctx->ev_start) (void)cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) (void)cudaEventDestroy(ctx->ev_stop);
     for (cudaEvent_t e : ctx->slice_events) (void)cudaEventDestroy(e);
+    for (ohp::TuneEntry& t : ctx->tune) {
+        for (int c = 0; c < ohp::kTuneCandidates; c++) {
+            if (t.ev[c][0]) (void)cudaEventDestroy(t.ev[c][0]);
+            if (t.ev[c][1]) (void)cudaEventDestroy(t.ev[c][1]);
+        }
+    }
     if (ctx->stream) (void)cudaStreamDestroy(ctx->stream);
     if (ctx->copy_in) (void)cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) (void)cudaStreamDestroy(ctx->copy_out);
@@ -853,6 +952,8 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
     };
     const bool timing = ctx->timing;
     ctx->timing = false; // per-kernel events are only meaningful for a single launch
+    const bool autotune = ctx->autotune;
+    ctx->autotune = false; // slices are small and PCIe-bound
     size_t lo = 0;
     while (lo < n) {
         uint64_t in_lo = UINT64_MAX, in_hi = 0, out_lo = UINT64_MAX, out_hi = 0, moved = 0;
@@ -884,6 +985,7 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
         OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
         if ((rc = launch(ctx, ctx->d_descs + lo, hi - lo, ctx->d_in, in_bytes, ctx->d_out, out_bytes, ctx->stream)) != OHP_OK) {
             ctx->timing = timing;
+            ctx->autotune = autotune;
             return rc;
         }
         OHP_CUDA(ctx, cudaEventRecord(ev_k, ctx->stream));
@@ -894,6 +996,7 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
         lo = hi;
     }
     ctx->timing = timing;
+    ctx->autotune = autotune;
     OHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     OHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return read_status(ctx, ctx->stream);
@@ -1088,6 +1191,8 @@ int ohp_flywheel_device(ohp_context* ctx, const ohp_flywheel_job* d_jobs, size_t
 }
 
 uint64_t ohp_launch_count(const ohp_context* ctx) { return ctx ? ctx->launches : 0; }
+
+uint32_t ohp_inflight_cap(const ohp_context* ctx) { return ctx ? ctx->last_cap_chunks : 0; }
 
 // Instrumentation builds only (-DOHP_PROFILE_WAITS): copy out and clear the 16 status words.
 int ohp_debug_counters(ohp_context* ctx, uint32_t* out16)

@@ -75,7 +75,8 @@ namespace ohp {
 #endif
 constexpr uint32_t kIssueWidth = OHP_ISSUE_WIDTH;     // chunks the loader warp can place and start in one round (one per lane)
 constexpr int kGroupsPerStep = OHP_GROUPS_PER_STEP; // independent 16-subsample groups a lane works on at once
-constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of this many consecutive chunks
+constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of (up to) this many consecutive chunks
+constexpr uint32_t kMinChunkBlock = 4;                // ... shortened for small batches so that every CTA gets work
 constexpr int kConsumerWarps = OHP_CONSUMER_WARPS;
 constexpr int kThreads = 32 + kConsumerWarps * 32; // loader warp + consumer warps
 constexpr int kRecSlots = 64;                      // two batches of 32 decoded chunk records
@@ -117,6 +118,9 @@ struct KernelParams
     uint64_t out_bytes;
     const uint16_t* table2;  // 512 x (2 * kRampArray[i])
     uint32_t* status;        // [0] error bits, [1] index of first offending chunk + 1
+    uint32_t cap_bytes;      // ring bytes a CTA may have in flight (<= kRingBytes)
+    uint32_t cap_chunks;     // chunks a CTA may have in flight (<= kRingSlots)
+    uint32_t chunk_block;    // chunks are dealt to the CTAs in runs of this many consecutive chunks
 };
 
 // One descriptor, unpacked; the checks are the reference's ASSERTs restated, shared by ohp_validate (host) and the
@@ -229,19 +233,19 @@ struct __align__(128) SharedStorage
 // Work distribution: chunks are dealt to the CTAs block-cyclically, kChunkBlock consecutive chunks at a time, so that
 // the chunks one CTA has in flight are neighbours in HBM (its loads and stores walk DRAM pages instead of hopping
 // grid * chunk bytes apart) while the grid as a whole still sweeps one narrow window of the arenas.
-__device__ __forceinline__ uint64_t cta_chunk_count(uint64_t n, uint32_t cta, uint32_t grid)
+__device__ __forceinline__ uint64_t cta_chunk_count(uint64_t n, uint32_t cta, uint32_t grid, uint32_t block)
 {
-    const uint64_t round = (uint64_t)grid * kChunkBlock;
+    const uint64_t round = (uint64_t)grid * block;
     const uint64_t full = n / round;
     const uint64_t rem = n - full * round;
-    const uint64_t mine = (uint64_t)cta * kChunkBlock;
-    const uint64_t extra = rem > mine ? (rem - mine < kChunkBlock ? rem - mine : kChunkBlock) : 0;
-    return full * kChunkBlock + extra;
+    const uint64_t mine = (uint64_t)cta * block;
+    const uint64_t extra = rem > mine ? (rem - mine < block ? rem - mine : block) : 0;
+    return full * block + extra;
 }
 // chunk index of this CTA's k-th chunk
-__device__ __forceinline__ uint64_t cta_chunk_index(uint64_t k, uint32_t cta, uint32_t grid)
+__device__ __forceinline__ uint64_t cta_chunk_index(uint64_t k, uint32_t cta, uint32_t grid, uint32_t block)
 {
-    return ((k / kChunkBlock) * grid + cta) * kChunkBlock + (k % kChunkBlock);
+    return ((k / block) * grid + cta) * block + (k % block);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -431,3 +431,37 @@ def test_converting_sinks_reject_what_the_reference_asserts_on(ctx):
         assert capi.validate(d, 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC, d
         with pytest.raises(capi.OhpError):
             ctx.process_host(d, np.zeros(64, np.uint8), np.zeros(4096, np.uint8))
+
+
+def test_inflight_tuning_never_changes_results(ctx, port):
+    """Large batches are tuned: the first launches of a batch shape each keep a different number of chunks in flight
+    (ohp_inflight_cap).  Every launch must produce the same bytes, and those are the oracle's."""
+    import torch
+    w = W.config5(n_streams=1024, seconds=0.4)
+    sched = capi.schedule_build(w.streams, w.events)
+    assert len(sched.chunks) >= 65536 and w.in_bytes + w.out_bytes >= (256 << 20)
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    d_desc = torch.from_numpy(sched.chunks.view(np.uint8).copy()).cuda()
+    d_in = torch.from_numpy(inp).cuda()
+    stream = torch.cuda.Stream()
+    st = stream.cuda_stream
+    caps, outs = [], []
+    for _ in range(6):
+        d_out = torch.zeros(w.out_bytes, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.process_device(d_desc.data_ptr(), len(sched.chunks), d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes, st)
+        ctx.sync(st)
+        caps.append(ctx.inflight_cap())
+        outs.append(d_out)
+    assert len(set(caps[:3])) == 3, caps           # three candidates explored ...
+    assert caps[3] == caps[4] == caps[5]           # ... then the fastest one is kept
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    # the first 24 streams against the oracle
+    k = int(sched.stream_chunk_begin[24])
+    sub = sched.chunks[:k]
+    hi = int(w.streams["dst_base"][24])
+    rc, want = port.process_chunks(sub, inp, hi)
+    assert rc == 0
+    mask = covered_mask(sub, hi)
+    assert np.array_equal(outs[0][:hi].cpu().numpy()[mask], want[mask])
