@@ -71,7 +71,10 @@ typedef struct ohp_stream_spec {
     uint32_t num_events;        /*   sorted by at_jiffies                                              */
     uint32_t driver_block_frames; /* 0: one playable per message; else the driver pulls blocks of this
                                    many frames and MsgPlayable::Split()s playables to fit              */
-    uint32_t reserved;
+    uint32_t codec_read_frames; /* 0: messages of chunk_frames (CodecWav, or no codec).  Else the codec reads this many
+                                   frames at a time (CodecAiffBase: 9216 B rounded down to frames), CodecController cuts
+                                   each read into chunk_frames pieces and DecodedAudioAggregator packs short pieces
+                                   together again (ohpipeline_b200/host/codec_source.h)                 */
 } ohp_stream_spec;
 
 /* Per-chunk facts that are not needed on the device but pin descriptor parity. */

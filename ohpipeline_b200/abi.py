@@ -52,6 +52,16 @@ assert CHUNK_DESC.itemsize == 32
 
 CHUNK_INFO = np.dtype([("direction", "<u4"), ("jiffies", "<u4")])
 
+# include/ohp_container.h
+CONTAINER_INFO = np.dtype([
+    ("kind", "<u4"), ("sample_rate", "<u4"), ("bit_depth_src", "<u4"), ("bit_depth", "<u4"), ("channels", "<u4"),
+    ("little_endian", "<u4"), ("bit_rate", "<u4"), ("streaming", "<u4"), ("data_offset", "<u8"), ("audio_bytes", "<u8"),
+    ("total_frames", "<u8"), ("track_length_jiffies", "<u8"),
+])
+assert CONTAINER_INFO.itemsize == 64
+CONTAINER_WAV, CONTAINER_AIFF, CONTAINER_AIFC = 1, 2, 3
+CONTAINER_OK, CONTAINER_E_UNRECOGNISED, CONTAINER_E_ENDED, CONTAINER_E_CORRUPT, CONTAINER_E_UNSUPPORTED, CONTAINER_E_ARG = range(6)
+
 # include/ohp_flywheel.h
 FLYWHEEL_JOB = np.dtype([
     ("src_off", "<u8"), ("dst_off", "<u8"), ("sample_rate", "<u4"), ("out_frames", "<u4"),
@@ -71,7 +81,7 @@ STREAM_SPEC = np.dtype([
     ("sample_rate", "<u4"), ("bit_depth", "<u4"), ("channels", "<u4"), ("in_little_endian", "<u4"),
     ("chunk_frames", "<u4"), ("out_fmt", "<u4"),
     ("total_frames", "<u8"), ("src_base", "<u8"), ("dst_base", "<u8"),
-    ("first_event", "<u4"), ("num_events", "<u4"), ("driver_block_frames", "<u4"), ("reserved", "<u4"),
+    ("first_event", "<u4"), ("num_events", "<u4"), ("driver_block_frames", "<u4"), ("codec_read_frames", "<u4"),
 ])
 assert STREAM_SPEC.itemsize == 64
 

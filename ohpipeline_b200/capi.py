@@ -113,6 +113,12 @@ def host_lib():
         L.ohp_flywheel_ramp_chunks.restype = C.c_int
         L.ohp_flywheel_ramp_chunks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t,
                                                C.POINTER(C.c_uint32)]
+        L.ohp_container_parse.restype = C.c_int
+        L.ohp_container_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.ohp_container_stream_spec.restype = C.c_int
+        L.ohp_container_stream_spec.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.ohp_codec_message_frames.restype = C.c_size_t
+        L.ohp_codec_message_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.ohp_schedule_num_chunks.restype = C.c_size_t
         L.ohp_schedule_num_chunks.argtypes = [C.c_void_p]
         for name in ("ohp_schedule_chunks", "ohp_schedule_chunk_info", "ohp_schedule_stream_chunk_begin",
@@ -152,6 +158,31 @@ def ramp_split(ramp, new_size, current_size):
     rem = np.zeros(1, dtype=abi.RAMP)
     rc = host_lib().ohp_ramp_split(_ptr(r), new_size, current_size, _ptr(rem))
     return rc, tuple(int(x) for x in r[0]), tuple(int(x) for x in rem[0])
+
+
+def container_parse(data, max_bit_depth=32):
+    """ohp_container_parse on a bytes-like object: (status, info record)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    info = np.zeros(1, dtype=abi.CONTAINER_INFO)
+    rc = host_lib().ohp_container_parse(_ptr(buf) if buf.size else None, buf.size, max_bit_depth, _ptr(info))
+    return int(rc), info[0]
+
+
+def container_stream_spec(info, container_len, arena_offset=0, dst_base=0):
+    """ohp_container_stream_spec: (status, STREAM_SPEC record)."""
+    rec = np.array([info], dtype=abi.CONTAINER_INFO)
+    spec = np.zeros(1, dtype=abi.STREAM_SPEC)
+    rc = host_lib().ohp_container_stream_spec(_ptr(rec), container_len, arena_offset, dst_base, _ptr(spec))
+    return int(rc), spec[0]
+
+
+def codec_message_frames(spec):
+    """Frames of every message the stream enters the pipeline with (ohp_codec_message_frames)."""
+    rec = np.array([spec], dtype=abi.STREAM_SPEC)
+    n = host_lib().ohp_codec_message_frames(_ptr(rec), None, 0)
+    out = np.zeros(n, dtype=np.uint32)
+    host_lib().ohp_codec_message_frames(_ptr(rec), _ptr(out), n)
+    return out
 
 
 def flywheel_ramp_chunks(job, current_ramp, src_off, dst_off):

@@ -18,6 +18,7 @@
 
 #include "../../include/ohp_schedule.h"
 #include "ramp_core.h"
+#include "codec_source.h"
 
 namespace ohp {
 namespace sched {
@@ -428,7 +429,11 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
     uint64_t frame = 0;
     uint64_t srcJiffies = 0;
     uint32_t silEv = 0;
-    while (frame < sp.total_frames) {
+    core::CodecSource source;
+    core::codec_source_init(source, sp.chunk_frames, sp.codec_read_frames, cx.frameBytes, cx.jps, sp.total_frames);
+    for (;;) {
+        const uint32_t frames = core::codec_source_next(source);
+        if (frames == 0) break;
         for (; silEv < cx.nEv; silEv++) {
             const ohp_ramp_event& e = cx.ev[silEv];
             if (e.op != OHP_EV_INSERT_SILENCE) continue;
@@ -444,8 +449,6 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
         }
         // DecodedAudio::ConstructPcm ASSERTs on the bit depth (Msg.cpp:349-366)
         if (!(cx.bits == 8 || cx.bits == 16 || cx.bits == 24 || cx.bits == 32)) return kErrAssert;
-        const uint64_t left = sp.total_frames - frame;
-        const uint32_t frames = (uint32_t)(left < sp.chunk_frames ? left : sp.chunk_frames);
         Msg m;
         m.cell = sp.src_base + frame * cx.frameBytes;
         m.size = frames * cx.jps;

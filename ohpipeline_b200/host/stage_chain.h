@@ -20,6 +20,7 @@
 #include <deque>
 
 #include "../../include/ohp_schedule.h"
+#include "codec_source.h"
 
 namespace ohp {
 
@@ -80,7 +81,11 @@ public:
         uint64_t frame = 0;
         uint64_t srcJiffies = 0;
         uint32_t silEv = 0;
-        while (frame < iSpec.total_frames) {
+        core::CodecSource source; // message sizes as the codec, CodecController and DecodedAudioAggregator leave them
+        core::codec_source_init(source, iSpec.chunk_frames, iSpec.codec_read_frames, iFrameBytes, iJps, iSpec.total_frames);
+        for (;;) {
+            const uint32_t frames = core::codec_source_next(source);
+            if (frames == 0) break;
             for (; silEv < iNumEvents; silEv++) {
                 const ohp_ramp_event& e = iEvents[silEv];
                 if (e.op != OHP_EV_INSERT_SILENCE) continue;
@@ -89,8 +94,6 @@ public:
                 Item it{Api::CreateSilence(iFactory, iSpec, jiffies), true};
                 Feed(0, it);
             }
-            const uint64_t left = iSpec.total_frames - frame;
-            const uint32_t frames = (uint32_t)(left < iSpec.chunk_frames ? left : iSpec.chunk_frames);
             Item it{Api::CreatePcm(iFactory, iSpec, frame, frames), false};
             Feed(0, it);
             frame += frames;

@@ -147,7 +147,6 @@ def config3(n_streams=4096, seconds=1.0, rate=48000, n_events=8, seed=3):
             up_at = t + 20 * MS + int(rng.integers(0, 10 * MS))
             lst.append((up_at, 1, abi.EV_RAMP_UP, 50 * MS))
             t = up_at + (int(rng.integers(1, 50 * MS)) if rng.random() < 0.4 else 50 * MS)
-        specs[-1]["reserved"] = 0
         evs.append(lst)
     return _finish("config3: %d x 8ch/32LE/%dk %.3gs, random starvation ramps" % (n_streams, rate // 1000, seconds),
                    specs, evs, seed=3 << 32)

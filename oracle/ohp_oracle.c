@@ -821,7 +821,36 @@ static int run_stream(run* r)
     uint64_t frame = 0;
     uint64_t src_jiffies = 0; /* PCM jiffies fed so far */
     uint32_t sil_ev = 0;
-    while (frame < sp->total_frames && !r->err) {
+    /* message sizes: codec reads -> CodecController::OutputAudioPcm pieces (CodecController.cpp:800-827) ->
+     * DecodedAudioAggregator::TryAggregate (DecodedAudioAggregator.cpp:134-186) */
+    uint64_t total_left = sp->total_frames;
+    uint32_t read_left = 0, held = 0;
+    while (!r->err) {
+        uint32_t frames = 0;
+        if (sp->codec_read_frames == 0) {
+            frames = (uint32_t)(total_left < sp->chunk_frames ? total_left : sp->chunk_frames);
+            total_left -= frames;
+        } else {
+            while (frames == 0) {
+                if (total_left == 0) { frames = held; held = 0; break; } /* OutputAggregatedAudio, :188-194 */
+                if (read_left == 0) read_left = (uint32_t)(total_left < sp->codec_read_frames ? total_left : sp->codec_read_frames);
+                const uint32_t piece = read_left < sp->chunk_frames ? read_left : sp->chunk_frames;
+                read_left -= piece;
+                total_left -= piece;
+#define AGG_FULL(f) ((f) * r->frame_bytes == CELL_MAX || (f) * r->jps >= 5u * OHP_JIFFIES_PER_MS - 7680u) /* :129-132, .h:19 */
+                if (held == 0) {
+                    if (AGG_FULL(piece)) frames = piece; else held = piece;
+                } else if ((held + piece) * r->frame_bytes <= CELL_MAX) {
+                    held += piece;
+                    if (AGG_FULL(held)) { frames = held; held = 0; }
+                } else {
+                    frames = held;
+                    held = piece;
+                }
+#undef AGG_FULL
+            }
+        }
+        if (frames == 0) break;
         /* MsgSilence entering ahead of the next PCM message */
         for (; sil_ev < r->nev && !r->err; sil_ev++) {
             const ohp_ramp_event* e = &r->ev[sil_ev];
@@ -840,8 +869,6 @@ static int run_stream(run* r)
             feed(r, 0, &m);
         }
         if (r->err) break;
-        const uint64_t left = sp->total_frames - frame;
-        const uint32_t frames = (uint32_t)(left < sp->chunk_frames ? left : sp->chunk_frames);
         msg m;
         memset(&m, 0, sizeof m);
         m.kind = MSG_PCM;

@@ -264,6 +264,16 @@ class Ref(_Lib):
         rc = f(_ptr(descs), len(descs), _ptr(inp), rate, jiffies, _ptr(planar), planar.size, C.byref(n))
         return rc, planar[:n.value].copy()
 
+    def aggregate(self, rate, channels, bits, frames):
+        """The real DecodedAudioAggregator: frame counts of the messages it passes on for the given input messages."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint32)
+        out = np.zeros(len(frames) + 4, dtype=np.uint32)
+        f = self.lib.ref_aggregate
+        f.restype = C.c_int
+        f.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        n = f(rate, channels, bits, _ptr(frames), len(frames), _ptr(out), len(out))
+        return None if n < 0 else out[:n].copy()
+
     def _free_result(self, res_ref):
         res = res_ref._obj
         self._libc_free(res.chunks)

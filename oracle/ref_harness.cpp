@@ -5,6 +5,7 @@
 //     /root/reference/OpenHome/Media/Utils/ProcessorAudioUtils.cpp
 //     /root/reference/OpenHome/Media/FlywheelRamper.cpp
 //     /root/reference/OpenHome/Media/Pipeline/StarvationRamper.cpp   (for FlywheelInput and RampGenerator)
+//     /root/reference/OpenHome/Media/Pipeline/DecodedAudioAggregator.cpp
 // (against the ohNet header shim in oracle/shim/) into oracle/_ref/libohref.so by oracle/Makefile.
 // It calls the reference's public API the way the reference's own unit tests do
 // (Media/Tests/TestMsg.cpp SuiteRamp / SuiteMsgPlayable): MsgFactory::CreateMsgAudioPcm ->
@@ -20,6 +21,7 @@
 #include <OpenHome/Media/Pipeline/RampArray.h>
 #include <OpenHome/Media/Pipeline/StarvationRamper.h>
 #include <OpenHome/Media/FlywheelRamper.h>
+#include <OpenHome/Media/Pipeline/DecodedAudioAggregator.h>
 
 #include <cstring>
 #include <cstdlib>
@@ -496,6 +498,59 @@ int ref_flywheel(uint32_t rate, uint32_t channels, uint32_t bits, uint32_t curre
     *numDescs = nd;
     delete f;
     return rc;
+}
+
+// ---- DecodedAudioAggregator -------------------------------------------------------------------------------------------
+
+namespace {
+class CollectFrames : public IPipelineElementDownstream
+{
+public:
+    CollectFrames(uint32_t* out, uint32_t cap, uint32_t jps) : iOut(out), iCap(cap), iJps(jps), iCount(0) {}
+    void Push(Msg* aMsg) override
+    {
+        MsgAudioPcm* pcm = dynamic_cast<MsgAudioPcm*>(aMsg);
+        if (pcm != nullptr && iCount < iCap) iOut[iCount] = pcm->Jiffies() / iJps;
+        if (pcm != nullptr) iCount++;
+        aMsg->RemoveRef();
+    }
+    uint32_t Count() const { return iCount; }
+private:
+    uint32_t* iOut; uint32_t iCap; uint32_t iJps; uint32_t iCount;
+};
+} // namespace
+
+// The real DecodedAudioAggregator fed with a MsgDecodedStream and then MsgAudioPcm messages of the given frame counts
+// (what CodecController queues); out receives the frame counts of the messages it passes on, a final MsgQuit flushes.
+int ref_aggregate(uint32_t rate, uint32_t channels, uint32_t bits, const uint32_t* frames, uint32_t n, uint32_t* out, uint32_t cap)
+{
+    NullInfoAggregator info;
+    MsgFactoryInitParams p;
+    p.SetMsgAudioPcmCount(64, 64);
+    p.SetMsgDecodedStreamCount(2);
+    MsgFactory factory(info, p);
+    try {
+        const uint32_t jps = Jiffies::PerSample(rate);
+        CollectFrames sink(out, cap, jps);
+        DecodedAudioAggregator agg(sink);
+        SpeakerProfile profile(2); // the aggregator does not look at it (its constructor ASSERTs above 3 fronts)
+        agg.Push(factory.CreateMsgDecodedStream(0, 0, bits, rate, channels, Brn("PCM"), 0, 0, true, true, false, false,
+                                                AudioFormat::Pcm, Multiroom::Allowed, profile, nullptr, RampType::Sample));
+        static TByte cell[AudioData::kMaxBytes];
+        TUint64 offset = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t bytes = frames[i] * channels * (bits / 8);
+            MsgAudioPcm* msg = factory.CreateMsgAudioPcm(Brn(cell, bytes), channels, rate, bits, AudioDataEndian::Big, offset);
+            offset += msg->Jiffies();
+            agg.Push(msg);
+        }
+        agg.Push(factory.CreateMsgQuit());
+        return (int)sink.Count();
+    }
+    catch (AssertionFailed& e) {
+        if (std::getenv("OHP_REF_VERBOSE")) std::fprintf(stderr, "ref_aggregate: ASSERT at %s:%u\n", e.File(), e.Line());
+        return -1;
+    }
 }
 
 int ref_hardware_threads(void)

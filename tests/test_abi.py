@@ -41,6 +41,14 @@ def test_cuda_library_exports_the_flywheel_generator():
         assert hasattr(lib, n), n
 
 
+def test_host_library_exports_the_container_front_end():
+    lib = capi.host_lib()
+    names = declared_functions("ohp_container.h")
+    assert names == ["ohp_codec_message_frames", "ohp_container_parse", "ohp_container_stream_spec"]
+    for n in names:
+        assert hasattr(lib, n), n
+
+
 def test_host_library_exports_every_declared_symbol():
     lib = capi.host_lib()
     names = declared_functions("ohp_schedule.h")
