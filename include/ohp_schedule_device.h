@@ -2,7 +2,7 @@
  * ohp_schedule_device.h -- C ABI of the DEVICE-side ramp-schedule builder (exported by libohp_b200.so).
  *
  * Same job as ohp_schedule_build (include/ohp_schedule.h) -- per-stream ramp events in, one ohp_chunk_desc per
- * MsgPlayable out -- but the walk runs on the GPU, one thread per stream, so descriptors are born in HBM next to
+ * MsgPlayable out -- but the walk runs on the GPU, a warp (or, for very many streams, a thread) per stream, so descriptors are born in HBM next to
  * the kernel that consumes them (ohp_process_device).  It replaces, for a batch of independent streams,
  *     Ramper::ProcessAudio            (OpenHome/Media/Pipeline/Ramper.cpp:114-134)
  *     Muter::ProcessAudio             (Muter.cpp:210-262)

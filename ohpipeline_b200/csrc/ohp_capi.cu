@@ -542,6 +542,8 @@ struct ohp_context
 
 namespace ohp {
 
+constexpr size_t kScheduleWarpTeamMaxStreams = 32768;
+
 static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess)
 {
     std::string msg = what;
@@ -1098,6 +1100,19 @@ static int schedule_status(ohp_context* ctx, cudaStream_t st)
     return fail(ctx, OHP_E_NO_MEMORY, buf);
 }
 
+// Threads per stream in the schedule kernels: a warp while warps-per-stream still fit the GPU a few times over, else one
+// thread.  OHP_SCHED_TEAM=1|32 pins it (experiments).
+static int schedule_team(size_t n_streams)
+{
+    static const int pinned = [] {
+        const char* e = std::getenv("OHP_SCHED_TEAM");
+        const int v = e ? std::atoi(e) : 0;
+        return (v == 1 || v == 32) ? v : 0;
+    }();
+    if (pinned) return pinned;
+    return n_streams <= kScheduleWarpTeamMaxStreams ? 32 : 1;
+}
+
 int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                               const ohp_ramp_event* d_events, size_t n_events, uint64_t* d_chunk_begin,
                               uint64_t* d_stream_out_bytes, uint64_t* total_chunks, void* stream)
@@ -1113,7 +1128,11 @@ int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams
     p.chunk_count = d_chunk_begin; p.out_bytes = d_stream_out_bytes;
     p.status = ctx->d_status + 2;
     if (n_streams) {
-        sched::schedule_kernel<false><<<(unsigned)((n_streams + 31) / 32), 32, 0, st>>>(p);
+        if (schedule_team(n_streams) == 32) {
+            sched::schedule_kernel<false, 32><<<sched::schedule_grid(n_streams, 32), sched::kScheduleBlock, 0, st>>>(p);
+        } else {
+            sched::schedule_kernel<false, 1><<<sched::schedule_grid(n_streams, 1), sched::kScheduleBlock, 0, st>>>(p);
+        }
         OHP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }
@@ -1144,7 +1163,11 @@ int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams,
     p.streams = d_streams; p.n_streams = n_streams; p.events = d_events; p.n_events = n_events;
     p.chunk_begin = d_chunk_begin; p.descs = d_chunks; p.info = d_info;
     p.status = ctx->d_status + 2;
-    sched::schedule_kernel<true><<<(unsigned)((n_streams + 31) / 32), 32, 0, st>>>(p);
+    if (schedule_team(n_streams) == 32) {
+        sched::schedule_kernel<true, 32><<<sched::schedule_grid(n_streams, 32), sched::kScheduleBlock, 0, st>>>(p);
+    } else {
+        sched::schedule_kernel<true, 1><<<sched::schedule_grid(n_streams, 1), sched::kScheduleBlock, 0, st>>>(p);
+    }
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return OHP_OK;

@@ -1,9 +1,9 @@
 // ohp_schedule_kernels.cuh -- device-side ramp-schedule builder: per-stream ramp events -> chunk
 // descriptors, on the GPU, so that the only host-serial step in front of ramp_convert_kernel disappears.
 //
-// ONE THREAD WALKS ONE STREAM (host/schedule_walk.h, which also compiles for the host so the CPU suite can test it).
-// A stream is strictly sequential -- every message's ramp starts where the previous one ended -- and streams are
-// independent, so the parallelism is across streams.  Two passes over the same walk: COUNT (chunks and
+// A TEAM OF THREADS WALKS ONE STREAM (host/schedule_walk.h, which also compiles for the host so the CPU suite can test
+// it).  Streams are independent; inside a stream only the ramp recurrence is sequential (every message's
+// ramp starts where the previous one ended), the rest of a steady stretch is done 32 messages at a time (bulk_step).  Two passes over the same walk: COUNT (chunks and
 // output bytes per stream), an exclusive scan, then EMIT (descriptors written at each stream's offset).  All integer;
 // the result is bit-identical to ohp_schedule_build (host) and to the reference's playables (tests/golden).
 #pragma once
@@ -30,16 +30,22 @@ struct ScheduleParams
     uint32_t* status;          // [0] error bits (1 << code), [1] 0xffffffff - lowest failing stream (atomicMax; 0 = none)
 };
 
-template <bool EMIT>
-__global__ void __launch_bounds__(32) schedule_kernel(const ScheduleParams p)
+// TEAM threads walk one stream: TEAM = 32 (a warp per stream: no divergence between streams, 32 descriptors per bulk
+// step written side by side) when streams are few enough for that to fill the GPU, TEAM = 1 (a thread per stream) when
+// there are so many streams that they alone do.  All lanes of a team hold the same state; see schedule_walk.h.
+template <bool EMIT, int TEAM>
+__global__ void __launch_bounds__(128) schedule_kernel(const ScheduleParams p)
 {
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t s = t / TEAM;
+    const uint32_t lane = (uint32_t)(t % TEAM);
     if (s >= p.n_streams) return;
     const ohp_stream_spec sp = p.streams[s];
     uint64_t nChunks, outBytes;
     ohp_chunk_desc* descs = EMIT ? p.descs + p.chunk_begin[s] : nullptr;
     ohp_chunk_info* info = (EMIT && p.info) ? p.info + p.chunk_begin[s] : nullptr;
-    const uint32_t rc = run_stream<EMIT>(sp, p.events, p.n_events, descs, info, nChunks, outBytes);
+    const uint32_t rc = run_stream<EMIT, TEAM, true>(sp, p.events, p.n_events, descs, info, nChunks, outBytes, lane);
+    if (lane != 0) return;
     if (rc != kOk) {
         atomicOr(&p.status[0], 1u << rc);
         atomicMax(&p.status[1], 0xffffffffu - (uint32_t)(s > 0xfffffffeull ? 0xfffffffeull : s));
@@ -48,6 +54,13 @@ __global__ void __launch_bounds__(32) schedule_kernel(const ScheduleParams p)
         p.chunk_count[s] = nChunks;
         if (p.out_bytes) p.out_bytes[s] = outBytes;
     }
+}
+
+// threads per block; grid for n streams
+constexpr unsigned kScheduleBlock = 128;
+inline unsigned schedule_grid(uint64_t n_streams, int team)
+{
+    return (unsigned)((n_streams * (uint64_t)team + kScheduleBlock - 1) / kScheduleBlock);
 }
 
 // In-place exclusive scan of counts[0..n) into begin[0..n] (begin has n+1 entries; begin[n] = total).  One CTA.

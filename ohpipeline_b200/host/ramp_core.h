@@ -57,6 +57,15 @@ OHP_HD bool ramp_is_valid(const RampPod& r)
     }
 }
 
+// (a * b + add) / d in 64 bits, as the reference computes it; 32-bit divide when the numerator fits (the GPU has no
+// 64-bit divider: __udivdi3-style code is ~10x the cost of a 32-bit divide, and most ramp steps fit).
+OHP_HD uint32_t mul_add_div(uint32_t a, uint32_t b, uint32_t add, uint32_t d)
+{
+    const uint64_t num = a * (uint64_t)b + add;
+    if ((num >> 32) == 0) return (uint32_t)num / d;
+    return (uint32_t)(num / d);
+}
+
 // two ramps over the same audio: the quieter one wins at both ends (Msg.cpp:721-734)
 OHP_HD void ramp_take_lower(RampPod& r, uint32_t aStart, uint32_t aEnd)
 {
@@ -82,7 +91,7 @@ OHP_HD int ramp_set(RampPod& r, uint32_t aStart, uint32_t aFragmentSize, uint32_
     // within its duration (Msg.cpp:603-605); an overshoot of less than the fragment size is rounding, anything more
     // is a caller bug (Msg.cpp:611, 620).
     const uint32_t distance = (aDirection == kDirDown) ? aStart : kRampMax - aStart;
-    const uint32_t delta = (uint32_t)((distance * (uint64_t)aFragmentSize + aRemainingDuration - 1) / aRemainingDuration);
+    const uint32_t delta = mul_add_div(distance, aFragmentSize, aRemainingDuration - 1, aRemainingDuration);
     uint32_t end;
     if (aDirection == kDirDown) {
         if (delta > aStart) {
@@ -154,10 +163,10 @@ OHP_HD int ramp_split(RampPod& r, uint32_t aNewSize, uint32_t aCurrentSize, Ramp
     aRest.enabled = 1;
     // proportional share, truncated; unsigned 32-bit span as in the reference (Msg.cpp:791-798)
     if (r.direction == kDirUp) {
-        r.end = r.start + (uint32_t)(((uint32_t)(r.end - r.start) * (uint64_t)aNewSize) / aCurrentSize);
+        r.end = r.start + mul_add_div((uint32_t)(r.end - r.start), aNewSize, 0, aCurrentSize);
     }
     else {
-        r.end = r.start - (uint32_t)(((uint32_t)(r.start - r.end) * (uint64_t)aNewSize) / aCurrentSize);
+        r.end = r.start - mul_add_div((uint32_t)(r.start - r.end), aNewSize, 0, aCurrentSize);
     }
     if (r.start == r.end) {
         r.direction = kDirNone; // also turns the first part of a muted message into an enabled flat ramp at 0

@@ -84,9 +84,14 @@ struct Playable
 
 enum Mode : uint32_t { Running = 0, RampingDown = 1, RampingUp = 2, Muted = 3 };
 
+constexpr uint64_t kNever = ~0ull;
+
+// One stage's state.  Indexed with compile-time constants only (the stage loop is unrolled), so on the device it lives
+// in registers; the stacks of pending split remainders are the only thing in local memory, and only splits touch them.
 struct Stage
 {
     uint64_t pos;
+    uint64_t nextAt;   // at_jiffies of this stage's next event (index nextEv), kNever when there is none left
     uint32_t mode, current, remaining, maxMsg, attenuation, nextEv, depth;
 };
 
@@ -98,6 +103,7 @@ struct StreamCtx
     uint32_t in_le, out_fmt;
     uint32_t blockBytes, blockFill;
     uint64_t dst_base;
+    uint32_t lane;         // this thread's index in the team walking the stream (host: 0); lane 0 writes in the general path
     // sink
     uint64_t nChunks, outBytes;
     ohp_chunk_desc* descs; // EMIT: this stream's first descriptor
@@ -230,36 +236,40 @@ OHP_HD uint32_t playable_split(Playable& p, uint32_t aBytes, Playable& rest, con
     return kOk;
 }
 
+// One 32-byte descriptor (layout: include/ohp_b200.h) for playable p as this stream's aIndex-th chunk, writing at
+// aOutOffset of the stream's output; two 128-bit stores on the device.
+OHP_HD void emit_desc(const StreamCtx& cx, const Playable& p, uint64_t aIndex, uint64_t aOutOffset)
+{
+    const uint32_t flags = (p.ramp.enabled ? OHP_F_RAMP_ENABLED : 0u) | (p.silence ? OHP_F_SILENCE : 0u)
+                         | ((!p.silence && cx.in_le) ? OHP_F_IN_LITTLE_ENDIAN : 0u);
+    const uint64_t src = p.silence ? 0 : p.arena;
+    const uint64_t dst = cx.dst_base + aOutOffset;
+    const uint32_t w4 = p.size;
+    const uint32_t w5 = (p.ramp.start & 0xffffu) | (p.ramp.end << 16);
+    const uint32_t w6 = (p.atten & 0xffffu) | (cx.bits << 16) | (cx.channels << 24);
+    const uint32_t w7 = flags | (cx.out_fmt << 8);
+#if defined(__CUDA_ARCH__)
+    uint4* out = reinterpret_cast<uint4*>(cx.descs + aIndex);
+    out[0] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)dst, (uint32_t)(dst >> 32));
+    out[1] = make_uint4(w4, w5, w6, w7);
+    if (cx.info) {
+        *reinterpret_cast<uint2*>(cx.info + aIndex) = make_uint2(p.ramp.direction, p.jiffies);
+    }
+#else
+    uint32_t* out = reinterpret_cast<uint32_t*>(cx.descs + aIndex);
+    out[0] = (uint32_t)src; out[1] = (uint32_t)(src >> 32); out[2] = (uint32_t)dst; out[3] = (uint32_t)(dst >> 32);
+    out[4] = w4; out[5] = w5; out[6] = w6; out[7] = w7;
+    if (cx.info) {
+        cx.info[aIndex].direction = p.ramp.direction;
+        cx.info[aIndex].jiffies = p.jiffies;
+    }
+#endif
+}
+
 template <bool EMIT>
 OHP_HD void on_playable(StreamCtx& cx, const Playable& p)
 {
-    if (EMIT) {
-        const uint32_t flags = (p.ramp.enabled ? OHP_F_RAMP_ENABLED : 0u) | (p.silence ? OHP_F_SILENCE : 0u)
-                             | ((!p.silence && cx.in_le) ? OHP_F_IN_LITTLE_ENDIAN : 0u);
-        const uint64_t src = p.silence ? 0 : p.arena;
-        const uint64_t dst = cx.dst_base + cx.outBytes;
-        // one 32-byte descriptor (layout: include/ohp_b200.h); two 128-bit stores on the device
-        const uint32_t w4 = p.size;
-        const uint32_t w5 = (p.ramp.start & 0xffffu) | (p.ramp.end << 16);
-        const uint32_t w6 = (p.atten & 0xffffu) | (cx.bits << 16) | (cx.channels << 24);
-        const uint32_t w7 = flags | (cx.out_fmt << 8);
-#if defined(__CUDA_ARCH__)
-        uint4* out = reinterpret_cast<uint4*>(cx.descs + cx.nChunks);
-        out[0] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)dst, (uint32_t)(dst >> 32));
-        out[1] = make_uint4(w4, w5, w6, w7);
-        if (cx.info) {
-            *reinterpret_cast<uint2*>(cx.info + cx.nChunks) = make_uint2(p.ramp.direction, p.jiffies);
-        }
-#else
-        uint32_t* out = reinterpret_cast<uint32_t*>(cx.descs + cx.nChunks);
-        out[0] = (uint32_t)src; out[1] = (uint32_t)(src >> 32); out[2] = (uint32_t)dst; out[3] = (uint32_t)(dst >> 32);
-        out[4] = w4; out[5] = w5; out[6] = w6; out[7] = w7;
-        if (cx.info) {
-            cx.info[cx.nChunks].direction = p.ramp.direction;
-            cx.info[cx.nChunks].jiffies = p.jiffies;
-        }
-#endif
-    }
+    if (EMIT && cx.lane == 0) emit_desc(cx, p, cx.nChunks, cx.outBytes);
     cx.nChunks++;
     cx.outBytes += p.size;
 }
@@ -293,17 +303,16 @@ OHP_HD uint32_t drive(StreamCtx& cx, const Msg& m)
     }
 }
 
-OHP_HD bool next_stage_event(const StreamCtx& cx, Stage& s, uint32_t stage, uint32_t& idx)
+// Point s.nextEv / s.nextAt at this stage's first event at or after index aFrom (MsgSilence insertions are fed by Run()).
+OHP_HD void stage_seek(const StreamCtx& cx, Stage& s, uint32_t stage, uint32_t aFrom)
 {
-    while (s.nextEv < cx.nEv) {
-        const ohp_ramp_event& e = cx.ev[s.nextEv];
-        if (e.stage == stage && e.op != OHP_EV_INSERT_SILENCE) {
-            idx = s.nextEv;
-            return true;
-        }
-        s.nextEv++;
+    uint32_t i = aFrom;
+    for (; i < cx.nEv; i++) {
+        const ohp_ramp_event& e = cx.ev[i];
+        if (e.stage == stage && e.op != OHP_EV_INSERT_SILENCE) break;
     }
-    return false;
+    s.nextEv = i;
+    s.nextAt = i < cx.nEv ? cx.ev[i].at_jiffies : kNever;
 }
 
 OHP_HD void apply_event(Stage& s, uint32_t op, uint32_t arg)
@@ -325,147 +334,368 @@ OHP_HD void apply_event(Stage& s, uint32_t op, uint32_t arg)
     }
 }
 
+OHP_HD bool push_msg(Stage& s, Packed* aRow, const Msg& m)
+{
+    if (s.depth == (uint32_t)kStackDepth) return false;
+    aRow[s.depth++] = pack(m);
+    return true;
+}
+
+// stage_chain.h Process(): one message through one stage; split remainders go onto the stage's stack (aRow).
+OHP_HD uint32_t stage_process(const StreamCtx& cx, Stage& s, uint32_t stage, Packed* aRow, Msg& msg)
+{
+    while (s.nextAt <= s.pos) {
+        const ohp_ramp_event& e = cx.ev[s.nextEv];
+        apply_event(s, e.op, e.arg);
+        stage_seek(cx, s, stage, s.nextEv + 1);
+    }
+    Msg rest;
+    if (s.nextAt < s.pos + msg.size) {
+        uint32_t at = (uint32_t)(s.nextAt - s.pos);
+        if (msg.silence) at -= at % cx.jps; // silence only splits on sample blocks
+        if (at == 0) {
+            const ohp_ramp_event& e = cx.ev[s.nextEv];
+            apply_event(s, e.op, e.arg);
+            stage_seek(cx, s, stage, s.nextEv + 1);
+        }
+        else {
+            const uint32_t e = msg_split(msg, at, rest, cx.jps);
+            if (e != kOk) return e;
+            if (!push_msg(s, aRow, rest)) return kErrDepth;
+        }
+    }
+    if (s.maxMsg != 0 && msg.size > s.maxMsg) {
+        if (s.maxMsg < cx.jps) return kErrSpec;
+        const uint32_t e = msg_split(msg, s.maxMsg, rest, cx.jps);
+        if (e != kOk) return e;
+        if (!push_msg(s, aRow, rest)) return kErrDepth;
+    }
+    if (!msg.silence && s.attenuation != OHP_UNITY_ATTENUATION) {
+        msg.atten = s.attenuation;
+    }
+    if (s.mode == RampingDown || s.mode == RampingUp) {
+        if (s.remaining > 0) {
+            if (msg.size > s.remaining) {
+                const uint32_t e = msg_split(msg, s.remaining, rest, cx.jps);
+                if (e != kOk) return e;
+                if (!push_msg(s, aRow, rest)) return kErrDepth;
+                if (msg.size == 0) return kErrAssert; // a MsgSilence split below one sample (see stage_chain.h)
+            }
+            bool haveSplit;
+            const uint32_t e = msg_set_ramp(msg, s.current, s.remaining, s.mode == RampingDown ? core::kDirDown : core::kDirUp,
+                                            rest, haveSplit, s.current, cx.jps);
+            if (e != kOk) return e;
+            if (haveSplit && !push_msg(s, aRow, rest)) return kErrDepth;
+        }
+        if (s.remaining == 0) {
+            if (s.mode == RampingUp) { s.mode = Running; s.current = core::kRampMax; }
+            else { s.mode = Muted; s.current = core::kRampMin; }
+        }
+    }
+    else if (s.mode == Muted) {
+        core::ramp_set_muted(msg.ramp);
+    }
+    s.pos += msg.size;
+    return kOk;
+}
+
+constexpr uint32_t kBulk = 32; // messages per bulk step
+
+// Team-wide operations: a warp's shuffles on the device when a warp walks the stream, nothing for a team of one.
+template <int STRIDE>
+OHP_HD uint32_t team_scan_exclusive(uint32_t v, uint32_t aLane, uint32_t& aTotal)
+{
+#if defined(__CUDA_ARCH__)
+    if (STRIDE == 32) {
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (aLane >= (uint32_t)o) x += y;
+        }
+        aTotal = __shfl_sync(0xffffffffu, x, 31);
+        return x - v;
+    }
+#endif
+    static_assert(STRIDE == 1 || STRIDE == 32, "a team is one thread or one warp");
+    (void)aLane;
+    aTotal = v;
+    return 0;
+}
+
+template <int STRIDE>
+OHP_HD bool team_any(bool aPred)
+{
+#if defined(__CUDA_ARCH__)
+    if (STRIDE == 32) return __any_sync(0xffffffffu, aPred) != 0;
+#endif
+    return aPred;
+}
+
+// The walk's position in the source: what Run() of stage_chain.h keeps between messages.
+struct Cursor
+{
+    uint64_t frame;       // frames of PCM fed so far
+    uint64_t srcJiffies;  // the same in jiffies
+    uint64_t silAt;       // at_jiffies of the next OHP_EV_INSERT_SILENCE event (index silEv), kNever when none is left
+    uint32_t silEv;
+};
+
+OHP_HD void seek_silence(const StreamCtx& cx, Cursor& c, uint32_t aFrom)
+{
+    uint32_t i = aFrom;
+    while (i < cx.nEv && cx.ev[i].op != OHP_EV_INSERT_SILENCE) i++;
+    c.silEv = i;
+    c.silAt = i < cx.nEv ? cx.ev[i].at_jiffies : kNever;
+}
+
+// BULK STEP: up to kBulk consecutive messages at once, where nothing can happen to them but what is known up front.
+//
+// Between two events a stream is in a steady state: the codec delivers uniform messages, every stage is Running or
+// Muted, or exactly one is ramping and the others are Running; no message is split, no stack is touched.  Then the
+// only thing that is sequential is the ramping stage's recurrence (each message's ramp starts where the previous one
+// ended, MsgAudio::SetRamp rounding up every time, Msg.cpp:603-605) -- one division per message.  Everything else
+// (CreatePlayable's jiffy -> byte conversions, the descriptor) depends on the message index alone.  So:
+//   1. shrink n until no event, ramp end, silence insertion or end of stream falls inside the n messages;
+//   2. run the recurrence for the n messages with the very code the general path uses (msg_set_ramp on a fresh
+//      message), every lane of the team redundantly, lane (k % STRIDE) keeping message k's ramp; an early finish
+//      (ramp reached kMin/kMax) or anything unusual ends the run there;
+//   3. lane i builds and emits messages i, i + STRIDE, ...: STRIDE descriptors per step, written side by side;
+//   4. advance all state by n messages.
+//   3b. with a driver that pulls fixed blocks (MsgPlayable::Split, Msg.cpp:2591-2624) a message becomes several
+//      playables; where the cuts fall follows from the message index, so lanes agree on their output slots through
+//      one prefix sum and each cuts its own message.
+// Returns n; 0 means "take the general path for the next message".  What the reference would ASSERT on in the stages
+// is left for the general path to find, at the same message; aErr only reports an ASSERT inside MsgPlayable::Split.
+template <bool EMIT, int STRIDE>
+OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[kStages], core::CodecSource& src, Cursor& cur,
+                          uint32_t& aErr)
+{
+    aErr = kOk;
+    if (src.read != 0) return 0;
+    if (!(cx.bits == 8 || cx.bits == 16 || cx.bits == 24 || cx.bits == 32)) return 0;
+    const uint32_t chunk = src.chunk;
+    const uint32_t size = chunk * cx.jps;
+    uint32_t n = kBulk;
+    if (size > 0xffffffffu / kBulk) return 0; // keep n * size in 32 bits (9216 one-byte frames at 7350 Hz: general path)
+    if (src.total_left < (uint64_t)n * chunk) n = (uint32_t)src.total_left / chunk;
+    if (n == 0) return 0;
+    // MsgSilence due before message k is fed when silAt <= srcJiffies + k * size
+    if (cur.silAt <= cur.srcJiffies + (uint64_t)(n - 1) * size) {
+        if (cur.silAt <= cur.srcJiffies) return 0;
+        n = (uint32_t)(cur.silAt - cur.srcJiffies - 1) / size + 1;
+    }
+    // stages: what mode, which one ramps, what attenuation the messages leave with
+    uint32_t ramping = 0, muted = 0, atten = OHP_UNITY_ATTENUATION;
+    uint32_t rMode = Running, rCurrent = 0, rRemaining = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < kStages; i++) {
+        const Stage& s = st[i];
+        if (s.maxMsg != 0 && size > s.maxMsg) return 0;
+        if (s.nextAt < s.pos + (uint64_t)n * size) {
+            if (s.nextAt <= s.pos) return 0;
+            n = (uint32_t)(s.nextAt - s.pos) / size; // whole messages in front of the event
+            if (n == 0) return 0;
+        }
+        if (s.attenuation != OHP_UNITY_ATTENUATION) atten = s.attenuation;
+        if (s.mode == Muted) muted++;
+        else if (s.mode != Running) {
+            ramping++;
+            rMode = s.mode; rCurrent = s.current; rRemaining = s.remaining;
+        }
+    }
+    if (ramping > 1 || (ramping == 1 && muted != 0)) return 0;
+    core::RampPod mine[kBulk / STRIDE];
+    if (ramping) {
+        if (rRemaining < size) return 0; // ramp end inside the next message (or a zero-length ramp): general path
+        if (rRemaining < n * size) n = rRemaining / size;
+        const uint32_t dir = rMode == RampingDown ? core::kDirDown : core::kDirUp;
+        uint32_t done = 0;
+        for (uint32_t k = 0; k < n; k++) {
+            Msg t, rest;
+            t.cell = 0; t.size = size; t.offset = 0; t.total = 0; t.atten = OHP_UNITY_ATTENUATION; t.silence = 0;
+            core::ramp_reset(t.ramp);
+            bool haveSplit;
+            uint32_t remaining = rRemaining, current = rCurrent;
+            const uint32_t e = msg_set_ramp(t, rCurrent, remaining, dir, rest, haveSplit, current, cx.jps);
+            if (e != kOk || haveSplit) break;
+            rRemaining = remaining; rCurrent = current;
+            if (k % STRIDE == cx.lane) mine[k / STRIDE] = t.ramp;
+            done = k + 1;
+            if (rRemaining == 0) { // as stage_process: the ramp is over, this message was its last
+                if (rMode == RampingUp) { rMode = Running; rCurrent = core::kRampMax; }
+                else { rMode = Muted; rCurrent = core::kRampMin; }
+                break;
+            }
+        }
+        n = done;
+        if (n == 0) return 0;
+    }
+    // every message of the run: the same size at offset 0 of its own cell
+    Msg m;
+    m.cell = 0; m.size = size; m.offset = 0; m.total = 0; m.atten = atten; m.silence = 0;
+    core::ramp_reset(m.ramp);
+    if (muted) core::ramp_set_muted(m.ramp);
+    const uint32_t bytes = create_playable(m, cx).size; // the same for every message of the run
+    const uint32_t block = (bytes != 0) ? cx.blockBytes : 0;
+    uint32_t pieces = 0; // playables emitted by the messages in front of this iteration's
+    uint32_t err = kOk;
+    if (EMIT || block != 0) {
+        for (uint32_t i0 = 0; i0 < n; i0 += STRIDE) {
+            const uint32_t i = i0 + cx.lane;
+            const bool active = i < n;
+            // a driver pulling fixed blocks (stage_chain.h Drive()): message i starts (fill + i * bytes) % block into a
+            // block and is cut at every block boundary strictly inside it
+            uint32_t fill = 0, count = active ? 1u : 0u;
+            if (block != 0 && active) {
+                fill = (cx.blockFill + i * bytes) % block;
+                count += (fill + bytes - 1) / block;
+            }
+            uint32_t total;
+            const uint32_t before = team_scan_exclusive<STRIDE>(count, cx.lane, total);
+            if (active && (EMIT || ramping)) { // counting needs the cuts themselves only for what Ramp::Split may ASSERT on
+                m.cell = sp.src_base + (cur.frame + (uint64_t)i * chunk) * cx.frameBytes;
+                if (ramping) m.ramp = mine[i / STRIDE];
+                Playable p = create_playable(m, cx);
+                uint64_t index = cx.nChunks + pieces + before;
+                uint64_t off = cx.outBytes + (uint64_t)i * bytes;
+                while (block != 0 && p.size > block - fill) {
+                    Playable rest;
+                    const uint32_t e = playable_split(p, block - fill, rest, cx);
+                    if (e != kOk) { err = e; break; }
+                    if (EMIT) emit_desc(cx, p, index, off);
+                    index++;
+                    off += p.size;
+                    fill = 0;
+                    p = rest;
+                }
+                if (EMIT && err == kOk) emit_desc(cx, p, index, off);
+            }
+            pieces += total;
+        }
+        aErr = team_any<STRIDE>(err != kOk) ? kErrAssert : kOk; // playable_split's only failure is an ASSERT
+    }
+    else {
+        pieces = n;
+    }
+    if (block != 0) cx.blockFill = (cx.blockFill + n * bytes) % block;
+    // advance
+    cx.nChunks += pieces;
+    cx.outBytes += (uint64_t)n * bytes;
+    cur.frame += (uint64_t)n * chunk;
+    cur.srcJiffies += (uint64_t)n * size;
+    src.total_left -= (uint64_t)n * chunk;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < kStages; i++) {
+        Stage& s = st[i];
+        s.pos += (uint64_t)n * size;
+        if (s.mode == RampingDown || s.mode == RampingUp) { s.mode = rMode; s.current = rCurrent; s.remaining = rRemaining; }
+    }
+    return n;
+}
+
 // One stream's walk.  The per-stage queues of stage_chain.h only ever grow at the front while a stage is being served
-// and are drained before the stage returns, so each is a stack; Feed()'s recursion becomes "serve the deepest
-// non-empty stage".
-template <bool EMIT>
+// and are drained before the stage returns, so each is a stack; Feed()'s recursion becomes: carry the message down
+// the remaining stages (in registers), hand it to the driver, then resume with the top of the deepest non-empty stack.
+// A team of STRIDE threads (device: a warp, or 1; host: 1) walks the stream holding identical state; they differ only
+// in cx.lane, i.e. in which messages of a bulk step they emit.  BULK = false is the message-at-a-time walk alone.
+template <bool EMIT, int STRIDE, bool BULK>
 OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
 {
     Packed stack[kStages][kStackDepth];
     Stage st[kStages];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int i = 0; i < kStages; i++) {
         st[i].pos = 0; st[i].mode = Running; st[i].current = core::kRampMax; st[i].remaining = 0; st[i].maxMsg = 0;
-        st[i].attenuation = OHP_UNITY_ATTENUATION; st[i].nextEv = 0; st[i].depth = 0;
+        st[i].attenuation = OHP_UNITY_ATTENUATION; st[i].depth = 0;
+        stage_seek(cx, st[i], (uint32_t)i, 0);
     }
     if (cx.jps == 0 || cx.frameBytes == 0) return kErrSpec;
     if (sp.chunk_frames == 0 || sp.chunk_frames * cx.frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return kErrSpec;
 
-    auto push = [&](int stage, const Msg& m) -> bool {
-        if (st[stage].depth == (uint32_t)kStackDepth) return false;
-        stack[stage][st[stage].depth++] = pack(m);
-        return true;
-    };
-
-    // stage_chain.h Process()
-    auto process = [&](int stage, Msg& msg) -> uint32_t {
-        Stage& s = st[stage];
-        uint32_t ei;
-        while (next_stage_event(cx, s, (uint32_t)stage, ei) && cx.ev[ei].at_jiffies <= s.pos) {
-            apply_event(s, cx.ev[ei].op, cx.ev[ei].arg);
-            s.nextEv = ei + 1;
-        }
-        Msg rest;
-        if (next_stage_event(cx, s, (uint32_t)stage, ei) && cx.ev[ei].at_jiffies < s.pos + msg.size) {
-            uint32_t at = (uint32_t)(cx.ev[ei].at_jiffies - s.pos);
-            if (msg.silence) at -= at % cx.jps; // silence only splits on sample blocks
-            if (at == 0) {
-                apply_event(s, cx.ev[ei].op, cx.ev[ei].arg);
-                s.nextEv = ei + 1;
-            }
-            else {
-                const uint32_t e = msg_split(msg, at, rest, cx.jps);
-                if (e != kOk) return e;
-                if (!push(stage, rest)) return kErrDepth;
-            }
-        }
-        if (s.maxMsg != 0 && msg.size > s.maxMsg) {
-            if (s.maxMsg < cx.jps) return kErrSpec;
-            const uint32_t e = msg_split(msg, s.maxMsg, rest, cx.jps);
-            if (e != kOk) return e;
-            if (!push(stage, rest)) return kErrDepth;
-        }
-        if (!msg.silence && s.attenuation != OHP_UNITY_ATTENUATION) {
-            msg.atten = s.attenuation;
-        }
-        if (s.mode == RampingDown || s.mode == RampingUp) {
-            if (s.remaining > 0) {
-                if (msg.size > s.remaining) {
-                    const uint32_t e = msg_split(msg, s.remaining, rest, cx.jps);
-                    if (e != kOk) return e;
-                    if (!push(stage, rest)) return kErrDepth;
-                    if (msg.size == 0) return kErrAssert; // a MsgSilence split below one sample (see stage_chain.h)
-                }
-                bool haveSplit;
-                const uint32_t e = msg_set_ramp(msg, s.current, s.remaining, s.mode == RampingDown ? core::kDirDown : core::kDirUp,
-                                                rest, haveSplit, s.current, cx.jps);
-                if (e != kOk) return e;
-                if (haveSplit && !push(stage, rest)) return kErrDepth;
-            }
-            if (s.remaining == 0) {
-                if (s.mode == RampingUp) { s.mode = Running; s.current = core::kRampMax; }
-                else { s.mode = Muted; s.current = core::kRampMin; }
-            }
-        }
-        else if (s.mode == Muted) {
-            core::ramp_set_muted(msg.ramp);
-        }
-        s.pos += msg.size;
-        return kOk;
-    };
-
-    // stage_chain.h Feed(0, item), iteratively
+    // stage_chain.h Feed(0, item)
     auto feed = [&](const Msg& first) -> uint32_t {
-        if (!push(0, first)) return kErrDepth;
+        Msg m = first;
+        int from = 0;
         for (;;) {
-            int stage = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < kStages; i++) {
+                if (i >= from) {
+                    const uint32_t e = stage_process(cx, st[i], (uint32_t)i, stack[i], m);
+                    if (e != kOk) return e;
+                }
+            }
+            const uint32_t e2 = drive<EMIT>(cx, m);
+            if (e2 != kOk) return e2;
+            from = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
             for (int i = kStages - 1; i >= 0; i--) {
-                if (stage < 0 && st[i].depth != 0) stage = i;
+                if (from < 0 && st[i].depth != 0) {
+                    from = i;
+                    m = unpack(stack[i][--st[i].depth]);
+                }
             }
-            if (stage < 0) return kOk;
-            Msg m = unpack(stack[stage][--st[stage].depth]);
-            const uint32_t e = process(stage, m);
-            if (e != kOk) return e;
-            if (stage + 1 == kStages) {
-                const uint32_t e2 = drive<EMIT>(cx, m);
-                if (e2 != kOk) return e2;
-            }
-            else if (!push(stage + 1, m)) {
-                return kErrDepth;
-            }
+            if (from < 0) return kOk;
         }
     };
 
     // stage_chain.h Run()
-    uint64_t frame = 0;
-    uint64_t srcJiffies = 0;
-    uint32_t silEv = 0;
+    Cursor cur;
+    cur.frame = 0;
+    cur.srcJiffies = 0;
+    seek_silence(cx, cur, 0);
     core::CodecSource source;
     core::codec_source_init(source, sp.chunk_frames, sp.codec_read_frames, cx.frameBytes, cx.jps, sp.total_frames);
     for (;;) {
+        if (BULK) {
+            uint32_t e;
+            const uint32_t n = bulk_step<EMIT, STRIDE>(sp, cx, st, source, cur, e);
+            if (e != kOk) return e;
+            if (n != 0) continue;
+        }
         const uint32_t frames = core::codec_source_next(source);
         if (frames == 0) break;
-        for (; silEv < cx.nEv; silEv++) {
-            const ohp_ramp_event& e = cx.ev[silEv];
-            if (e.op != OHP_EV_INSERT_SILENCE) continue;
-            if (e.at_jiffies > srcJiffies) break;
+        Msg m;
+        while (cur.silAt <= cur.srcJiffies) {
             // MsgFactory::CreateMsgSilence / MsgSilence::Initialise (Msg.cpp:2547-2560)
-            Msg m;
-            uint32_t jiffies = e.arg;
+            uint32_t jiffies = cx.ev[cur.silEv].arg;
             core::round_down_non_zero_sample_block(jiffies, cx.jps);
             m.cell = 0; m.size = jiffies; m.total = jiffies; m.offset = 0; m.atten = OHP_UNITY_ATTENUATION; m.silence = 1;
             core::ramp_reset(m.ramp);
             const uint32_t rc = feed(m);
             if (rc != kOk) return rc;
+            seek_silence(cx, cur, cur.silEv + 1);
         }
         // DecodedAudio::ConstructPcm ASSERTs on the bit depth (Msg.cpp:349-366)
         if (!(cx.bits == 8 || cx.bits == 16 || cx.bits == 24 || cx.bits == 32)) return kErrAssert;
-        Msg m;
-        m.cell = sp.src_base + frame * cx.frameBytes;
+        m.cell = sp.src_base + cur.frame * cx.frameBytes;
         m.size = frames * cx.jps;
         m.total = 0; m.offset = 0; m.atten = OHP_UNITY_ATTENUATION; m.silence = 0;
         core::ramp_reset(m.ramp);
         const uint32_t rc = feed(m);
         if (rc != kOk) return rc;
-        frame += frames;
-        srcJiffies += (uint64_t)frames * cx.jps;
+        cur.frame += frames;
+        cur.srcJiffies += (uint64_t)frames * cx.jps;
     }
     return kOk;
 }
 
 // Fill the per-stream context from a spec and walk it.  aEvents is the WHOLE events array (aNumEvents entries).
-template <bool EMIT>
+// aLane: this thread's index in its team of STRIDE (0 on the host).
+template <bool EMIT, int STRIDE = 1, bool BULK = true>
 OHP_HD uint32_t run_stream(const ohp_stream_spec& sp, const ohp_ramp_event* aEvents, uint64_t aNumEvents,
-                           ohp_chunk_desc* aDescs, ohp_chunk_info* aInfo, uint64_t& aNumChunks, uint64_t& aOutBytes)
+                           ohp_chunk_desc* aDescs, ohp_chunk_info* aInfo, uint64_t& aNumChunks, uint64_t& aOutBytes,
+                           uint32_t aLane = 0)
 {
     aNumChunks = 0;
     aOutBytes = 0;
@@ -483,11 +713,12 @@ OHP_HD uint32_t run_stream(const ohp_stream_spec& sp, const ohp_ramp_event* aEve
     cx.blockBytes = sp.driver_block_frames * cx.frameBytes;
     cx.blockFill = 0;
     cx.dst_base = sp.dst_base;
+    cx.lane = aLane;
     cx.nChunks = 0;
     cx.outBytes = 0;
     cx.descs = EMIT ? aDescs : nullptr;
     cx.info = EMIT ? aInfo : nullptr;
-    const uint32_t rc = walk_stream<EMIT>(sp, cx);
+    const uint32_t rc = walk_stream<EMIT, STRIDE, BULK>(sp, cx);
     if (rc != kOk) return rc;
     aNumChunks = cx.nChunks;
     aOutBytes = cx.outBytes;
