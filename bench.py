@@ -44,6 +44,8 @@ def build_workload(name, streams, seconds):
         return workloads.config3(n_streams=streams or 4096, seconds=seconds or 1.0,
                                  n_events=int(os.environ.get("OHP_C3_EVENTS", "8")))  # experiment knob: 0 = no ramps, uniform chunks
     if name == "config4":
+        return workloads.config4(n_streams=streams or 16384, seconds=seconds or 0.25)
+    if name == "mixed":  # the stress version of config4: tiny messages, one-sample caps, one-frame driver blocks
         return workloads.mixed(n_streams=streams or 16384, seed=4, max_frames=int((seconds or 1.0) * 48000))
     if name == "config1":
         return workloads.config1(seconds or 10.0)

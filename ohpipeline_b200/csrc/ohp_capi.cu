@@ -100,6 +100,8 @@ __device__ __forceinline__ void report(const KernelParams& p, uint32_t bits, uin
 // CTA the chunk with ordinal k uses barrier pair k % kBarPairs and is transformed by whichever consumer warp draws
 // ticket k (OHP_DYNAMIC) -- so a warp that met a run of expensive chunks does not hold the in-order ring up while
 // its neighbours idle -- or by warp k % kConsumerWarps (static).
+// SERIAL_PLACE: how the loader warp places chunks in the ring (compiled twice; the context picks per batch shape).
+template <bool SERIAL_PLACE>
 __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     for (uint32_t i = threadIdx.x; i < OHP_RAMP_TABLE_ENTRIES; i += kThreads) sm.table2[i] = p.table2[i];
     __syncthreads();
 
+    [[maybe_unused]] uint32_t n_rounds = 0, n_inflight = 0;
     [[maybe_unused]] long long w_loader = 0, w_full = 0, w_store = 0, w_xform = 0, w_fence = 0, w_issue = 0;
 #ifdef OHP_PROFILE_WAITS
     const long long t_begin = clock64();
@@ -188,11 +191,19 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     free_bytes += bytes;
                     rd += nrel;
                 }
-                // (2) place as many of the next chunks as fit right now (warp-uniform; lane g keeps chunk j + g's offset)
+                // (2) place as many of the next chunks as fit right now, all at once: lane g stands for chunk j + g.
+                //     Slots are contiguous, so the first chunk that would cross the end of the ring moves to offset 0
+                //     and the bytes it skipped are charged to it; a prefix sum of the needs gives every candidate its
+                //     offset and the running cost, and "fits" is monotone in g, so one ballot counts the chunks placed.
                 uint32_t fit = 0, my_wr = 0;
-                {
+                // Two ways to place (the kernel is compiled with each; the context measures which one a batch shape
+                // prefers, see TuneEntry).  When the ring is nearly full (large uniform chunks: the consumers set the
+                // pace) a round places one to three chunks and what counts is how soon after a release the next load
+                // starts: a short serial loop.  When there is room (small or mixed chunks: the loader sets the pace) what
+                // counts is chunks per round: the scan.
+                if (SERIAL_PLACE) {
                     uint32_t wr_s = wr, free_s = free_bytes;
-                    for (uint32_t g = 0; g < kIssueWidth && j + g < count; g++) {
+                    for (uint32_t g = 0; g < kSerialWidth && j + g < count; g++) {
                         const uint32_t need = __shfl_sync(0xffffffffu, my_need, j + g);
                         const bool wrap = wr_s + need > kRingBytes;       // the slot must be contiguous: skip the end of the ring
                         const uint32_t waste = wrap ? kRingBytes - wr_s : 0u;
@@ -214,6 +225,44 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     }
                     wr = wr_s;
                     free_bytes = free_s;
+                }
+                else {
+                    const uint32_t width = count - j < kIssueWidth ? count - j : kIssueWidth;
+                    uint32_t need = __shfl_sync(0xffffffffu, my_need, (j + lane) & 31u);
+                    need = lane < width ? need : 0u;
+                    uint32_t incl = need;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (uint32_t)o) incl += y;
+                    }
+                    const uint32_t excl = incl - need;
+                    const uint32_t wmask = __ballot_sync(0xffffffffu, wr + incl > kRingBytes);
+                    const uint32_t wl = wmask ? (uint32_t)__ffs((int)wmask) - 1u : 32u;   // the lane that wraps (32: none)
+                    const uint32_t excl_w = __shfl_sync(0xffffffffu, excl, wl & 31u);
+                    const uint32_t waste = wl < 32u ? kRingBytes - (wr + excl_w) : 0u;
+                    const uint32_t cost_incl = incl + (lane >= wl ? waste : 0u);
+                    const bool ok = lane < width && cost_incl <= free_bytes && it0 + lane - rd < p.cap_chunks;
+                    const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+                    fit = okmask == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~okmask) - 1u;
+                    if (fit == 0) {
+                        // ring full: block on the oldest slot (one lane polls), then sweep again
+                        if (lane == 0) {
+                            OHP_ACC(w_loader, mbar_wait(smem_u32(&sm.empty[(uint32_t)(rd % kBarPairs)]), (uint32_t)(rd / kBarPairs) & 1u, p.status));
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                    my_wr = lane < wl ? wr + excl : excl - excl_w;
+                    // ring slot (it0 + g) % kRingSlots remembers what chunk g took, for the sweep that reclaims it
+                    const uint32_t cost = need + (lane == wl ? waste : 0u);
+                    const uint32_t g = (lane + kRingSlots - (uint32_t)(it0 % kRingSlots)) % kRingSlots;
+                    const uint32_t got = __shfl_sync(0xffffffffu, cost, g & 31u);
+                    if (lane < kRingSlots && g < fit) my_slot_bytes = got;
+                    const uint32_t last_incl = __shfl_sync(0xffffffffu, incl, fit - 1u);
+                    const uint32_t last_cost = __shfl_sync(0xffffffffu, cost_incl, fit - 1u);
+                    wr = fit > wl ? last_incl - excl_w : wr + last_incl;
+                    free_bytes -= last_cost;
                 }
                 // (3) lanes 0..fit-1 start chunk j + lane
                 {
@@ -247,6 +296,9 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                         }
                     }
                 }
+#ifdef OHP_PROFILE_WAITS
+                n_rounds++; n_inflight += (uint32_t)(it0 - rd);
+#endif
                 j += fit;
             }
 #else
@@ -303,6 +355,10 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
         }
         if (lane == 0) {
             OHP_FLUSH(4, w_loader);
+#ifdef OHP_PROFILE_WAITS
+            atomicAdd(&p.status[7], n_rounds);      // issue rounds that placed something
+            atomicAdd(&p.status[14], n_inflight >> 4); // chunks in flight when they started, summed (/16)
+#endif
 #ifdef OHP_PROFILE_WAITS
             atomicAdd(&p.status[8], (uint32_t)((clock64() - t_begin) >> 12));
 #endif
@@ -492,17 +548,23 @@ static thread_local std::string g_create_error;
 // (profiles/README.md).  So a context learns it per batch signature: the first launches of a signature each run with a
 // different candidate between CUDA events on the caller's stream, later launches read the finished timings and use the
 // fastest.  Results never depend on the cap; only large batches are tuned.
-constexpr int kTuneCandidates = 3;  // three, so that a benchmark's customary three warm-up launches do all the exploring
-static const uint32_t kTuneCaps[kTuneCandidates] = {kRingSlots, 12u, 18u};
+constexpr int kTuneCandidates = 3;  // few, so that a benchmark's customary warm-up launches do (nearly) all the exploring
+static const uint32_t kTuneCaps[kTuneCandidates] = {kRingSlots, 12u, 24u};
+static const uint32_t kTuneSerial[kTuneCandidates] = {0u, 1u, 0u}; // the loader's placement mode that goes with each cap
 constexpr uint64_t kTuneMinBytes = 256ull << 20; // batches below this are launch-latency territory: not worth tuning
 constexpr uint64_t kTuneMinChunks = 65536;
+// The first launch of a new shape runs cold (instruction cache, TLBs, the descriptors' first trip through L2), a few
+// per cent slower than it will ever be again: its candidate gets a second, warm trial.
+constexpr int kTuneTrials = kTuneCandidates + 1;
+static const int kTrialCandidate[kTuneTrials] = {0, 1, 2, 0};
 struct TuneEntry
 {
     uint64_t n = 0, in_bytes = 0, out_bytes = 0;
-    int launched = 0;                 // candidates started so far
+    int launched = 0;                 // trials started so far
+    bool done[kTuneTrials] = {};      // trial's time has been read
     bool have[kTuneCandidates] = {};
-    float ms[kTuneCandidates] = {};
-    cudaEvent_t ev[kTuneCandidates][2] = {};
+    float ms[kTuneCandidates] = {};   // latest trial of each candidate
+    cudaEvent_t ev[kTuneTrials][2] = {};
     uint64_t last_use = 0;
 };
 
@@ -532,6 +594,7 @@ struct ohp_context
     uint32_t cap_chunks = ohp::kRingSlots;
     uint32_t chunk_block = ohp::kChunkBlock;
     bool cap_pinned = false;               // OHP_CAP_CHUNKS / OHP_CAP_BYTES given: no tuning
+    uint32_t serial_place = 0;             // loader placement mode when not tuned (experiments: OHP_SERIAL_PLACE=1)
     bool autotune = true;                  // OHP_AUTOTUNE=0 turns it off
     std::vector<ohp::TuneEntry> tune;      // one entry per batch signature seen (a few)
     uint32_t last_cap_chunks = ohp::kRingSlots; // what the most recent launch used (ohp_inflight_cap)
@@ -591,6 +654,7 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
     p.status = ctx->d_status;
     p.cap_bytes = ctx->cap_bytes;
     p.cap_chunks = ctx->cap_chunks;
+    p.serial_place = ctx->serial_place;
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctx->ctas_per_sm;
     // chunks are dealt in runs of chunk_block: long runs keep what a CTA has in flight inside one stretch of each arena,
     // short ones keep every CTA busy when the batch is small (at least ~8 runs per CTA)
@@ -615,34 +679,49 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
                 tune = &ctx->tune[0];
                 for (TuneEntry& t : ctx->tune) if (t.last_use < tune->last_use) tune = &t;
                 for (int c = 0; c < kTuneCandidates; c++) { tune->have[c] = false; }
+                for (int t = 0; t < kTuneTrials; t++) { tune->done[t] = false; }
                 tune->launched = 0;
             }
             tune->n = n; tune->in_bytes = in_bytes; tune->out_bytes = out_bytes;
         }
         tune->last_use = ++use_clock;
-        int best = -1;
-        for (int c = 0; c < tune->launched; c++) {
-            if (!tune->have[c] && cudaEventQuery(tune->ev[c][1]) == cudaSuccess) {
+        for (int t = 0; t < tune->launched; t++) {
+            if (!tune->done[t] && cudaEventQuery(tune->ev[t][1]) == cudaSuccess) {
                 float ms = 0.f;
-                if (cudaEventElapsedTime(&ms, tune->ev[c][0], tune->ev[c][1]) == cudaSuccess) { tune->ms[c] = ms; tune->have[c] = true; }
+                if (cudaEventElapsedTime(&ms, tune->ev[t][0], tune->ev[t][1]) == cudaSuccess) {
+                    tune->ms[kTrialCandidate[t]] = ms;
+                    tune->have[kTrialCandidate[t]] = true;
+                    tune->done[t] = true;
+                }
             }
-            if (tune->have[c] && (best < 0 || tune->ms[c] < tune->ms[best])) best = c;
         }
         (void)cudaGetLastError(); // cudaErrorNotReady from the query is not an error
-        if (tune->launched < kTuneCandidates) {
+        int best = -1;
+        for (int c = 0; c < kTuneCandidates; c++) {
+            if (tune->have[c] && (best < 0 || tune->ms[c] < tune->ms[best])) best = c;
+        }
+        if (tune->launched == kTuneCandidates && tune->have[0] && tune->have[1] && tune->have[2]) {
+            // the warm re-trial of the first candidate is only worth a launch if it could still win
+            const float other = tune->ms[1] < tune->ms[2] ? tune->ms[1] : tune->ms[2];
+            if (tune->ms[0] > 1.06f * other) tune->launched = kTuneTrials;
+        }
+        if (tune->launched < kTuneTrials) {
             trial = tune->launched;
             for (int k = 0; k < 2; k++) {
                 if (!tune->ev[trial][k]) OHP_CUDA(ctx, cudaEventCreate(&tune->ev[trial][k]));
             }
-            p.cap_chunks = kTuneCaps[trial];
+            p.cap_chunks = kTuneCaps[kTrialCandidate[trial]];
+            p.serial_place = kTuneSerial[kTrialCandidate[trial]];
         } else if (best >= 0) {
             p.cap_chunks = kTuneCaps[best];
+            p.serial_place = kTuneSerial[best];
         }
     }
     ctx->last_cap_chunks = p.cap_chunks;
     if (ctx->timing) OHP_CUDA(ctx, cudaEventRecord(ctx->ev_start, st));
     if (trial >= 0) OHP_CUDA(ctx, cudaEventRecord(tune->ev[trial][0], st));
-    ramp_convert_kernel<<<(unsigned)grid, kThreads, sizeof(SharedStorage), st>>>(p);
+    if (p.serial_place) ramp_convert_kernel<true><<<(unsigned)grid, kThreads, sizeof(SharedStorage), st>>>(p);
+    else ramp_convert_kernel<false><<<(unsigned)grid, kThreads, sizeof(SharedStorage), st>>>(p);
     OHP_CUDA(ctx, cudaGetLastError());
     if (trial >= 0) {
         OHP_CUDA(ctx, cudaEventRecord(tune->ev[trial][1], st));
@@ -823,6 +902,7 @@ int ohp_create(int device, ohp_context** out_ctx)
         const long v = std::atol(e);
         if (v >= 1 && v <= (long)kRingSlots) { ctx->cap_chunks = (uint32_t)v; ctx->cap_pinned = true; }
     }
+    if (const char* e = std::getenv("OHP_SERIAL_PLACE")) ctx->serial_place = std::atoi(e) != 0 ? 1u : 0u;
 #define OHP_CREATE(call)                                                          \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -853,8 +933,9 @@ int ohp_create(int device, ohp_context** out_ctx)
     }
     {
         int per_sm = 0;
-        OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedStorage)));
-        OHP_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ramp_convert_kernel, kThreads, sizeof(SharedStorage)));
+        OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedStorage)));
+        OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedStorage)));
+        OHP_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ramp_convert_kernel<false>, kThreads, sizeof(SharedStorage)));
         ctx->ctas_per_sm = per_sm > 0 ? per_sm : 1;
     }
 #undef OHP_CREATE
@@ -877,7 +958,7 @@ int ohp_destroy(ohp_context* ctx)
     if (ctx->ev_stop) (void)cudaEventDestroy(ctx->ev_stop);
     for (cudaEvent_t e : ctx->slice_events) (void)cudaEventDestroy(e);
     for (ohp::TuneEntry& t : ctx->tune) {
-        for (int c = 0; c < ohp::kTuneCandidates; c++) {
+        for (int c = 0; c < ohp::kTuneTrials; c++) {
             if (t.ev[c][0]) (void)cudaEventDestroy(t.ev[c][0]);
             if (t.ev[c][1]) (void)cudaEventDestroy(t.ev[c][1]);
         }

@@ -65,7 +65,7 @@ namespace ohp {
 #define OHP_CONSUMER_POLL 0 /* 0: every lane waits on the barrier; 1: lane 0 waits, __syncwarp; 2: one look by all, then 1 */
 #endif
 #ifndef OHP_ISSUE_WIDTH
-#define OHP_ISSUE_WIDTH 8
+#define OHP_ISSUE_WIDTH 16
 #endif
 #ifndef OHP_GROUPS_PER_STEP
 #define OHP_GROUPS_PER_STEP 1
@@ -74,6 +74,7 @@ namespace ohp {
 #define OHP_DYNAMIC 1       /* 1: consumer warps take chunks by ticket (first come, first served); 0: chunk k -> warp k % warps */
 #endif
 constexpr uint32_t kIssueWidth = OHP_ISSUE_WIDTH;     // chunks the loader warp can place and start in one round (one per lane)
+constexpr uint32_t kSerialWidth = 8;                  // ... and at most this many per round in serial-placement mode
 constexpr int kGroupsPerStep = OHP_GROUPS_PER_STEP; // independent 16-subsample groups a lane works on at once
 constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of (up to) this many consecutive chunks
 constexpr uint32_t kMinChunkBlock = 4;                // ... shortened for small batches so that every CTA gets work
@@ -121,6 +122,8 @@ struct KernelParams
     uint32_t cap_bytes;      // ring bytes a CTA may have in flight (<= kRingBytes)
     uint32_t cap_chunks;     // chunks a CTA may have in flight (<= kRingSlots)
     uint32_t chunk_block;    // chunks are dealt to the CTAs in runs of this many consecutive chunks
+    uint32_t serial_place;   // host side only: which instantiation runs (1 = loader places chunks one after the other, up to
+                             // kSerialWidth a round; 0 = all at once by prefix sum, up to kIssueWidth)
 };
 
 // One descriptor, unpacked; the checks are the reference's ASSERTs restated, shared by ohp_validate (host) and the

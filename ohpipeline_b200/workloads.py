@@ -166,6 +166,83 @@ def config5(n_streams=65536, seconds=1.0):
     return _finish("config5: %d x 2ch/24/96k %.3gs, full-length ramps" % (n_streams, seconds), specs, evs, seed=5 << 32)
 
 
+def config4(n_streams=16384, seconds=0.25, seed=4):
+    """BASELINE configs[3] as SURVEY 8d spells it out: per stream the PRNG picks bits in {8,16,24,32}, 1-8 channels
+    (6-ch/32-bit included), one of the eight rates 44.1-384 kHz, wire endianness and sink (P1, or P2 where the depth
+    allows); messages are what a codec delivers, min(5 ms, 9216 B).  Ramps as the pipeline elements make them:
+    a Ramper-style ramp up at the start (stage 0), StarvationRamper events -- 20 ms down, 50 ms up -- at jiffy
+    positions aligned to nothing, some of them cut short by the next one (stage 1: partial ramps, messages split at
+    the remaining ramp size), a Muter-style 500 ms ramp down / up on top (stage 2: ramps running against each other,
+    Ramp::Set's intersect + split-fragment path), a driver pulling 1-10 ms blocks on a quarter of the streams
+    (MsgPlayable::Split at arbitrary byte counts), muted stretches, MsgSilence, one-sample chunks (events one sample
+    apart) and, on 16-bit streams, an attenuation window over a tenth of the stream.  `mixed` below is the stress
+    version of the same idea (tiny messages, caps of one sample); this one keeps the sizes a pipeline produces."""
+    rng = np.random.default_rng(seed)
+    rates = (44100, 48000, 88200, 96000, 176400, 192000, 352800, 384000)
+    specs, evs, slack = [], [], []
+    for i in range(n_streams):
+        bits = int(rng.choice((8, 16, 24, 32)))
+        ch = int(rng.integers(1, 9))
+        rate = int(rng.choice(rates))
+        le = bool(rng.integers(0, 2))
+        jps = abi.jiffies_per_sample(rate)
+        fb = ch * bits // 8
+        chunk = max_chunk_frames(rate, bits, ch)
+        total = max(chunk, int(rate * seconds))
+        total_j = total * jps
+        use_silence = rng.random() < 0.1
+        # the packed-LE sink ASSERTs on ProcessSilence (TestCodecInteractiveMain.cpp:564-567): P2 streams get no
+        # MsgSilence and nothing that mutes
+        want_p2 = bits != 32 and not use_silence and rng.random() < 0.25
+        block = int(rng.integers(rate // 1000, rate // 100 + 1)) if rng.random() < 0.25 else 0
+        spec = _spec(rate, bits, ch, le, chunk, total, abi.OUT_PACKED_LE if want_p2 else abi.OUT_PACKED_BE, block)
+        q = jps if use_silence else 1   # a MsgSilence cannot be split inside a sample: sample-aligned event grid
+        lst = []
+        extra = 0
+
+        def at(lo, hi):
+            return int(rng.integers(lo, max(lo + 1, hi))) // q * q
+
+        if rng.random() < 0.5:
+            lst.append((0, 0, abi.EV_MUTE, 0))
+            lst.append((0, 0, abi.EV_RAMP_UP, 50 * MS))          # Ramper: short ramp up when a stream starts
+        t = at(0, total_j // 4)
+        for _ in range(int(rng.integers(0, 4))):                 # StarvationRamper: down 20 ms, (halt,) up 50 ms
+            if t >= total_j:
+                break
+            if not want_p2:
+                lst.append((t, 1, abi.EV_RAMP_DOWN, 20 * MS))
+                up_at = t + (at(1, 20 * MS) if rng.random() < 0.3 else 20 * MS + at(0, 10 * MS))
+            else:
+                lst.append((t, 1, abi.EV_RAMP_DOWN, 4 * total_j + 20 * MS))   # stays audible
+                up_at = t + at(1, 20 * MS)
+            lst.append((up_at, 1, abi.EV_RAMP_UP, 50 * MS))
+            t = up_at + (at(1, 50 * MS) if rng.random() < 0.3 else 50 * MS + at(0, total_j // 4))
+        if rng.random() < 0.3:                                   # Muter on top
+            m0 = at(0, total_j)
+            lst.append((m0, 2, abi.EV_RAMP_DOWN, (4 * total_j + 500 * MS) if want_p2 else 500 * MS))
+            if rng.random() < 0.7:
+                lst.append((m0 + at(1, 600 * MS), 2, abi.EV_RAMP_UP, 500 * MS))
+        if rng.random() < 0.02:                                  # one-sample chunks
+            e0 = at(0, total_j) // jps * jps
+            lst.append((e0, 1, abi.EV_RAMP_UP, 50 * MS))
+            lst.append((e0 + jps, 1, abi.EV_RAMP_UP, 50 * MS))
+        if bits == 16:
+            a0 = at(0, total_j - total_j // 10)
+            lst.append((a0, 3, abi.EV_SET_ATTENUATION, int(rng.choice((64, 128, 192, 255, 257, 384, 511)))))
+            lst.append((a0 + total_j // 10 // q * q, 3, abi.EV_SET_ATTENUATION, abi.UNITY_ATTENUATION))
+        if use_silence:
+            for _ in range(int(rng.integers(1, 3))):
+                sj = int(rng.integers(1, 20 * (rate // 1000) + 1)) * jps
+                lst.append((at(0, total_j) // jps * jps, 0, abi.EV_INSERT_SILENCE, sj))
+                extra += (sj // jps) * fb
+        specs.append(spec)
+        evs.append(lst)
+        slack.append(extra)
+    return _finish("config4: %d streams mixed formats %.3gs, pipeline-shaped ramps" % (n_streams, seconds), specs, evs,
+                   seed=(4 << 32) + seed, slack=slack)
+
+
 def mixed(n_streams=64, seed=4, max_frames=6000, with_silence=True, p2=True):
     """BASELINE configs[3] in miniature: random formats (8/16/24/32-bit, 1-8 ch, 44.1-384 kHz, BE/LE, P1/P2),
     partial ramps, stacked ramps on several stages (-> Ramp::Set merge / intersect / split), muted stretches,

@@ -52,3 +52,7 @@ for label, i in (("loader blocked: ring full, waiting for a slot to be released"
                  ("consumer warp 0: fence.proxy.async + __syncwarp", 10),
                  ("consumer warp 0: issuing the store (ragged bytes + TMA)", 11)):
     print("  %-82s %5.1f%% of CTA lifetime" % (label, 100.0 * v[i] / max(life, 1)))
+rounds, infl = buf[7], buf[14] * 16.0
+if rounds:
+    print("  loader: %.2f chunks placed per issue round, %.1f chunks in flight when a round starts (cap %d)"
+          % (len(sched.chunks) / rounds, infl / rounds, ctx.inflight_cap()))

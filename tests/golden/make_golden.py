@@ -30,6 +30,9 @@ def cases():
     yield "config2_x2", W.config2(n_streams=2, seconds=0.05)
     yield "config3_x3", W.config3(n_streams=3, seconds=0.4)
     yield "config5_x2", W.config5(n_streams=2, seconds=0.05)
+    c4 = W.config4(n_streams=24, seconds=0.1, seed=4)
+    c4.streams["out_fmt"] = abi.OUT_PACKED_BE     # the linked reference only has the packed-BE sink
+    yield "config4_x24", c4
     for seed in (101, 102, 103, 104):
         w = W.mixed(n_streams=12, seed=seed, max_frames=1500)
         w.streams["out_fmt"] = abi.OUT_PACKED_BE  # the linked reference only has the packed-BE sink
@@ -40,7 +43,10 @@ def main():
     ref = pyoracle.Ref()
     port = pyoracle.Port()
     total = 0
+    only = sys.argv[1:]
     for name, w in cases():
+        if only and name not in only:
+            continue
         inp = port.fill_pcm(w.in_bytes, w.seed)
         rc, out, chunks, info = ref.run(w.streams, w.events, inp, w.out_bytes, threads=1)
         assert rc == 0, (name, rc)
@@ -56,6 +62,8 @@ def main():
         total += os.path.getsize(path)
         print("%-16s %6d chunks %8d bytes out -> %s (%d B)" % (name, len(chunks), w.out_bytes, os.path.basename(path),
                                                                 os.path.getsize(path)))
+    if only:
+        return
     # function-level vectors: Ramp::Set / Ramp::Split on random and edge arguments
     rng = np.random.default_rng(7)
     K = abi.RAMP_MAX
