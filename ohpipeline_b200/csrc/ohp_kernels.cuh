@@ -8,11 +8,13 @@
 //                       are already in flight), then the whole warp runs the issue loop in lockstep, everything it
 //                       needs of chunk j arriving by shuffle from lane j:  (1) lanes test the "empty" barriers of all
 //                       slots in flight at once and reclaim, in order, what has been released;  (2) as many of the next
-//                       chunks as fit are given contiguous slots in the ring;  (3) one lane per placed chunk starts ONE
-//                       TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on the slot's "full" mbarrier)
-//                       of the 16-byte-aligned span covering the chunk's source bytes.  When the consumers keep up the
-//                       ring is full and the loader places one chunk per released slot; when the loader is what limits
-//                       (small chunks) there is room, and it places up to OHP_ISSUE_WIDTH per round;
+//                       chunks as fit are given contiguous slots in the ring -- all at once, by a prefix sum of their
+//                       sizes over the lanes (SERIAL_PLACE = false), or one after the other (SERIAL_PLACE = true: fewer
+//                       dependent shuffles when the ring is full and only one to three fit);  (3) one lane per placed
+//                       chunk starts ONE TMA bulk copy (cp.async.bulk.shared::cluster.global, completion on the slot's
+//                       "full" mbarrier) of the 16-byte-aligned span covering the chunk's source bytes.  With large
+//                       chunks the ring is full and the loader places one chunk per released slot; with small chunks
+//                       the loader is what limits, and it places up to OHP_ISSUE_WIDTH per round;
 //   consumers           take chunks by TICKET (a shared-memory counter), first come first served, so a warp that met
 //                       a run of expensive chunks does not hold up the in-order ring while its neighbours idle.  The
 //                       warp waits on the chunk's "full" mbarrier, transforms the chunk IN PLACE in "units" of four
