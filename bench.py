@@ -191,7 +191,26 @@ def pick_cpu_sample(w, threads, target_s=6.0):
     return max(1, n)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line and nothing else: libraries that print there (NCCL's version banner comes from C
+    code, at the first collective) are pointed at stderr, the line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -237,7 +256,7 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------------------
@@ -420,7 +439,7 @@ def main():
                 "subsamples_per_s": subsamples_per_step * world / (ms_per_step * 1e-3),
                 "payload_gb_per_s_per_gpu": (in_payload + payload) / (ms_per_step * 1e-3) / 1e9,
                 "checksum_of_checksums": checksum_of_checksums}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
