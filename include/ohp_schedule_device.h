@@ -41,6 +41,24 @@ int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams,
                              const ohp_ramp_event* d_events, size_t n_events, const uint64_t* d_chunk_begin,
                              ohp_chunk_desc* d_chunks, ohp_chunk_info* d_info /* may be NULL */, void* stream);
 
+/*
+ * The whole stage in one call, for a batch of streams whose PCM sits in HOST memory: stream specs and ramp events in,
+ * the bytes every stream's driver would have read out.  It is MsgFactory::CreateMsgAudioPcm -> pipeline elements ->
+ * CreatePlayable -> MsgPlayable::Read(IPcmProcessor&) for n_streams independent pipelines (Msg.cpp:2234-2262, 2646-2653
+ * and the stage files above), with no per-message work on any host core: the descriptors are built on the GPU and stay
+ * there (specs + events are all that crosses PCIe on their behalf), PCM moves in slices of whole streams, H2D / kernel /
+ * D2H pipelined.  h_in / h_out should be pinned (ohp_host_alloc) for full PCIe speed.  Synchronous.
+ *   h_stream_out_bytes (n_streams, may be NULL): bytes each stream produced at h_out + dst_base.
+ *   total_chunks (may be NULL): playables read.
+ * Output bytes between streams (alignment gaps) that fall inside a slice's span receive unspecified values.
+ * Errors: as ohp_schedule_count_device (the reference would ASSERT: OHP_E_INVALID_DESC; spec not representable:
+ * OHP_E_INVALID_ARG), OHP_E_OUT_OF_RANGE when a stream reaches outside the arenas.
+ */
+int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, size_t n_streams,
+                         const ohp_ramp_event* h_events, size_t n_events,
+                         const uint8_t* h_in, uint64_t in_bytes, uint8_t* h_out, uint64_t out_bytes,
+                         uint64_t* h_stream_out_bytes, uint64_t* total_chunks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,10 @@ def cuda_lib():
             L.ohp_schedule_emit_device.restype = C.c_int
             L.ohp_schedule_emit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        if hasattr(L, "ohp_run_streams_host"):
+            L.ohp_run_streams_host.restype = C.c_int
+            L.ohp_run_streams_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
+                                               C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
         L.ohp_set_timing.restype = C.c_int
         L.ohp_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.ohp_last_kernel_ms.restype = C.c_double
@@ -415,6 +419,19 @@ class Context:
             for q in ptrs:
                 self.device_free(q)
         return Schedule(chunks, info, begin, outb)
+
+    def run_streams_host(self, streams, events, inp, out):
+        """ohp_run_streams_host: specs + events + host PCM in, bytes out; returns (per-stream output bytes, chunks)."""
+        streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+        events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+        assert inp.dtype == np.uint8 and out.dtype == np.uint8 and inp.flags.c_contiguous and out.flags.c_contiguous
+        outb = np.zeros(len(streams), dtype=np.uint64)
+        total = C.c_uint64(0)
+        self._check(self._L.ohp_run_streams_host(self._h, _ptr(streams) if len(streams) else None, len(streams),
+                                                 _ptr(events) if len(events) else None, len(events),
+                                                 _ptr(inp) if inp.size else None, inp.size, _ptr(out), out.size,
+                                                 _ptr(outb) if len(streams) else None, C.byref(total)))
+        return outb, int(total.value)
 
     def set_timing(self, enabled):
         self._check(self._L.ohp_set_timing(self._h, int(bool(enabled))))

@@ -585,6 +585,12 @@ struct ohp_context
     uint8_t* d_in = nullptr;  uint64_t d_in_cap = 0;
     uint8_t* d_out = nullptr; uint64_t d_out_cap = 0;
     ohp_chunk_desc* d_descs = nullptr; uint64_t d_descs_cap = 0;
+    // ohp_run_streams_host staging (grown on demand)
+    ohp_stream_spec* d_specs = nullptr; uint64_t d_specs_cap = 0;
+    ohp_ramp_event* d_events = nullptr; uint64_t d_events_cap = 0;
+    uint64_t* d_begin = nullptr; uint64_t d_begin_cap = 0;
+    uint64_t* d_outb = nullptr; uint64_t d_outb_cap = 0;
+    std::vector<uint64_t> h_begin, h_outb;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timing = false;
     bool timed = false;
@@ -953,6 +959,10 @@ int ohp_destroy(ohp_context* ctx)
     if (ctx->d_descs) (void)cudaFree(ctx->d_descs);
     if (ctx->d_table2) (void)cudaFree(ctx->d_table2);
     if (ctx->d_status) (void)cudaFree(ctx->d_status);
+    if (ctx->d_specs) (void)cudaFree(ctx->d_specs);
+    if (ctx->d_events) (void)cudaFree(ctx->d_events);
+    if (ctx->d_begin) (void)cudaFree(ctx->d_begin);
+    if (ctx->d_outb) (void)cudaFree(ctx->d_outb);
     if (ctx->h_status) (void)cudaFreeHost(ctx->h_status);
     if (ctx->ev_start) (void)cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) (void)cudaEventDestroy(ctx->ev_stop);
@@ -1252,6 +1262,112 @@ int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams,
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return OHP_OK;
+}
+
+// The whole stage for a batch of streams in HOST memory (include/ohp_schedule_device.h).
+int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, size_t n_streams,
+                         const ohp_ramp_event* h_events, size_t n_events,
+                         const uint8_t* h_in, uint64_t in_bytes, uint8_t* h_out, uint64_t out_bytes,
+                         uint64_t* h_stream_out_bytes, uint64_t* total_chunks)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (total_chunks) *total_chunks = 0;
+    if (n_streams == 0) return OHP_OK;
+    if (!h_streams || !h_out || (!h_in && in_bytes) || (n_events && !h_events)) return fail(ctx, OHP_E_INVALID_ARG, "null host pointer");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = grow(ctx, ctx->d_specs, ctx->d_specs_cap, (uint64_t)n_streams * sizeof(ohp_stream_spec))) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_events, ctx->d_events_cap, (uint64_t)(n_events ? n_events : 1) * sizeof(ohp_ramp_event))) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_begin, ctx->d_begin_cap, (uint64_t)(n_streams + 1) * sizeof(uint64_t))) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_outb, ctx->d_outb_cap, (uint64_t)n_streams * sizeof(uint64_t))) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_in, ctx->d_in_cap, in_bytes + 16)) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_out, ctx->d_out_cap, out_bytes + 16)) != OHP_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    // 1. descriptors, born and kept in HBM: specs and events are all that crosses PCIe on their behalf
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_specs, h_streams, n_streams * sizeof(ohp_stream_spec), cudaMemcpyHostToDevice, st));
+    if (n_events) OHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_events, h_events, n_events * sizeof(ohp_ramp_event), cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    if ((rc = ohp_schedule_count_device(ctx, ctx->d_specs, n_streams, ctx->d_events, n_events, ctx->d_begin, ctx->d_outb, &total, st)) != OHP_OK) return rc;
+    if (total_chunks) *total_chunks = total;
+    if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, (total ? total : 1) * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+    if ((rc = ohp_schedule_emit_device(ctx, ctx->d_specs, n_streams, ctx->d_events, n_events, ctx->d_begin, ctx->d_descs, nullptr, st)) != OHP_OK) return rc;
+    ctx->h_begin.resize(n_streams + 1);
+    ctx->h_outb.resize(n_streams);
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_begin.data(), ctx->d_begin, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_outb.data(), ctx->d_outb, n_streams * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_stream_out_bytes) std::memcpy(h_stream_out_bytes, ctx->h_outb.data(), n_streams * sizeof(uint64_t));
+    // every stream's spans must lie inside the arenas (the kernel checks each chunk too; this names the stream)
+    for (size_t s = 0; s < n_streams; s++) {
+        const ohp_stream_spec& sp = h_streams[s];
+        const uint64_t in_len = sp.total_frames * (uint64_t)(sp.channels * (sp.bit_depth / 8u));
+        if (sp.src_base > in_bytes || in_len > in_bytes - sp.src_base || sp.dst_base > out_bytes || ctx->h_outb[s] > out_bytes - sp.dst_base) {
+            char buf[96];
+            std::snprintf(buf, sizeof buf, "stream %zu reaches outside the arenas", s);
+            return fail(ctx, OHP_E_OUT_OF_RANGE, buf);
+        }
+    }
+    // 2. PCM in slices of whole streams, H2D / kernel / D2H pipelined over three streams (as ohp_process_host)
+    const uint64_t kSliceBytes = 48ull << 20;
+    std::vector<cudaEvent_t>& evs = ctx->slice_events;
+    size_t ev_used = 0;
+    auto next_event = [&](cudaEvent_t* out_ev) -> cudaError_t {
+        if (ev_used == evs.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (err != cudaSuccess) return err;
+            evs.push_back(e);
+        }
+        *out_ev = evs[ev_used++];
+        return cudaSuccess;
+    };
+    const bool timing = ctx->timing;
+    ctx->timing = false;
+    const bool autotune = ctx->autotune;
+    ctx->autotune = false; // slices are small and PCIe-bound
+    size_t lo = 0;
+    rc = OHP_OK;
+    while (lo < n_streams && rc == OHP_OK) {
+        uint64_t in_lo = UINT64_MAX, in_hi = 0, out_lo = UINT64_MAX, out_hi = 0, moved = 0;
+        size_t hi = lo;
+        while (hi < n_streams && (moved < kSliceBytes || hi == lo)) {
+            const ohp_stream_spec& sp = h_streams[hi];
+            const uint64_t in_len = sp.total_frames * (uint64_t)(sp.channels * (sp.bit_depth / 8u));
+            if (in_len) {
+                in_lo = sp.src_base < in_lo ? sp.src_base : in_lo;
+                in_hi = sp.src_base + in_len > in_hi ? sp.src_base + in_len : in_hi;
+            }
+            if (ctx->h_outb[hi]) {
+                out_lo = sp.dst_base < out_lo ? sp.dst_base : out_lo;
+                out_hi = sp.dst_base + ctx->h_outb[hi] > out_hi ? sp.dst_base + ctx->h_outb[hi] : out_hi;
+            }
+            moved += in_len + ctx->h_outb[hi];
+            hi++;
+        }
+        const uint64_t c_lo = ctx->h_begin[lo], c_hi = ctx->h_begin[hi];
+        cudaEvent_t ev_in, ev_k;
+        OHP_CUDA(ctx, next_event(&ev_in));
+        OHP_CUDA(ctx, next_event(&ev_k));
+        if (in_hi > in_lo) {
+            OHP_CUDA(ctx, cudaMemcpyAsync(ctx->d_in + in_lo, h_in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
+        OHP_CUDA(ctx, cudaEventRecord(ev_in, ctx->copy_in));
+        OHP_CUDA(ctx, cudaStreamWaitEvent(st, ev_in, 0));
+        rc = launch(ctx, ctx->d_descs + c_lo, (size_t)(c_hi - c_lo), ctx->d_in, in_bytes, ctx->d_out, out_bytes, st);
+        if (rc != OHP_OK) break;
+        OHP_CUDA(ctx, cudaEventRecord(ev_k, st));
+        OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k, 0));
+        if (out_hi > out_lo) {
+            OHP_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+        lo = hi;
+    }
+    ctx->timing = timing;
+    ctx->autotune = autotune;
+    OHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (rc != OHP_OK) return rc;
+    return read_status(ctx, st);
 }
 
 // Flywheel ramp generator (include/ohp_flywheel.h) ---------------------------------------------------------------

@@ -159,3 +159,51 @@ def test_descriptors_built_on_the_gpu_drive_the_hot_path(ctx, port):
     got = d_out.cpu().numpy()
     mask = covered_mask(chunks, w.out_bytes)
     assert np.array_equal(got[mask], want[mask])
+
+
+@pytest.mark.parametrize("make", [
+    lambda: workloads.config1(6.2),
+    lambda: workloads.config4(n_streams=80, seconds=0.12, seed=9),
+    lambda: workloads.mixed(n_streams=64, seed=33, max_frames=4000),
+    lambda: workloads.config5(n_streams=700, seconds=0.25),     # > 48 MB each way: several slices in flight
+], ids=["config1", "config4", "mixed", "config5_sliced"])
+def test_whole_stage_in_one_call_from_host_buffers(ctx, port, make):
+    """ohp_run_streams_host: specs + events + host PCM in, bytes out -- descriptors never exist on the host.
+    Bytes, per-stream output sizes and chunk count against the oracle."""
+    w = make()
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    rc, want, chunks, _ = port.run(w.streams, w.events, inp, w.out_bytes)
+    assert rc == 0
+    host = capi.schedule_build(w.streams, w.events)
+    got = np.zeros(w.out_bytes, dtype=np.uint8)
+    outb, total = ctx.run_streams_host(w.streams, w.events, inp, got)
+    assert total == len(chunks)
+    assert np.array_equal(outb, host.stream_out_bytes)
+    mask = covered_mask(chunks, w.out_bytes)
+    assert np.array_equal(got[mask], want[mask])
+
+
+def test_whole_stage_call_reports_what_the_parts_report(ctx):
+    w = workloads.config5(n_streams=4, seconds=0.02)
+    inp = np.zeros(w.in_bytes, dtype=np.uint8)
+    out = np.zeros(w.out_bytes, dtype=np.uint8)
+    # nothing to do
+    outb, total = ctx.run_streams_host(w.streams[:0], w.events[:0], inp, out)
+    assert total == 0 and len(outb) == 0
+    # a spec the message model cannot represent
+    bad = w.streams.copy()
+    bad["sample_rate"][2] = 12345
+    with pytest.raises(capi.OhpError) as e:
+        ctx.run_streams_host(bad, w.events, inp, out)
+    assert e.value.status == abi.E_INVALID_ARG and "stream 2" in str(e.value)
+    # a stream that reaches outside the output arena
+    with pytest.raises(capi.OhpError) as e:
+        ctx.run_streams_host(w.streams, w.events, inp, out[:w.out_bytes // 2])
+    assert e.value.status == abi.E_OUT_OF_RANGE
+    # ... and outside the input arena
+    with pytest.raises(capi.OhpError) as e:
+        ctx.run_streams_host(w.streams, w.events, inp[:w.in_bytes // 2], out)
+    assert e.value.status == abi.E_OUT_OF_RANGE
+    # the context is still usable
+    outb, total = ctx.run_streams_host(w.streams, w.events, inp, out)
+    assert total == len(capi.schedule_build(w.streams, w.events).chunks)
