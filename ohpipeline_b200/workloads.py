@@ -243,6 +243,54 @@ def config4(n_streams=16384, seconds=0.25, seed=4):
                    seed=(4 << 32) + seed, slack=slack)
 
 
+def steady_edges(seed, n_streams=160):
+    """Streams made for the walk's bulk step (32 uniform messages at a time): events exactly on, one jiffy and one
+    sample either side of message boundaries; ramps whose length is a whole number of messages, give or take one
+    jiffy; ramps that finish early; silence insertions on and off message boundaries; driver blocks that divide,
+    equal, exceed and are coprime to the message size; a last message that is short; events past the end."""
+    rng = np.random.default_rng(seed)
+    specs, evs, slack = [], [], []
+    for _ in range(n_streams):
+        rate = int(rng.choice((44100, 48000, 96000, 192000)))
+        bits = int(rng.choice((8, 16, 24, 32)))
+        ch = int(rng.choice((1, 2, 6)))
+        jps = abi.jiffies_per_sample(rate)
+        fb = ch * bits // 8
+        chunk = int(rng.choice((max_chunk_frames(rate, bits, ch), 64, 100)))
+        chunk = min(chunk, max_chunk_frames(rate, bits, ch))
+        msgs = int(rng.integers(1, 150))
+        total = msgs * chunk + int(rng.choice((0, 0, 1, chunk // 2)))
+        msg_j = chunk * jps
+        block = int(rng.choice((0, 0, chunk, chunk // 2, 2 * chunk, chunk + 1, 7, 3 * chunk - 1)))
+        use_silence = rng.random() < 0.3
+        q = jps if use_silence else 1
+        spec = _spec(rate, bits, ch, bool(rng.integers(0, 2)), chunk, total, abi.OUT_PACKED_BE, max(block, 0))
+        lst, extra = [], 0
+
+        def near_boundary():
+            k = int(rng.integers(0, msgs + 2))
+            return max(0, k * msg_j + int(rng.choice((0, 0, 1, -1, jps, -jps, msg_j // 2)))) // q * q
+
+        for _ in range(int(rng.integers(0, 5))):
+            stage = int(rng.integers(0, 3))
+            op = int(rng.choice((abi.EV_RAMP_DOWN, abi.EV_RAMP_UP, abi.EV_RAMP_DOWN, abi.EV_RAMP_UP, abi.EV_MUTE, abi.EV_UNMUTE)))
+            dur = max(q, (int(rng.integers(1, 40)) * msg_j + int(rng.choice((0, 0, 1, -1, jps)))) // q * q)
+            lst.append((near_boundary(), stage, op, dur if op in (abi.EV_RAMP_DOWN, abi.EV_RAMP_UP) else 0))
+        if rng.random() < 0.3:
+            lst.append((0, int(rng.integers(0, 3)), abi.EV_MAX_MSG_JIFFIES, int(rng.choice((msg_j, msg_j + 1, 2 * msg_j, max(jps, msg_j // 3))))))
+        if bits == 16 and rng.random() < 0.5:
+            lst.append((near_boundary(), 3, abi.EV_SET_ATTENUATION, int(rng.integers(0, 512))))
+        if use_silence:
+            for _ in range(int(rng.integers(1, 3))):
+                sj = int(rng.integers(1, 300)) * jps
+                lst.append((near_boundary() // jps * jps, 0, abi.EV_INSERT_SILENCE, sj))
+                extra += (sj // jps) * fb
+        specs.append(spec)
+        evs.append(lst)
+        slack.append(extra)
+    return _finish("steady-edges %d" % seed, specs, evs, seed=(6 << 32) + seed, slack=slack)
+
+
 def mixed(n_streams=64, seed=4, max_frames=6000, with_silence=True, p2=True):
     """BASELINE configs[3] in miniature: random formats (8/16/24/32-bit, 1-8 ch, 44.1-384 kHz, BE/LE, P1/P2),
     partial ramps, stacked ramps on several stages (-> Ramp::Set merge / intersect / split), muted stretches,

@@ -63,3 +63,23 @@ def test_walk_refuses_what_the_class_model_refuses():
     # seed 21 of the 3001-stream mix holds a MsgSilence split below one sample: the reference ASSERTs
     w = workloads.mixed(n_streams=3001, seed=21, max_frames=700)
     assert check(w.streams, w.events) is None
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_bulk_step_edges_match_class_model(seed):
+    w = workloads.steady_edges(seed)
+    # stream by stream, so that one the reference ASSERTs on does not hide its neighbours
+    asserted = 0
+    for k in range(len(w.streams)):
+        s = w.streams[k:k + 1].copy()
+        ev = w.events[int(s[0]["first_event"]):int(s[0]["first_event"]) + int(s[0]["num_events"])].copy()
+        s[0]["first_event"] = 0
+        if check(s, ev) is None:
+            asserted += 1
+    assert asserted < len(w.streams) // 4
+
+
+@pytest.mark.parametrize("seed", [4, 21, 22, 23])
+def test_walk_matches_class_model_on_pipeline_shaped_mix(seed):
+    w = workloads.config4(n_streams=300, seconds=0.3, seed=seed)
+    assert check(w.streams, w.events) is not None
