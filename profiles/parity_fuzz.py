@@ -1,0 +1,64 @@
+"""Parity campaign on the GPU box: many seeds of the randomized workloads through the whole stage on the GPU
+(ohp_run_streams_host: device-built descriptors + ramp_convert_kernel) against the C oracle, byte for byte on
+everything a chunk covers, plus per-stream output sizes and chunk counts.  The oracle is the checker here, as in
+tests/; nothing under oracle/ is on the product path.
+    python profiles/parity_fuzz.py [seconds_budget] > gpurun_out/parity_fuzz.json"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from ohpipeline_b200 import abi, capi, workloads  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+from util import covered_mask  # noqa: E402
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 150.0
+    port = pyoracle.Port()
+    ctx = capi.Context(0)
+    gens = [("mixed", lambda s: workloads.mixed(n_streams=96, seed=s, max_frames=5000)),
+            ("steady_edges", lambda s: workloads.steady_edges(s, n_streams=96)),
+            ("config4", lambda s: workloads.config4(n_streams=64, seconds=0.1, seed=s))]
+    tot = {g: {"workloads": 0, "streams": 0, "chunks": 0, "bytes_checked": 0, "asserting_streams_dropped": 0} for g, _ in gens}
+    failures = []
+    t0 = time.time()
+    seed = 1000
+    while time.time() - t0 < budget and not failures:
+        for name, make in gens:
+            w = make(seed)
+            # streams the reference ASSERTs on are found by the host model one at a time and dropped
+            keep = []
+            for k in range(len(w.streams)):
+                s = w.streams[k:k + 1].copy()
+                ev = w.events[int(s[0]["first_event"]):int(s[0]["first_event"]) + int(s[0]["num_events"])]
+                s[0]["first_event"] = 0
+                try:
+                    capi.schedule_build(s, ev)
+                    keep.append(k)
+                except capi.OhpError:
+                    tot[name]["asserting_streams_dropped"] += 1
+            streams = w.streams[keep].copy()
+            inp = port.fill_pcm(w.in_bytes, w.seed)
+            rc, want, chunks, _ = port.run(streams, w.events, inp, w.out_bytes)
+            assert rc == 0, (name, seed, rc)
+            got = np.zeros(w.out_bytes, dtype=np.uint8)
+            outb, total = ctx.run_streams_host(streams, w.events, inp, got)
+            mask = covered_mask(chunks, w.out_bytes)
+            ok = total == len(chunks) and np.array_equal(got[mask], want[mask])
+            if not ok:
+                failures.append({"generator": name, "seed": seed, "chunks_gpu": int(total), "chunks_oracle": int(len(chunks))})
+            t = tot[name]
+            t["workloads"] += 1; t["streams"] += len(streams); t["chunks"] += int(total); t["bytes_checked"] += int(mask.sum())
+        seed += 1
+    print(json.dumps({"seconds": round(time.time() - t0, 1), "seeds": seed - 1000, "failures": failures, "totals": tot}))
+    return 1 if failures else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
