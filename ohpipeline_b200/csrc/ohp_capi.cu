@@ -603,6 +603,7 @@ struct ohp_context
     uint32_t serial_place = 0;             // loader placement mode when not tuned (experiments: OHP_SERIAL_PLACE=1)
     bool autotune = true;                  // OHP_AUTOTUNE=0 turns it off
     std::vector<ohp::TuneEntry> tune;      // one entry per batch signature seen (a few)
+    uint64_t tune_clock = 0;               // least-recently-used eviction among them
     uint32_t last_cap_chunks = ohp::kRingSlots; // what the most recent launch used (ohp_inflight_cap)
     cpu_set_t local_cpus;                  // cores of the NUMA node this GPU hangs off (empty set: unknown)
     bool have_local_cpus = false;
@@ -629,6 +630,18 @@ static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = 
         cudaError_t e_ = (call);                                                \
         if (e_ != cudaSuccess) return fail((ctx), OHP_E_CUDA, #call, e_);       \
     } while (0)
+
+// Sliced host-buffer calls launch many small kernels: per-kernel timing and in-flight tuning are off for their duration
+// and come back however the call ends.
+struct SliceMode
+{
+    ohp_context* ctx;
+    bool timing, autotune;
+    explicit SliceMode(ohp_context* c) : ctx(c), timing(c->timing), autotune(c->autotune) { c->timing = false; c->autotune = false; }
+    ~SliceMode() { ctx->timing = timing; ctx->autotune = autotune; }
+    SliceMode(const SliceMode&) = delete;
+    SliceMode& operator=(const SliceMode&) = delete;
+};
 
 static int check_desc(const ohp_chunk_desc& d, uint64_t in_bytes, uint64_t out_bytes, DescDerived* derived = nullptr)
 {
@@ -673,7 +686,6 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
     TuneEntry* tune = nullptr;
     int trial = -1;
     if (ctx->autotune && !ctx->cap_pinned && in_bytes + out_bytes >= kTuneMinBytes && n >= kTuneMinChunks) {
-        static uint64_t use_clock = 0;
         for (TuneEntry& t : ctx->tune) {
             if (t.n == n && t.in_bytes == in_bytes && t.out_bytes == out_bytes) tune = &t;
         }
@@ -690,7 +702,7 @@ static int launch(ohp_context* ctx, const ohp_chunk_desc* d_descs, size_t n, con
             }
             tune->n = n; tune->in_bytes = in_bytes; tune->out_bytes = out_bytes;
         }
-        tune->last_use = ++use_clock;
+        tune->last_use = ++ctx->tune_clock;
         for (int t = 0; t < tune->launched; t++) {
             if (!tune->done[t] && cudaEventQuery(tune->ev[t][1]) == cudaSuccess) {
                 float ms = 0.f;
@@ -1043,10 +1055,7 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
         *out_ev = evs[ev_used++];
         return cudaSuccess;
     };
-    const bool timing = ctx->timing;
-    ctx->timing = false; // per-kernel events are only meaningful for a single launch
-    const bool autotune = ctx->autotune;
-    ctx->autotune = false; // slices are small and PCIe-bound
+    const SliceMode slice_mode(ctx); // per-kernel events are only meaningful for a single launch; slices are PCIe-bound
     size_t lo = 0;
     while (lo < n) {
         uint64_t in_lo = UINT64_MAX, in_hi = 0, out_lo = UINT64_MAX, out_hi = 0, moved = 0;
@@ -1076,11 +1085,7 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
         }
         OHP_CUDA(ctx, cudaEventRecord(ev_in, ctx->copy_in));
         OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in, 0));
-        if ((rc = launch(ctx, ctx->d_descs + lo, hi - lo, ctx->d_in, in_bytes, ctx->d_out, out_bytes, ctx->stream)) != OHP_OK) {
-            ctx->timing = timing;
-            ctx->autotune = autotune;
-            return rc;
-        }
+        if ((rc = launch(ctx, ctx->d_descs + lo, hi - lo, ctx->d_in, in_bytes, ctx->d_out, out_bytes, ctx->stream)) != OHP_OK) return rc;
         OHP_CUDA(ctx, cudaEventRecord(ev_k, ctx->stream));
         OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k, 0));
         if (out_hi > out_lo) {
@@ -1088,8 +1093,6 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
         }
         lo = hi;
     }
-    ctx->timing = timing;
-    ctx->autotune = autotune;
     OHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     OHP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return read_status(ctx, ctx->stream);
@@ -1321,10 +1324,7 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
         *out_ev = evs[ev_used++];
         return cudaSuccess;
     };
-    const bool timing = ctx->timing;
-    ctx->timing = false;
-    const bool autotune = ctx->autotune;
-    ctx->autotune = false; // slices are small and PCIe-bound
+    const SliceMode slice_mode(ctx);
     size_t lo = 0;
     rc = OHP_OK;
     while (lo < n_streams && rc == OHP_OK) {
@@ -1362,8 +1362,6 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
         }
         lo = hi;
     }
-    ctx->timing = timing;
-    ctx->autotune = autotune;
     OHP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     OHP_CUDA(ctx, cudaStreamSynchronize(st));
     if (rc != OHP_OK) return rc;
