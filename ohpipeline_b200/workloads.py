@@ -243,6 +243,26 @@ def config4(n_streams=16384, seconds=0.25, seed=4):
                    seed=(4 << 32) + seed, slack=slack)
 
 
+def all_rates(channels=2, seconds=0.3):
+    """Every PCM rate Jiffies::PerSample accepts (Msg.cpp:424-470: 7350 Hz ... 384 kHz) at every bit depth, the way
+    SuiteStarvationRamper sweeps them (TestStarvationRamper.cpp:861-915): one starvation per stream -- ramp down
+    kRampDownJiffies = 20 ms from a position aligned to nothing, halt, ramp up 50 ms -- messages of 5 ms."""
+    specs, evs = [], []
+    k = 0
+    for rate in abi.PCM_SAMPLE_RATES:
+        jps = abi.jiffies_per_sample(rate)
+        for bits in (8, 16, 24, 32):
+            chunk = max_chunk_frames(rate, bits, channels)
+            total = int(rate * seconds)
+            specs.append(_spec(rate, bits, channels, (k % 2) == 1, chunk, total))
+            down_at = total * jps // 4 + 977 * k + 1          # mid-message, mid-sample
+            up_at = down_at + 20 * MS + 5 * MS
+            evs.append([(0, 1, abi.EV_MAX_MSG_JIFFIES, 5 * MS), (down_at, 1, abi.EV_RAMP_DOWN, 20 * MS),
+                        (up_at, 1, abi.EV_RAMP_UP, 50 * MS)])
+            k += 1
+    return _finish("all rates x depths: %d streams, 20 ms down / 50 ms up" % len(specs), specs, evs, seed=7 << 32)
+
+
 def steady_edges(seed, n_streams=160):
     """Streams made for the walk's bulk step (32 uniform messages at a time): events exactly on, one jiffy and one
     sample either side of message boundaries; ramps whose length is a whole number of messages, give or take one

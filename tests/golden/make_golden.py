@@ -33,6 +33,7 @@ def cases():
     c4 = W.config4(n_streams=24, seconds=0.1, seed=4)
     c4.streams["out_fmt"] = abi.OUT_PACKED_BE     # the linked reference only has the packed-BE sink
     yield "config4_x24", c4
+    yield "all_rates", W.all_rates(seconds=0.2)               # 18 rates x 4 depths through a starvation
     yield "steady_edges_3", W.steady_edges(3, n_streams=48)   # the schedule walk's bulk step: events on / next to message boundaries
     for seed in (101, 102, 103, 104):
         w = W.mixed(n_streams=12, seed=seed, max_frames=1500)

@@ -81,6 +81,12 @@ def test_config3_8ch_32bit_le_starvation_ramps(ctx, port):
     check_workload(ctx, port, W.config3(n_streams=4, seconds=0.25, rate=192000), host=False)
 
 
+def test_every_rate_and_depth(ctx, port):
+    """7350 Hz ... 384 kHz x 8/16/24/32 bits (SuiteStarvationRamper's sweep), stereo and 6-channel."""
+    check_workload(ctx, port, W.all_rates())
+    check_workload(ctx, port, W.all_rates(channels=6, seconds=0.2), host=False)
+
+
 def test_config5_stereo24_96k(ctx, port):
     check_workload(ctx, port, W.config5(n_streams=16, seconds=0.25))
 

@@ -45,6 +45,12 @@ def test_baseline_configs(port, ref):
         assert compare(port, ref, w) is not None
 
 
+def test_every_rate_and_depth(port, ref):
+    """All 18 rates x 8/16/24/32 bits through a starvation (SuiteStarvationRamper's sweep, TestStarvationRamper.cpp:861-915)."""
+    assert compare(port, ref, W.all_rates()) is not None
+    assert compare(port, ref, W.all_rates(channels=6, seconds=0.2)) is not None
+
+
 @pytest.mark.parametrize("seed", range(40))
 def test_mixed_schedules(port, ref, seed):
     compare(port, ref, W.mixed(n_streams=24, seed=1000 + seed))

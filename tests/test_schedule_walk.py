@@ -83,3 +83,28 @@ def test_bulk_step_edges_match_class_model(seed):
 def test_walk_matches_class_model_on_pipeline_shaped_mix(seed):
     w = workloads.config4(n_streams=300, seconds=0.3, seed=seed)
     assert check(w.streams, w.events) is not None
+
+
+def test_starvation_ramps_at_every_rate_take_exactly_their_duration():
+    """SuiteStarvationRamper's properties (TestStarvationRamper.cpp:324-346, 634-692, 861-915) on the host model and the
+    walk, for all 18 rates x 4 depths: the ramp down takes exactly 20 ms of audio, the ramp up exactly 50 ms, every
+    playable's ramp starts where the previous one ended, what lies between is muted, the rest untouched."""
+    w = workloads.all_rates()
+    host = check(w.streams, w.events)
+    assert host is not None and len(w.streams) == 18 * 4
+    ms = abi.JIFFIES_PER_MS
+    for s in range(len(w.streams)):
+        a, b = int(host.stream_chunk_begin[s]), int(host.stream_chunk_begin[s + 1])
+        c, info = host.chunks[a:b], host.info[a:b]
+        down = info["direction"] == abi.DIR_DOWN
+        up = info["direction"] == abi.DIR_UP
+        assert int(info["jiffies"][down].sum()) == 20 * ms and int(info["jiffies"][up].sum()) == 50 * ms
+        for sel, first, last in ((down, abi.RAMP_MAX, 0), (up, 0, abi.RAMP_MAX)):
+            starts, ends = c["ramp_start"][sel], c["ramp_end"][sel]
+            assert starts[0] == first and ends[-1] == last
+            assert np.array_equal(starts[1:], ends[:-1])
+        i_down, i_up = np.nonzero(down)[0], np.nonzero(up)[0]
+        between = c[i_down[-1] + 1:i_up[0]]
+        assert len(between) and (between["flags"] & abi.F_SILENCE).all()          # Halt: muted audio plays as silence
+        outside = np.concatenate([c[:i_down[0]], c[i_up[-1] + 1:]])
+        assert not (outside["flags"] & (abi.F_RAMP_ENABLED | abi.F_SILENCE)).any()
