@@ -449,56 +449,92 @@ OHP_HD void seek_silence(const StreamCtx& cx, Cursor& c, uint32_t aFrom)
     c.silAt = i < cx.nEv ? cx.ev[i].at_jiffies : kNever;
 }
 
+// Messages taken from the codec source but not yet fed (only behind a block-reading codec, CodecSource::read != 0,
+// where message sizes are not uniform: the bulk step needs to see the sizes of the next ones).
+struct Lookahead
+{
+    uint32_t frames[kBulk];
+    uint32_t head, count;
+};
+
+OHP_HD void lookahead_fill(core::CodecSource& src, Lookahead& la)
+{
+    if (la.head != la.count) return;
+    la.head = 0;
+    la.count = 0;
+    while (la.count < kBulk) {
+        const uint32_t f = core::codec_source_next(src);
+        if (f == 0) break;
+        la.frames[la.count++] = f;
+    }
+}
+
+// Frames of the next message to enter the stage chain (0: the stream is over).
+OHP_HD uint32_t next_message(core::CodecSource& src, Lookahead& la)
+{
+    if (src.read == 0) return core::codec_source_next(src);
+    lookahead_fill(src, la);
+    return la.head != la.count ? la.frames[la.head++] : 0u;
+}
+
 // BULK STEP: up to kBulk consecutive messages at once, where nothing can happen to them but what is known up front.
 //
-// Between two events a stream is in a steady state: the codec delivers uniform messages, every stage is Running or
-// Muted, or exactly one is ramping and the others are Running; no message is split, no stack is touched.  Then the
-// only thing that is sequential is the ramping stage's recurrence (each message's ramp starts where the previous one
-// ended, MsgAudio::SetRamp rounding up every time, Msg.cpp:603-605) -- one division per message.  Everything else
-// (CreatePlayable's jiffy -> byte conversions, the descriptor) depends on the message index alone.  So:
-//   1. shrink n until no event, ramp end, silence insertion or end of stream falls inside the n messages;
-//   2. run the recurrence for the n messages with the very code the general path uses (msg_set_ramp on a fresh
-//      message), every lane of the team redundantly, lane (k % STRIDE) keeping message k's ramp; an early finish
-//      (ramp reached kMin/kMax) or anything unusual ends the run there;
+// Between two events a stream is in a steady state: every stage is Running or Muted, or exactly one is ramping and
+// the others are Running; no message is split, no stack is touched.  Then the only thing that is sequential is the
+// ramping stage's recurrence (each message's ramp starts where the previous one ended, MsgAudio::SetRamp rounding up
+// every time, Msg.cpp:603-605) -- one division per message.  Everything else (CreatePlayable's jiffy -> byte
+// conversions, the descriptor) depends on the message's index and position alone.  So:
+//   1. find the run: n messages that no event, ramp end, silence insertion, message-size cap or end of stream touches.
+//      Uniform messages (CodecWav, or no codec): closed forms, a division only where something cuts the run short.
+//      Behind a block-reading codec (CodecAiffBase + DecodedAudioAggregator: runs of 5 ms messages with a longer one
+//      where two reads meet) the sizes come from a lookahead buffer and the same tests are made message by message;
+//   2. run the recurrence over the run with the very code the general path uses (msg_set_ramp on a fresh message),
+//      every lane of the team redundantly, lane (k % STRIDE) keeping message k's ramp, size and position; an early
+//      finish (ramp reached kMin/kMax) or anything unusual ends the run there;
 //   3. lane i builds and emits messages i, i + STRIDE, ...: STRIDE descriptors per step, written side by side;
-//   4. advance all state by n messages.
 //   3b. with a driver that pulls fixed blocks (MsgPlayable::Split, Msg.cpp:2591-2624) a message becomes several
-//      playables; where the cuts fall follows from the message index, so lanes agree on their output slots through
-//      one prefix sum and each cuts its own message.
+//      playables; where the cuts fall follows from the message's position, so lanes agree on their output slots
+//      through one prefix sum and each cuts its own message;
+//   4. advance all state by n messages.
 // Returns n; 0 means "take the general path for the next message".  What the reference would ASSERT on in the stages
 // is left for the general path to find, at the same message; aErr only reports an ASSERT inside MsgPlayable::Split.
-template <bool EMIT, int STRIDE>
-OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[kStages], core::CodecSource& src, Cursor& cur,
-                          uint32_t& aErr)
+// UNIFORM: src.read == 0 (compiled separately so that the uniform case pays nothing for the ragged one's tests).
+template <bool EMIT, int STRIDE, bool UNIFORM>
+OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[kStages], core::CodecSource& src, Lookahead& la,
+                          Cursor& cur, uint32_t& aErr)
 {
     aErr = kOk;
-    if (src.read != 0) return 0;
     if (!(cx.bits == 8 || cx.bits == 16 || cx.bits == 24 || cx.bits == 32)) return 0;
-    const uint32_t chunk = src.chunk;
-    const uint32_t size = chunk * cx.jps;
-    uint32_t n = kBulk;
-    if (size > 0xffffffffu / kBulk) return 0; // keep n * size in 32 bits (9216 one-byte frames at 7350 Hz: general path)
-    if (src.total_left < (uint64_t)n * chunk) n = (uint32_t)src.total_left / chunk;
-    if (n == 0) return 0;
-    // MsgSilence due before message k is fed when silAt <= srcJiffies + k * size
-    if (cur.silAt <= cur.srcJiffies + (uint64_t)(n - 1) * size) {
-        if (cur.silAt <= cur.srcJiffies) return 0;
-        n = (uint32_t)(cur.silAt - cur.srcJiffies - 1) / size + 1;
+    constexpr bool uniform = UNIFORM;
+    uint32_t n, chunk = 0, size = 0;
+    if (uniform) {
+        chunk = src.chunk;
+        size = chunk * cx.jps;
+        if (size > 0xffffffffu / kBulk) return 0; // keep n * size in 32 bits (9216 one-byte frames at 7350 Hz: general path)
+        n = kBulk;
+        if (src.total_left < (uint64_t)n * chunk) n = (uint32_t)src.total_left / chunk;
     }
-    // stages: what mode, which one ramps, what attenuation the messages leave with
+    else {
+        lookahead_fill(src, la);
+        n = la.count - la.head;
+    }
+    if (n == 0) return 0;
+    if (cur.silAt <= cur.srcJiffies) return 0; // a MsgSilence is due first
+    const uint64_t silRoom = cur.silAt - cur.srcJiffies; // message k goes ahead of it iff its position is below this
+    if (uniform && silRoom <= (uint64_t)(n - 1) * size) n = (uint32_t)(silRoom - 1) / size + 1;
+    // stages: what mode, which one ramps, what attenuation the messages leave with, how far the next event is
     uint32_t ramping = 0, muted = 0, atten = OHP_UNITY_ATTENUATION;
     uint32_t rMode = Running, rCurrent = 0, rRemaining = 0;
+    uint64_t eventRoom = kNever;     // jiffies that can pass every stage before its next event
+    uint32_t sizeCap = 0xffffffffu;  // the tightest OHP_EV_MAX_MSG_JIFFIES in force
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < kStages; i++) {
         const Stage& s = st[i];
-        if (s.maxMsg != 0 && size > s.maxMsg) return 0;
-        if (s.nextAt < s.pos + (uint64_t)n * size) {
-            if (s.nextAt <= s.pos) return 0;
-            n = (uint32_t)(s.nextAt - s.pos) / size; // whole messages in front of the event
-            if (n == 0) return 0;
-        }
+        if (s.nextAt <= s.pos) return 0; // an event to apply first
+        if (s.nextAt - s.pos < eventRoom) eventRoom = s.nextAt - s.pos;
+        if (s.maxMsg != 0 && s.maxMsg < sizeCap) sizeCap = s.maxMsg;
         if (s.attenuation != OHP_UNITY_ATTENUATION) atten = s.attenuation;
         if (s.mode == Muted) muted++;
         else if (s.mode != Running) {
@@ -507,24 +543,54 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
         }
     }
     if (ramping > 1 || (ramping == 1 && muted != 0)) return 0;
+    if (ramping && rRemaining == 0) return 0; // a zero-length ramp: the general path flips the mode
+    if (uniform) {
+        if (size > sizeCap) return 0;
+        if (eventRoom < (uint64_t)n * size) n = (uint32_t)eventRoom / size; // whole messages in front of the event
+        if (ramping && rRemaining < n * size) n = rRemaining / size;        // ... and of the end of the ramp
+        if (n == 0) return 0;
+    }
+    // the run, message by message: ragged sizes are tested as they come; the ramp recurrence advances
     core::RampPod mine[kBulk / STRIDE];
-    if (ramping) {
-        if (rRemaining < size) return 0; // ramp end inside the next message (or a zero-length ramp): general path
-        if (rRemaining < n * size) n = rRemaining / size;
+    uint32_t mineFrames[kBulk / STRIDE];
+    uint32_t minePos[kBulk / STRIDE];   // frames of the run in front of the message
+    uint32_t posFrames = 0;
+    uint64_t posJiffies = 0;
+    if (uniform && !ramping) {
+        posFrames = n * chunk;
+        posJiffies = (uint64_t)n * size;
+        for (uint32_t i = cx.lane; i < n; i += STRIDE) { mineFrames[i / STRIDE] = chunk; minePos[i / STRIDE] = i * chunk; }
+    }
+    else {
         const uint32_t dir = rMode == RampingDown ? core::kDirDown : core::kDirUp;
         uint32_t done = 0;
         for (uint32_t k = 0; k < n; k++) {
-            Msg t, rest;
-            t.cell = 0; t.size = size; t.offset = 0; t.total = 0; t.atten = OHP_UNITY_ATTENUATION; t.silence = 0;
-            core::ramp_reset(t.ramp);
-            bool haveSplit;
-            uint32_t remaining = rRemaining, current = rCurrent;
-            const uint32_t e = msg_set_ramp(t, rCurrent, remaining, dir, rest, haveSplit, current, cx.jps);
-            if (e != kOk || haveSplit) break;
-            rRemaining = remaining; rCurrent = current;
-            if (k % STRIDE == cx.lane) mine[k / STRIDE] = t.ramp;
+            const uint32_t f = uniform ? chunk : la.frames[la.head + k];
+            const uint32_t sz = f * cx.jps;
+            if (!uniform) {
+                if (sz > sizeCap || posJiffies + sz > eventRoom || posJiffies >= silRoom) break;
+            }
+            core::RampPod ramp;
+            if (ramping) {
+                if (rRemaining < sz) break; // the ramp ends inside this message: it will be split
+                Msg t, rest;
+                t.cell = 0; t.size = sz; t.offset = 0; t.total = 0; t.atten = OHP_UNITY_ATTENUATION; t.silence = 0;
+                core::ramp_reset(t.ramp);
+                bool haveSplit;
+                uint32_t remaining = rRemaining, current = rCurrent;
+                const uint32_t e = msg_set_ramp(t, rCurrent, remaining, dir, rest, haveSplit, current, cx.jps);
+                if (e != kOk || haveSplit) break;
+                rRemaining = remaining; rCurrent = current;
+                ramp = t.ramp;
+            }
+            else {
+                core::ramp_reset(ramp);
+            }
+            if (k % STRIDE == cx.lane) { mine[k / STRIDE] = ramp; mineFrames[k / STRIDE] = f; minePos[k / STRIDE] = posFrames; }
+            posFrames += f;
+            posJiffies += sz;
             done = k + 1;
-            if (rRemaining == 0) { // as stage_process: the ramp is over, this message was its last
+            if (ramping && rRemaining == 0) { // as stage_process: the ramp is over, this message was its last
                 if (rMode == RampingUp) { rMode = Running; rCurrent = core::kRampMax; }
                 else { rMode = Muted; rCurrent = core::kRampMin; }
                 break;
@@ -533,34 +599,37 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
         n = done;
         if (n == 0) return 0;
     }
-    // every message of the run: the same size at offset 0 of its own cell
+    // every message of the run sits at offset 0 of its own cell; frames * frameBytes bytes each (CreatePlayable)
     Msg m;
-    m.cell = 0; m.size = size; m.offset = 0; m.total = 0; m.atten = atten; m.silence = 0;
+    m.cell = 0; m.size = 0; m.offset = 0; m.total = 0; m.atten = atten; m.silence = 0;
     core::ramp_reset(m.ramp);
     if (muted) core::ramp_set_muted(m.ramp);
-    const uint32_t bytes = create_playable(m, cx).size; // the same for every message of the run
-    const uint32_t block = (bytes != 0) ? cx.blockBytes : 0;
+    const uint32_t block = cx.blockBytes;
     uint32_t pieces = 0; // playables emitted by the messages in front of this iteration's
     uint32_t err = kOk;
     if (EMIT || block != 0) {
         for (uint32_t i0 = 0; i0 < n; i0 += STRIDE) {
             const uint32_t i = i0 + cx.lane;
             const bool active = i < n;
-            // a driver pulling fixed blocks (stage_chain.h Drive()): message i starts (fill + i * bytes) % block into a
-            // block and is cut at every block boundary strictly inside it
+            const uint32_t frames = active ? mineFrames[i / STRIDE] : 0u;
+            const uint32_t before_bytes = active ? minePos[i / STRIDE] * cx.frameBytes : 0u;
+            const uint32_t bytes = frames * cx.frameBytes;
+            // a driver pulling fixed blocks (stage_chain.h Drive()): the message starts (fill + bytes before it) % block
+            // into a block and is cut at every block boundary strictly inside it
             uint32_t fill = 0, count = active ? 1u : 0u;
             if (block != 0 && active) {
-                fill = (cx.blockFill + i * bytes) % block;
+                fill = (cx.blockFill + before_bytes) % block;
                 count += (fill + bytes - 1) / block;
             }
             uint32_t total;
             const uint32_t before = team_scan_exclusive<STRIDE>(count, cx.lane, total);
             if (active && (EMIT || ramping)) { // counting needs the cuts themselves only for what Ramp::Split may ASSERT on
-                m.cell = sp.src_base + (cur.frame + (uint64_t)i * chunk) * cx.frameBytes;
+                m.cell = sp.src_base + (cur.frame + minePos[i / STRIDE]) * cx.frameBytes;
+                m.size = frames * cx.jps;
                 if (ramping) m.ramp = mine[i / STRIDE];
                 Playable p = create_playable(m, cx);
                 uint64_t index = cx.nChunks + pieces + before;
-                uint64_t off = cx.outBytes + (uint64_t)i * bytes;
+                uint64_t off = cx.outBytes + before_bytes;
                 while (block != 0 && p.size > block - fill) {
                     Playable rest;
                     const uint32_t e = playable_split(p, block - fill, rest, cx);
@@ -580,19 +649,21 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
     else {
         pieces = n;
     }
-    if (block != 0) cx.blockFill = (cx.blockFill + n * bytes) % block;
+    const uint64_t run_bytes = (uint64_t)posFrames * cx.frameBytes;
+    if (block != 0) cx.blockFill = (uint32_t)((cx.blockFill + run_bytes) % block);
     // advance
     cx.nChunks += pieces;
-    cx.outBytes += (uint64_t)n * bytes;
-    cur.frame += (uint64_t)n * chunk;
-    cur.srcJiffies += (uint64_t)n * size;
-    src.total_left -= (uint64_t)n * chunk;
+    cx.outBytes += run_bytes;
+    cur.frame += posFrames;
+    cur.srcJiffies += posJiffies;
+    if (uniform) src.total_left -= posFrames;
+    else la.head += n;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < kStages; i++) {
         Stage& s = st[i];
-        s.pos += (uint64_t)n * size;
+        s.pos += posJiffies;
         if (s.mode == RampingDown || s.mode == RampingUp) { s.mode = rMode; s.current = rCurrent; s.remaining = rRemaining; }
     }
     return n;
@@ -656,14 +727,23 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
     seek_silence(cx, cur, 0);
     core::CodecSource source;
     core::codec_source_init(source, sp.chunk_frames, sp.codec_read_frames, cx.frameBytes, cx.jps, sp.total_frames);
+    Lookahead la;
+    la.head = la.count = 0;
     for (;;) {
         if (BULK) {
             uint32_t e;
-            const uint32_t n = bulk_step<EMIT, STRIDE>(sp, cx, st, source, cur, e);
+            const uint32_t n = source.read == 0 ? bulk_step<EMIT, STRIDE, true>(sp, cx, st, source, la, cur, e)
+                                                : bulk_step<EMIT, STRIDE, false>(sp, cx, st, source, la, cur, e);
             if (e != kOk) return e;
+#ifdef OHP_WALK_STATS
+            if (n != 0) { g_bulk_calls++; g_bulk_msgs += n; }
+#endif
             if (n != 0) continue;
         }
-        const uint32_t frames = core::codec_source_next(source);
+        const uint32_t frames = next_message(source, la);
+#ifdef OHP_WALK_STATS
+        if (frames != 0) g_general++;
+#endif
         if (frames == 0) break;
         Msg m;
         while (cur.silAt <= cur.srcJiffies) {

@@ -285,6 +285,8 @@ def steady_edges(seed, n_streams=160):
         use_silence = rng.random() < 0.3
         q = jps if use_silence else 1
         spec = _spec(rate, bits, ch, bool(rng.integers(0, 2)), chunk, total, abi.OUT_PACKED_BE, max(block, 0))
+        if chunk == max_chunk_frames(rate, bits, ch) and rng.random() < 0.3:
+            spec["codec_read_frames"] = abi.MAX_PCM_CHUNK_BYTES // fb     # born from an Aiff file (CodecAiffBase reads blocks)
         lst, extra = [], 0
 
         def near_boundary():
