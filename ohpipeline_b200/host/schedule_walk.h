@@ -556,23 +556,18 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
     uint32_t minePos[kBulk / STRIDE];   // frames of the run in front of the message
     uint32_t posFrames = 0;
     uint64_t posJiffies = 0;
-    if (uniform && !ramping) {
-        posFrames = n * chunk;
-        posJiffies = (uint64_t)n * size;
-        for (uint32_t i = cx.lane; i < n; i += STRIDE) { mineFrames[i / STRIDE] = chunk; minePos[i / STRIDE] = i * chunk; }
-    }
-    else {
+    if (!uniform || ramping) {
         const uint32_t dir = rMode == RampingDown ? core::kDirDown : core::kDirUp;
         uint32_t done = 0;
         for (uint32_t k = 0; k < n; k++) {
             const uint32_t f = uniform ? chunk : la.frames[la.head + k];
-            const uint32_t sz = f * cx.jps;
+            const uint32_t sz = uniform ? size : f * cx.jps;
             if (!uniform) {
                 if (sz > sizeCap || posJiffies + sz > eventRoom || posJiffies >= silRoom) break;
             }
             core::RampPod ramp;
             if (ramping) {
-                if (rRemaining < sz) break; // the ramp ends inside this message: it will be split
+                if (!uniform && rRemaining < sz) break; // the ramp ends inside this message: it will be split
                 Msg t, rest;
                 t.cell = 0; t.size = sz; t.offset = 0; t.total = 0; t.atten = OHP_UNITY_ATTENUATION; t.silence = 0;
                 core::ramp_reset(t.ramp);
@@ -586,9 +581,11 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
             else {
                 core::ramp_reset(ramp);
             }
-            if (k % STRIDE == cx.lane) { mine[k / STRIDE] = ramp; mineFrames[k / STRIDE] = f; minePos[k / STRIDE] = posFrames; }
-            posFrames += f;
-            posJiffies += sz;
+            if (k % STRIDE == cx.lane) {
+                mine[k / STRIDE] = ramp;
+                if (!uniform) { mineFrames[k / STRIDE] = f; minePos[k / STRIDE] = posFrames; }
+            }
+            if (!uniform) { posFrames += f; posJiffies += sz; }
             done = k + 1;
             if (ramping && rRemaining == 0) { // as stage_process: the ramp is over, this message was its last
                 if (rMode == RampingUp) { rMode = Running; rCurrent = core::kRampMax; }
@@ -598,6 +595,10 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
         }
         n = done;
         if (n == 0) return 0;
+    }
+    if (uniform) { // positions follow from the index
+        posFrames = n * chunk;
+        posJiffies = (uint64_t)n * size;
     }
     // every message of the run sits at offset 0 of its own cell; frames * frameBytes bytes each (CreatePlayable)
     Msg m;
@@ -611,8 +612,9 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
         for (uint32_t i0 = 0; i0 < n; i0 += STRIDE) {
             const uint32_t i = i0 + cx.lane;
             const bool active = i < n;
-            const uint32_t frames = active ? mineFrames[i / STRIDE] : 0u;
-            const uint32_t before_bytes = active ? minePos[i / STRIDE] * cx.frameBytes : 0u;
+            const uint32_t frames = !active ? 0u : (uniform ? chunk : mineFrames[i / STRIDE]);
+            const uint32_t before_frames = !active ? 0u : (uniform ? i * chunk : minePos[i / STRIDE]);
+            const uint32_t before_bytes = before_frames * cx.frameBytes;
             const uint32_t bytes = frames * cx.frameBytes;
             // a driver pulling fixed blocks (stage_chain.h Drive()): the message starts (fill + bytes before it) % block
             // into a block and is cut at every block boundary strictly inside it
@@ -624,7 +626,7 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
             uint32_t total;
             const uint32_t before = team_scan_exclusive<STRIDE>(count, cx.lane, total);
             if (active && (EMIT || ramping)) { // counting needs the cuts themselves only for what Ramp::Split may ASSERT on
-                m.cell = sp.src_base + (cur.frame + minePos[i / STRIDE]) * cx.frameBytes;
+                m.cell = sp.src_base + (cur.frame + before_frames) * cx.frameBytes;
                 m.size = frames * cx.jps;
                 if (ramping) m.ramp = mine[i / STRIDE];
                 Playable p = create_playable(m, cx);
