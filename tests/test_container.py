@@ -309,3 +309,33 @@ def test_batch_born_from_container_bytes_on_the_gpu(ctx, port):
         be = raw.reshape(-1, b)[:, ::-1].reshape(-1) if (little and b > 1) else raw
         lo = int(w.streams[k]["dst_base"])
         assert np.array_equal(got[lo:lo + n], be), cases[k]
+
+
+def test_parser_survives_mutated_and_truncated_headers():
+    """Hostile bytes: every prefix of valid files and thousands of random mutations parse to a status, never past the
+    buffer (the reader is bounds-checked; run under the default allocator this would crash on an over-read of the
+    exact-size numpy buffer often enough to notice), and whatever parses OK describes audio that lies inside the file
+    or is clamped by ohp_container_stream_spec."""
+    rng = np.random.default_rng(11)
+    seeds = [wav_bytes(44100, 16, 2, 50)[0], wav_bytes(96000, 24, 6, 20)[0], aiff_bytes(48000, 24, 2, 40)[0],
+             aiff_bytes(44100, 16, 2, 40, sowt=True)[0]]
+    statuses = set()
+    for data in seeds:
+        for cut in range(0, min(len(data), 120)):
+            rc, _ = capi.container_parse(data[:cut])
+            statuses.add(rc)
+            assert rc != abi.CONTAINER_OK or cut >= 44
+        for _ in range(1500):
+            b = bytearray(data[:int(rng.integers(12, len(data) + 1))])
+            for _ in range(int(rng.integers(1, 6))):
+                i = int(rng.integers(0, min(len(b), 64)))
+                b[i] = int(rng.integers(0, 256))
+            rc, info = capi.container_parse(bytes(b))
+            statuses.add(rc)
+            assert 0 <= rc <= abi.CONTAINER_E_ARG
+            if rc == abi.CONTAINER_OK:
+                rc2, spec = capi.container_stream_spec(info, len(b))
+                if rc2 == abi.CONTAINER_OK:
+                    fb = int(spec["channels"]) * int(spec["bit_depth"]) // 8
+                    assert int(spec["src_base"]) + int(spec["total_frames"]) * fb <= len(b)
+    assert {abi.CONTAINER_OK, abi.CONTAINER_E_UNRECOGNISED, abi.CONTAINER_E_ENDED, abi.CONTAINER_E_CORRUPT} <= statuses
