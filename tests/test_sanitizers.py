@@ -71,3 +71,37 @@ def test_schedule_model_and_walk_under_sanitizers(tmp_path):
         dump(workloads.config3(n_streams=30, seconds=1.0))
     exe = build(tmp_path, "schedule_fuzz", [os.path.join(HOST, "schedule.cpp"), os.path.join(HOST, "msg_model.cpp")])
     assert "chunks" in run(exe, path)
+
+
+def test_bulk_step_covers_the_steady_stretches(tmp_path):
+    """A performance property of the GPU schedule builder that can be checked on the CPU: on the BASELINE configs nearly
+    every message goes through the bulk step (32 at a time); only what an event, a ramp end or a split touches is
+    walked one at a time."""
+    cases = [("config2", workloads.config2(n_streams=4, seconds=10.0), 0.99, 28.0),
+             ("config5", workloads.config5(n_streams=8, seconds=1.0), 0.97, 20.0),
+             ("config3", workloads.config3(n_streams=64, seconds=1.0), 0.80, 4.0),
+             ("config4", workloads.config4(n_streams=256, seconds=0.25), 0.75, 4.0),
+             ("all_rates", workloads.all_rates(), 0.80, 4.0)]
+    aiff = workloads.config2(n_streams=4, seconds=10.0)
+    aiff.streams["sample_rate"] = 44100; aiff.streams["bit_depth"] = 16; aiff.streams["chunk_frames"] = 220
+    aiff.streams["total_frames"] = 441000; aiff.streams["codec_read_frames"] = 9216 // 4
+    cases.append(("aiff-born", aiff, 0.99, 25.0))
+    path = str(tmp_path / "cases.bin")
+    with open(path, "wb") as out:
+        for _, w, _, _ in cases:
+            out.write(struct.pack("<II", len(w.streams), len(w.events)) + w.streams.tobytes() + w.events.tobytes())
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "walk_stats")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                        os.path.join(ROOT, "tests", "sanitize", "walk_stats.cpp")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    lines = subprocess.run([exe, path], stdout=subprocess.PIPE, text=True, check=True).stdout.strip().splitlines()
+    assert len(lines) == len(cases)
+    for (name, _, min_share, min_run), line in zip(cases, lines):
+        chunks, calls, bulk, general = (int(x) for x in line.split())
+        assert chunks > 0 and calls > 0, name
+        share = bulk / (bulk + general)
+        assert share >= min_share, (name, share)
+        assert bulk / calls >= min_run, (name, bulk / calls)
