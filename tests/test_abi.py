@@ -135,3 +135,17 @@ def test_validate_rejects_what_the_reference_asserts_on():
         assert capi.validate(d, 1 << 20, 1 << 20)[0] == abi.E_INVALID_DESC, d
     assert capi.validate(make_desc(bytes=24, bit_depth=24, channels=2, src_off=60), 64, 64)[0] == abi.E_OUT_OF_RANGE
     assert capi.validate(make_desc(bytes=24, bit_depth=24, channels=2, dst_off=60), 64, 64)[0] == abi.E_OUT_OF_RANGE
+
+
+def test_headers_are_plain_c99_and_cxx11(tmp_path):
+    """The drop-in boundary is a C ABI: every header in include/ compiles alone as strict C99 and as C++11 (no torch, no
+    CUDA types in the signatures), so cgo / JNI / ctypes / a C++ adapter can all bind it."""
+    import glob
+    import subprocess
+    for hdr in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        src = tmp_path / "one.c"
+        src.write_text('#include "%s"\nint main(void) { return 0; }\n' % os.path.basename(hdr))
+        for cmd in (["gcc", "-std=c99"], ["g++", "-std=c++11", "-x", "c++"]):
+            r = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c", str(src),
+                                      "-o", str(tmp_path / "one.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert r.returncode == 0, (hdr, cmd, r.stdout[-2000:])
