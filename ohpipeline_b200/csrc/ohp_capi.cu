@@ -18,6 +18,7 @@
 #include <sched.h>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace ohp {
@@ -364,12 +365,43 @@ uint32_t ohp_chunk_out_bytes(const ohp_chunk_desc* d)
 int ohp_validate(const ohp_chunk_desc* descs, size_t n, uint64_t in_bytes, uint64_t out_bytes, size_t* bad_index)
 {
     if (!descs && n) return OHP_E_INVALID_ARG;
-    for (size_t i = 0; i < n; i++) {
-        const int rc = check_desc(descs[i], in_bytes, out_bytes);
-        if (rc != OHP_OK) {
-            if (bad_index) *bad_index = i;
-            return rc;
+    // the first offending descriptor in [lo, hi), or hi
+    auto scan = [&](size_t lo, size_t hi, int* rc_out) -> size_t {
+        for (size_t i = lo; i < hi; i++) {
+            const int rc = check_desc(descs[i], in_bytes, out_bytes);
+            if (rc != OHP_OK) { *rc_out = rc; return i; }
         }
+        return hi;
+    };
+    // large batches (ohp_process_host checks millions of descriptors before the first byte moves): over a few threads
+    unsigned workers = 1;
+    if (n >= (1u << 18)) {
+        workers = std::thread::hardware_concurrency();
+        workers = workers == 0 ? 1u : (workers > 8u ? 8u : workers);
+    }
+    size_t first_bad = n;
+    int first_rc = OHP_OK;
+    if (workers <= 1) {
+        first_bad = scan(0, n, &first_rc);
+    }
+    else {
+        std::vector<size_t> bad(workers, n);
+        std::vector<int> rcs(workers, OHP_OK);
+        std::vector<std::thread> pool;
+        const size_t per = (n + workers - 1) / workers;
+        for (unsigned t = 0; t < workers; t++) {
+            const size_t lo = (size_t)t * per < n ? (size_t)t * per : n;
+            const size_t hi = lo + per < n ? lo + per : n;
+            pool.emplace_back([&, t, lo, hi] { const size_t b = scan(lo, hi, &rcs[t]); bad[t] = b < hi ? b : n; });
+        }
+        for (std::thread& th : pool) th.join();
+        for (unsigned t = 0; t < workers; t++) {
+            if (bad[t] < first_bad) { first_bad = bad[t]; first_rc = rcs[t]; }
+        }
+    }
+    if (first_bad < n) {
+        if (bad_index) *bad_index = first_bad;
+        return first_rc;
     }
     return OHP_OK;
 }
