@@ -72,6 +72,9 @@ namespace ohp {
 #ifndef OHP_GROUPS_PER_STEP
 #define OHP_GROUPS_PER_STEP 1
 #endif
+#ifndef OHP_DEFER_RELEASE
+#define OHP_DEFER_RELEASE 0 /* experiment, not measured yet: a consumer hands its slot back when it takes its next chunk (see the kernel) */
+#endif
 #ifndef OHP_DYNAMIC
 #define OHP_DYNAMIC 1       /* 1: consumer warps take chunks by ticket (first come, first served); 0: chunk k -> warp k % warps */
 #endif

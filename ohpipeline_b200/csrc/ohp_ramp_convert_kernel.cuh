@@ -352,6 +352,10 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
         // ------------------------------------------------------------------ consumers: one warp per chunk
         const uint32_t cw = warp - 1;
         const uint32_t table = smem_u32(&sm.table2[0]);
+#if OHP_DEFER_RELEASE
+        constexpr uint32_t kNoPending = 0xffffffffu;
+        uint32_t pending = kNoPending; // barrier pair of the chunk whose slot this warp has yet to hand back
+#endif
 #if OHP_DYNAMIC
         for (;;) {
             unsigned long long ticket = 0;
@@ -363,6 +367,18 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
             const uint32_t bs = (uint32_t)(it % kBarPairs);
             const uint32_t ph = (uint32_t)(it / kBarPairs) & 1u;
+#if OHP_DEFER_RELEASE
+            // Experiment (off): the previous chunk's slot is handed back only now, so that its bulk store drains while the
+            // ticket is fetched.  It MUST be handed back before this warp blocks: the loader reclaims in order, and the
+            // chunk waited for may be the one that needs that very slot.
+            if (pending != kNoPending) {
+                const bool ready = __all_sync(0xffffffffu, mbar_test(smem_u32(&sm.full[bs]), ph));
+                if (!ready) {
+                    if (lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
+                    pending = kNoPending;
+                }
+            }
+#endif
 #if OHP_CONSUMER_POLL == 0
             OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
 #elif OHP_CONSUMER_POLL == 1
@@ -372,6 +388,12 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
             if (!__all_sync(0xffffffffu, mbar_test(smem_u32(&sm.full[bs]), ph))) {
                 if (lane == 0) OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
                 __syncwarp();
+            }
+#endif
+#if OHP_DEFER_RELEASE
+            if (pending != kNoPending) { // the data was there already: the store had the ticket fetch to drain in
+                if (lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
+                pending = kNoPending;
             }
 #endif
             const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
@@ -451,12 +473,17 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     const long long ts = clock64();
                     w_issue += ts - tx2;
 #endif
+#if !OHP_DEFER_RELEASE
                     tma_wait_read<0>(); // the slot can be reused once the bulk store has READ it
 #ifdef OHP_PROFILE_WAITS
                     w_store += clock64() - ts;
 #endif
                     mbar_arrive(smem_u32(&sm.empty[bs]));
+#endif
                 }
+#if OHP_DEFER_RELEASE
+                pending = bs;
+#endif
                 __syncwarp();
             } else {
                 if (kind == kSilence) {
@@ -467,6 +494,9 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs]));
             }
         }
+#if OHP_DEFER_RELEASE
+        if (pending != kNoPending && lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
+#endif
         if (lane == 0) {
             tma_wait_all<0>(); // every bulk store complete before the CTA (and its shared memory) goes away
             if (cw == 0) { OHP_FLUSH(5, w_full); OHP_FLUSH(6, w_store); OHP_FLUSH(9, w_xform); OHP_FLUSH(10, w_fence); OHP_FLUSH(11, w_issue); }
