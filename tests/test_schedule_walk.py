@@ -108,3 +108,37 @@ def test_starvation_ramps_at_every_rate_take_exactly_their_duration():
         assert len(between) and (between["flags"] & abi.F_SILENCE).all()          # Halt: muted audio plays as silence
         outside = np.concatenate([c[:i_down[0]], c[i_up[-1] + 1:]])
         assert not (outside["flags"] & (abi.F_RAMP_ENABLED | abi.F_SILENCE)).any()
+
+
+@pytest.mark.parametrize("rate,bits", [(44100, 16), (192000, 24), (48000, 32)])
+def test_ramp_lengths_of_the_pipeline_elements(rate, bits):
+    """SuiteRamper / SuiteMuter (TestRamper.cpp:399-437, TestMuter.cpp:306-338): a ramp takes exactly the jiffies it was
+    configured with -- Ramper's long and short ramps (500 / 50 ms, Pipeline.h:102-104), Muter's 500 ms, StarvationRamper's
+    20 ms down / 50 ms up -- wherever in a message it starts; audio outside it is untouched (up) or muted (after down)."""
+    ms = abi.JIFFIES_PER_MS
+    jps = abi.jiffies_per_sample(rate)
+    chunk = workloads.max_chunk_frames(rate, bits, 2)
+    total = rate * 2
+    for dur_ms in (20, 50, 500):
+        for op, mute_first in ((abi.EV_RAMP_DOWN, False), (abi.EV_RAMP_UP, True)):
+            start = 300 * ms + 12345            # mid-message, mid-sample
+            ev = ([(0, 0, abi.EV_MUTE, 0)] if mute_first else []) + [(start, 0, op, dur_ms * ms)]
+            w = workloads._finish("ramp length", [workloads._spec(rate, bits, 2, False, chunk, total)], [ev], seed=1)
+            host = check(w.streams, w.events)
+            assert host is not None
+            d = host.info["direction"]
+            sel = d == (abi.DIR_DOWN if op == abi.EV_RAMP_DOWN else abi.DIR_UP)
+            assert int(host.info["jiffies"][sel].sum()) == dur_ms * ms
+            c = host.chunks[sel]
+            assert c["ramp_start"][0] == (abi.RAMP_MAX if op == abi.EV_RAMP_DOWN else 0)
+            assert c["ramp_end"][-1] == (0 if op == abi.EV_RAMP_DOWN else abi.RAMP_MAX)
+            assert np.array_equal(c["ramp_start"][1:], c["ramp_end"][:-1])
+            first, last = np.nonzero(sel)[0][[0, -1]]
+            before, after = host.chunks[:first], host.chunks[last + 1:]
+            quiet = abi.F_SILENCE
+            if op == abi.EV_RAMP_DOWN:
+                assert not (before["flags"] & (abi.F_RAMP_ENABLED | quiet)).any() and (after["flags"] & quiet).all() and len(after)
+            else:
+                assert (before["flags"] & quiet).all() and not (after["flags"] & (abi.F_RAMP_ENABLED | quiet)).any() and len(after)
+            # the bytes in front of the ramp are whole samples: the split at a mid-sample jiffy rounds down (Msg.cpp:2236-2240)
+            assert int(before["bytes"].sum()) == (start // jps) * 2 * bits // 8
