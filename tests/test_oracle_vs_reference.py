@@ -51,6 +51,25 @@ def test_every_rate_and_depth(port, ref):
     assert compare(port, ref, W.all_rates(channels=6, seconds=0.2)) is not None
 
 
+@pytest.mark.parametrize("seed", [4, 31, 32])
+def test_pipeline_shaped_mix(port, ref, seed):
+    """BASELINE configs[3] as the bench runs it (workloads.config4): the reference, the port and the host mirror agree."""
+    assert compare(port, ref, W.config4(n_streams=120, seconds=0.12, seed=seed)) is not None
+
+
+@pytest.mark.parametrize("seed", [3, 51, 52])
+def test_bulk_step_edge_cases(port, ref, seed):
+    """Events on and next to message boundaries, whole-message ramps, Aiff-born streams, driver blocks (workloads.
+    steady_edges) -- stream by stream, so that one the reference ASSERTs on does not hide its neighbours."""
+    w = W.steady_edges(seed, n_streams=60)
+    refused = 0
+    for k in range(len(w.streams)):
+        one = W.Workload(w.name, w.streams[k:k + 1].copy(), w.events, w.in_bytes, w.out_bytes, w.seed)
+        if compare(port, ref, one) is None:
+            refused += 1
+    assert refused < 6
+
+
 @pytest.mark.parametrize("seed", range(40))
 def test_mixed_schedules(port, ref, seed):
     compare(port, ref, W.mixed(n_streams=24, seed=1000 + seed))
