@@ -105,3 +105,22 @@ def test_bulk_step_covers_the_steady_stretches(tmp_path):
         share = bulk / (bulk + general)
         assert share >= min_share, (name, share)
         assert bulk / calls >= min_run, (name, bulk / calls)
+
+
+def test_cpp_host_mirror_suite_under_sanitizers(tmp_path):
+    """The reference-style C++ suites of the host mirror (tests/cpp/test_host_api.cpp, CPU part: ramp algebra and the
+    message model with its ref-counted, recycled messages) under ASan + UBSan + leak check."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    pkg = os.path.join(ROOT, "ohpipeline_b200")
+    exe = str(tmp_path / "test_host_api_san")
+    r = subprocess.run(["g++"] + FLAGS + ["-o", exe, os.path.join(ROOT, "tests", "cpp", "test_host_api.cpp"),
+                                          os.path.join(HOST, "msg_model.cpp"), "-L" + pkg, "-lohp_b200", "-Wl,-rpath," + pkg, "-ldl"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0 and "sanitize" in r.stdout and "cannot find" in r.stdout:
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stdout[-3000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "PASS" in r.stdout and "0 failures" in r.stdout, r.stdout[-3000:]
