@@ -133,6 +133,9 @@ int         ohp_process_device(ohp_context* ctx, const ohp_chunk_desc* d_descs, 
  * Same, with HOST buffers: validates, copies descriptors and input to the device, runs the
  * kernel and copies the output back, pipelined in slices over the context's copy streams.
  * Synchronous.  h_in / h_out may be pageable; pinned memory (ohp_host_alloc) is faster.
+ * Only bytes some chunk covers are written to h_out: everything else reads afterwards as the caller left it (a hole of
+ * up to 4 KiB between two covered ranges is overwritten and restored while the call runs).  However the call ends, no
+ * copy or kernel of it is still in flight when it returns.
  */
 int         ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n,
                              const uint8_t* h_in, uint64_t in_bytes,

@@ -50,7 +50,8 @@ int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams,
  * D2H pipelined.  h_in / h_out should be pinned (ohp_host_alloc) for full PCIe speed.  Synchronous.
  *   h_stream_out_bytes (n_streams, may be NULL): bytes each stream produced at h_out + dst_base.
  *   total_chunks (may be NULL): playables read.
- * Output bytes between streams (alignment gaps) that fall inside a slice's span receive unspecified values.
+ * Only bytes some stream produces are written: gaps between streams in h_out read afterwards as the caller left them.
+ * On any error nothing of the call is still in flight when it returns.
  * Errors: as ohp_schedule_count_device (the reference would ASSERT: OHP_E_INVALID_DESC; spec not representable:
  * OHP_E_INVALID_ARG), OHP_E_OUT_OF_RANGE when a stream reaches outside the arenas.
  */

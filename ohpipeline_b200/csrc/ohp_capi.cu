@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <cctype>
 #include <mutex>
 #include <sched.h>
@@ -131,6 +132,103 @@ struct SliceMode
     ~SliceMode() { ctx->timing = timing; ctx->autotune = autotune; }
     SliceMode(const SliceMode&) = delete;
     SliceMode& operator=(const SliceMode&) = delete;
+};
+
+// The synchronous host-buffer calls drive three streams.  However such a call ends -- a failed launch or copy in the
+// middle of the slice loop included -- nothing of it may still be in flight when it returns: the caller is free to reuse
+// or free h_in / h_out the moment it has the status.
+struct DrainOnExit
+{
+    ohp_context* ctx;
+    cudaStream_t compute;
+    DrainOnExit(ohp_context* c, cudaStream_t st) : ctx(c), compute(st) {}
+    ~DrainOnExit()
+    {
+        if (ctx->copy_in) (void)cudaStreamSynchronize(ctx->copy_in);
+        if (compute) (void)cudaStreamSynchronize(compute);
+        if (ctx->copy_out) (void)cudaStreamSynchronize(ctx->copy_out);
+        (void)cudaGetLastError(); // the call's own status has been decided already
+    }
+    DrainOnExit(const DrainOnExit&) = delete;
+    DrainOnExit& operator=(const DrainOnExit&) = delete;
+};
+
+// What a host-buffer call copies back.  Only bytes some chunk writes belong to the call: everything else in h_out is
+// the caller's and must read afterwards as it did before.  A slice's covered ranges are merged into few, large D2H
+// copies; a small hole between two of them (alignment padding between streams, typically < 16 bytes) is bridged.  What
+// a bridge drags along is either covered by another slice -- whose own copy, earlier or later on the in-order copy
+// stream, leaves the final bytes -- or covered by nothing in the whole batch: those holes are found by one pass over the
+// whole batch BEFORE anything is issued, their bytes saved, and put back once the copies have drained.
+class RangeSet
+{
+public:
+    static constexpr uint64_t kBridge = 4096;
+    void Add(uint64_t off, uint64_t len)
+    {
+        if (len == 0) return;
+        if (!iRanges.empty() && off == iRanges.back().hi) { iRanges.back().hi = off + len; return; }
+        if (!iRanges.empty() && off < iRanges.back().hi) iSorted = false;
+        iRanges.push_back(Range{off, off + len});
+    }
+    // Sort and merge what was added; f(lo, hi) for every maximal covered range, g(lo, hi) for every hole <= kBridge
+    // between two of them (which is then bridged: the ranges either side reach f as one).
+    template <class F, class G>
+    void Merge(F f, G g)
+    {
+        if (iRanges.empty()) return;
+        if (!iSorted) std::sort(iRanges.begin(), iRanges.end(), [](const Range& a, const Range& b) { return a.lo < b.lo; });
+        uint64_t lo = iRanges[0].lo, hi = iRanges[0].hi;
+        for (size_t i = 1; i < iRanges.size(); i++) {
+            const Range& r = iRanges[i];
+            if (r.lo <= hi) { hi = r.hi > hi ? r.hi : hi; continue; }
+            if (r.lo - hi <= kBridge) { g(hi, r.lo); hi = r.hi; continue; }
+            f(lo, hi);
+            lo = r.lo; hi = r.hi;
+        }
+        f(lo, hi);
+        iRanges.clear();
+        iSorted = true;
+    }
+private:
+    struct Range { uint64_t lo, hi; };
+    std::vector<Range> iRanges;
+    bool iSorted = true;
+};
+
+class CopyBackPlan
+{
+public:
+    explicit CopyBackPlan(uint8_t* h_out) : iOut(h_out) {}
+    ~CopyBackPlan() { Restore(); }
+    RangeSet& Batch() { return iBatch; }   // every range the whole call covers ...
+    void SaveHoles()                       // ... then, before the first copy is issued
+    {
+        iBatch.Merge([](uint64_t, uint64_t) {},
+                     [this](uint64_t lo, uint64_t hi) {
+                         iHoles.push_back(Hole{lo, (uint32_t)(hi - lo), iSaved.size()});
+                         iSaved.insert(iSaved.end(), iOut + lo, iOut + hi);
+                     });
+    }
+    RangeSet& Slice() { return iSlice; }   // the ranges of one slice ...
+    const std::vector<std::pair<uint64_t, uint64_t>>& Copies() // ... and the [lo, hi) copies that bring them back
+    {
+        iCopies.clear();
+        iSlice.Merge([this](uint64_t lo, uint64_t hi) { iCopies.emplace_back(lo, hi); }, [](uint64_t, uint64_t) {});
+        return iCopies;
+    }
+    void Restore() // only after the copies have completed
+    {
+        for (const Hole& h : iHoles) std::memcpy(iOut + h.off, iSaved.data() + h.at, h.len);
+        iHoles.clear();
+        iSaved.clear();
+    }
+private:
+    struct Hole { uint64_t off; uint32_t len; size_t at; };
+    uint8_t* iOut;
+    RangeSet iBatch, iSlice;
+    std::vector<Hole> iHoles;
+    std::vector<uint8_t> iSaved;
+    std::vector<std::pair<uint64_t, uint64_t>> iCopies;
 };
 
 static int check_desc(const ohp_chunk_desc& d, uint64_t in_bytes, uint64_t out_bytes, DescDerived* derived = nullptr)
@@ -486,7 +584,10 @@ int ohp_destroy(ohp_context* ctx)
 {
     if (!ctx) return OHP_E_INVALID_ARG;
     if (ctx->device >= 0) (void)cudaSetDevice(ctx->device);
-    if (ctx->stream) { (void)cudaStreamSynchronize(ctx->stream); }
+    if (ctx->copy_in) (void)cudaStreamSynchronize(ctx->copy_in);
+    if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_out) (void)cudaStreamSynchronize(ctx->copy_out);
+    (void)cudaGetLastError();
     if (ctx->d_in) (void)cudaFree(ctx->d_in);
     if (ctx->d_out) (void)cudaFree(ctx->d_out);
     if (ctx->d_descs) (void)cudaFree(ctx->d_descs);
@@ -561,9 +662,25 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
     //   copy_in: H2D of the slice's descriptors and of the input span its chunks read
     //   stream : kernel over the slice
     //   copy_out: D2H of the output span its chunks write
-    // The device arenas are full size, so slices never alias; spans are [min offset, max end) over the slice.
-    // Bytes of h_out inside a slice's span that no chunk covers receive unspecified values.
+    // The device arenas are full size, so slices never alias; the input span is [min offset, max end) over the slice,
+    // the output goes back range by range (CopyBackPlan): h_out bytes no chunk covers are left as the caller had them.
     const uint64_t kSliceBytes = 48ull << 20;
+    // declared in this order: on every exit the streams drain first, then the bridged holes are put back
+    CopyBackPlan plan(h_out);
+    const DrainOnExit drain(ctx, ctx->stream);
+    auto add_ranges = [&](RangeSet& set, const ohp_chunk_desc& d) {
+        if (d.out_fmt <= OHP_OUT_PACKED_LE) { set.Add(d.dst_off, d.bytes); return; }
+        DescDerived dv;
+        (void)check_desc(d, in_bytes, out_bytes, &dv);
+        if (d.out_fmt == OHP_OUT_PLANAR32_BE) {
+            // one range per channel plane: the planes are aux frames apart and only dv.frames of each are written
+            for (uint32_t c = 0; c < d.channels; c++) set.Add(d.dst_off + (uint64_t)c * d.aux * 4u, (uint64_t)dv.frames * 4u);
+        } else {
+            set.Add(d.dst_off, dv.out_bytes);
+        }
+    };
+    for (size_t i = 0; i < n; i++) add_ranges(plan.Batch(), h_descs[i]);
+    plan.SaveHoles();
     std::vector<cudaEvent_t>& evs = ctx->slice_events;
     size_t ev_used = 0;
     auto next_event = [&](cudaEvent_t* out_ev) -> cudaError_t {
@@ -579,7 +696,7 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
     const SliceMode slice_mode(ctx); // per-kernel events are only meaningful for a single launch; slices are PCIe-bound
     size_t lo = 0;
     while (lo < n) {
-        uint64_t in_lo = UINT64_MAX, in_hi = 0, out_lo = UINT64_MAX, out_hi = 0, moved = 0;
+        uint64_t in_lo = UINT64_MAX, in_hi = 0, moved = 0;
         size_t hi = lo;
         while (hi < n && (moved < kSliceBytes || hi == lo)) {
             const ohp_chunk_desc& d = h_descs[hi];
@@ -588,11 +705,8 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
                     in_lo = d.src_off < in_lo ? d.src_off : in_lo;
                     in_hi = d.src_off + d.bytes > in_hi ? d.src_off + d.bytes : in_hi;
                 }
-                DescDerived dv;
-                (void)check_desc(d, in_bytes, out_bytes, &dv);
-                out_lo = d.dst_off < out_lo ? d.dst_off : out_lo;
-                out_hi = d.dst_off + dv.out_extent > out_hi ? d.dst_off + dv.out_extent : out_hi;
-                moved += (uint64_t)d.bytes + dv.out_extent;
+                add_ranges(plan.Slice(), d);
+                moved += 2ull * d.bytes;
             }
             hi++;
         }
@@ -609,8 +723,8 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
         if ((rc = launch(ctx, ctx->d_descs + lo, hi - lo, ctx->d_in, in_bytes, ctx->d_out, out_bytes, ctx->stream)) != OHP_OK) return rc;
         OHP_CUDA(ctx, cudaEventRecord(ev_k, ctx->stream));
         OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k, 0));
-        if (out_hi > out_lo) {
-            OHP_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->copy_out));
+        for (const auto& c : plan.Copies()) {
+            OHP_CUDA(ctx, cudaMemcpyAsync(h_out + c.first, ctx->d_out + c.first, c.second - c.first, cudaMemcpyDeviceToHost, ctx->copy_out));
         }
         lo = hi;
     }
@@ -846,10 +960,14 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
         return cudaSuccess;
     };
     const SliceMode slice_mode(ctx);
+    CopyBackPlan plan(h_out); // a stream's chunks tile [dst_base, dst_base + its output bytes): one range per stream
+    const DrainOnExit drain(ctx, st);
+    for (size_t s = 0; s < n_streams; s++) plan.Batch().Add(h_streams[s].dst_base, ctx->h_outb[s]);
+    plan.SaveHoles();
     size_t lo = 0;
     rc = OHP_OK;
     while (lo < n_streams && rc == OHP_OK) {
-        uint64_t in_lo = UINT64_MAX, in_hi = 0, out_lo = UINT64_MAX, out_hi = 0, moved = 0;
+        uint64_t in_lo = UINT64_MAX, in_hi = 0, moved = 0;
         size_t hi = lo;
         while (hi < n_streams && (moved < kSliceBytes || hi == lo)) {
             const ohp_stream_spec& sp = h_streams[hi];
@@ -858,10 +976,7 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
                 in_lo = sp.src_base < in_lo ? sp.src_base : in_lo;
                 in_hi = sp.src_base + in_len > in_hi ? sp.src_base + in_len : in_hi;
             }
-            if (ctx->h_outb[hi]) {
-                out_lo = sp.dst_base < out_lo ? sp.dst_base : out_lo;
-                out_hi = sp.dst_base + ctx->h_outb[hi] > out_hi ? sp.dst_base + ctx->h_outb[hi] : out_hi;
-            }
+            plan.Slice().Add(sp.dst_base, ctx->h_outb[hi]);
             moved += in_len + ctx->h_outb[hi];
             hi++;
         }
@@ -878,8 +993,8 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
         if (rc != OHP_OK) break;
         OHP_CUDA(ctx, cudaEventRecord(ev_k, st));
         OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_k, 0));
-        if (out_hi > out_lo) {
-            OHP_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->copy_out));
+        for (const auto& c : plan.Copies()) {
+            OHP_CUDA(ctx, cudaMemcpyAsync(h_out + c.first, ctx->d_out + c.first, c.second - c.first, cudaMemcpyDeviceToHost, ctx->copy_out));
         }
         lo = hi;
     }

@@ -73,7 +73,7 @@ namespace ohp {
 #define OHP_GROUPS_PER_STEP 1
 #endif
 #ifndef OHP_DEFER_RELEASE
-#define OHP_DEFER_RELEASE 0 /* experiment, not measured yet: a consumer hands its slot back when it takes its next chunk (see the kernel) */
+#define OHP_DEFER_RELEASE 2 /* 0: never, 1: always, 2: serial-placement instantiation only (see the consumer loop) */
 #endif
 #ifndef OHP_DYNAMIC
 #define OHP_DYNAMIC 1       /* 1: consumer warps take chunks by ticket (first come, first served); 0: chunk k -> warp k % warps */
@@ -89,7 +89,7 @@ constexpr int kRecSlots = 64;                      // two batches of 32 decoded 
 constexpr uint32_t kRingSlots = OHP_RING_SLOTS;    // chunks in flight per CTA (barrier pairs); <= 32
 constexpr uint32_t kRingBytes = OHP_RING_BYTES;    // shared-memory byte ring the chunk slots are carved from
 constexpr uint32_t kMaxChunk = OHP_MAX_PCM_CHUNK_BYTES;
-constexpr uint32_t kSlotFront = 16;                // the output image may start up to 15 bytes before the input image
+constexpr uint32_t kSlotFront = 0;                 // (the output image never starts below the input image any more)
 constexpr uint32_t kSlotBack = 80;                 // over-read / over-write of the last 16-subsample group + funnel word
 static_assert(kRingBytes % 16 == 0 && kRingBytes >= 2 * (kSlotFront + kMaxChunk + 16 + kSlotBack), "ring too small");
 static_assert(kRingSlots <= 32, "ring slots: at most one decode batch");
@@ -612,58 +612,54 @@ __device__ __forceinline__ void load_ctx(const ChunkRec& cr, UnitCtx& cx, RampRe
     rr.c = cr.ramp_c; rr.sign = cr.ramp_sign; rr.total = cr.ramp_total; rr.magic = cr.ramp_magic; rr.shift = cr.ramp_shift;
 }
 
-// General path: the chunk starts at any byte of the staged span (in_addr + head); one unit per thread per step,
-// word loads realigned with a funnel shift.
-// In place: the output image starts at out_addr <= the input image (in_addr + head), so a warp step's stores never
-// reach bytes a LATER step still has to read; inside a step every lane loads before any lane stores (__syncwarp).
-template <int B, uint32_t CHM>
-__device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t lane)
+// The image of a chunk lands in its slot at in_addr + head, head = source address & 15 (the bulk load moves whole
+// 16-byte words).  Every lane takes groups of four units (16 subsamples = B x 16 bytes), whatever the head:
+//   ALIGNED (head == 0)  B 128-bit shared-memory loads per group, nothing else;
+//   otherwise            B + 1 of them from the 16-byte boundary below the group, then the group's 4 B words are cut
+//                        out of the 4 B + 4 loaded: a word offset (head / 4: the same for the whole chunk, so a
+//                        warp-uniform switch with compile-time register indices in every arm) and a funnel shift by the
+//                        byte offset (head % 4).
+// The transformed group goes back with B 128-bit stores to in_addr + g * 16 B -- the output image starts ON the 16-byte
+// boundary, up to 15 bytes below the input image.  In place: the stores of group g cover [g * 16 B, (g + 1) * 16 B) of the
+// slot, the loads of a LATER step start at or above that, and inside a step every lane loads before any lane stores
+// (__syncwarp).  Which way the image then leaves the slot is the store's business (store_image_warp).
+template <int B>
+__device__ __forceinline__ void cut_group_words(const uint32_t (&v)[4 * B + 4], uint32_t (&r)[4 * B + 1], uint32_t word_off, uint32_t bit_off)
 {
-    UnitCtx cx;
-    RampRegs rr;
-    rr.table = table;
-    load_ctx(cr, cx, rr);
-    const uint32_t units = cr.units;
-    const uint32_t src = in_addr + (cr.head & ~3u);
-    const uint32_t fshift = (cr.head & 3u) * 8u;
-    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
-        const uint32_t u = u0 + lane;
-        uint32_t raw[B + 1], r[B + 1], w[B];
-        const uint32_t a = src + u * (4u * B);
-        if (u < units) {
+    switch (word_off) {
+    case 0:
 #pragma unroll
-            for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
-        } else {
+        for (int k = 0; k < 4 * B; k++) r[k] = __funnelshift_r(v[k], v[k + 1], bit_off);
+        break;
+    case 1:
 #pragma unroll
-            for (int i = 0; i <= B; i++) raw[i] = 0;
-        }
-        __syncwarp();
+        for (int k = 0; k < 4 * B; k++) r[k] = __funnelshift_r(v[k + 1], v[k + 2], bit_off);
+        break;
+    case 2:
 #pragma unroll
-        for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
-        r[B] = 0;
-        process_unit<B, CHM>(cx, rr, u, r, w);
-        if (u < units) {
-            const uint32_t d = out_addr + u * (4u * B);
+        for (int k = 0; k < 4 * B; k++) r[k] = __funnelshift_r(v[k + 2], v[k + 3], bit_off);
+        break;
+    default:
 #pragma unroll
-            for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
-        }
+        for (int k = 0; k < 4 * B; k++) r[k] = __funnelshift_r(v[k + 3], v[k + 4], bit_off);
+        break;
     }
+    r[4 * B] = 0;
 }
 
-// Fast path: the image starts on a 16-byte boundary and the output goes back to the same bytes.  Each lane takes
-// groups of four units (16 subsamples = B x 16 bytes) with 128-bit shared-memory loads and stores.
-// g_begin..groups: the groups to transform (the whole chunk in the shipped kernel).
-template <int B, uint32_t CHM>
-__device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t,
-                                               uint32_t g_begin, uint32_t groups)
+template <int B, uint32_t CHM, bool ALIGNED>
+__device__ __noinline__ void transform_wide(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t t)
 {
     UnitCtx cx;
     RampRegs rr;
     rr.table = table;
     load_ctx(cr, cx, rr);
+    const uint32_t groups = (cr.units + 3u) >> 2;
+    const uint32_t word_off = cr.head >> 2;
+    const uint32_t bit_off = (cr.head & 3u) * 8u;
     // kGroupsPerStep independent groups per lane per step: one basic block, so their dependency chains interleave
     // (a lone warp per chunk has no other warp to hide LDS / IMAD latency behind)
-    for (uint32_t gb = g_begin; gb < groups; gb += 32u * kGroupsPerStep) { // warp-uniform trip count (the step synchronises the warp)
+    for (uint32_t gb = 0; gb < groups; gb += 32u * kGroupsPerStep) { // warp-uniform trip count (the step synchronises the warp)
         const uint32_t g0 = gb + t;
         uint32_t r[kGroupsPerStep][4 * B + 1];
         uint32_t w[kGroupsPerStep][4 * B];
@@ -671,12 +667,22 @@ __device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t tabl
         for (int s = 0; s < kGroupsPerStep; s++) {
             const uint32_t g = min(g0 + 32u * s, groups - 1u); // clamp: the surplus copy recomputes the last group, unstored
             const uint32_t a = in_addr + g * (16u * B);
+            if constexpr (ALIGNED) {
 #pragma unroll
-            for (int i = 0; i < B; i++) {
-                const uint4 v = lds128(a + 16u * i);
-                r[s][4 * i + 0] = v.x; r[s][4 * i + 1] = v.y; r[s][4 * i + 2] = v.z; r[s][4 * i + 3] = v.w;
+                for (int i = 0; i < B; i++) {
+                    const uint4 v = lds128(a + 16u * i);
+                    r[s][4 * i + 0] = v.x; r[s][4 * i + 1] = v.y; r[s][4 * i + 2] = v.z; r[s][4 * i + 3] = v.w;
+                }
+                r[s][4 * B] = 0;
+            } else {
+                uint32_t v[4 * B + 4];
+#pragma unroll
+                for (int i = 0; i <= B; i++) {
+                    const uint4 q = lds128(a + 16u * i);
+                    v[4 * i + 0] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+                }
+                cut_group_words<B>(v, r[s], word_off, bit_off);
             }
-            r[s][4 * B] = 0;
         }
         __syncwarp(); // (clamped lanes re-read a group another lane is about to overwrite in place)
 #pragma unroll
@@ -696,32 +702,13 @@ __device__ __noinline__ void transform_aligned(const ChunkRec& cr, uint32_t tabl
         for (int s = 0; s < kGroupsPerStep; s++) {
             const uint32_t g = g0 + 32u * s;
             if (g < groups) {
-                const uint32_t d = out_addr + g * (16u * B);
+                const uint32_t d = in_addr + g * (16u * B);
 #pragma unroll
                 for (int i = 0; i < B; i++) {
                     sts128(d + 16u * i, make_uint4(w[s][4 * i + 0], w[s][4 * i + 1], w[s][4 * i + 2], w[s][4 * i + 3]));
                 }
             }
         }
-    }
-}
-
-// Verbatim pass-through (Msg.cpp:2782-2784) when source and destination disagree mod 16: slide the image down from
-// in_addr + head to out_addr (4-byte aligned, <= in_addr + head), whole words realigned with a funnel shift.
-__device__ __noinline__ void shift_chunk(uint32_t in_addr, uint32_t head, uint32_t out_addr, uint32_t bytes, uint32_t lane)
-{
-    const uint32_t words = (bytes + 3u) >> 2;
-    const uint32_t src = in_addr + (head & ~3u);
-    const uint32_t fshift = (head & 3u) * 8u;
-    for (uint32_t w0 = 0; w0 < words; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        uint32_t a = 0, b = 0;
-        if (w < words) {
-            a = lds32(src + 4u * w);
-            b = lds32(src + 4u * w + 4u);
-        }
-        __syncwarp();
-        if (w < words) sts32(out_addr + 4u * w, __funnelshift_r(a, b, fshift));
     }
 }
 
@@ -877,28 +864,58 @@ __device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint
 }
 
 template <int B>
-__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t out_addr, uint32_t t,
-                                                   uint32_t g_begin, uint32_t g_end)
+__device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t t)
 {
     const uint32_t chm = (cr.variant >> 2) & 3u;
-    const bool aligned = (cr.variant & 16u) != 0;
-    if (aligned && chm == kChmStereo) transform_aligned<B, kChmStereo>(cr, table, in_addr, out_addr, t, g_begin, g_end);
-    else if (aligned && chm == kChmMul4) transform_aligned<B, kChmMul4>(cr, table, in_addr, out_addr, t, g_begin, g_end);
-    else if (chm == kChmStereo) transform_any<B, kChmStereo>(cr, table, in_addr, out_addr, t);
-    else if (chm == kChmMul4) transform_any<B, kChmMul4>(cr, table, in_addr, out_addr, t);
-    else if (chm == kChmMono) transform_any<B, kChmMono>(cr, table, in_addr, out_addr, t);
-    else transform_any<B, kChmOther>(cr, table, in_addr, out_addr, t);
+    if (cr.variant & 16u) { // head == 0
+        if (chm == kChmStereo) transform_wide<B, kChmStereo, true>(cr, table, in_addr, t);
+        else if (chm == kChmMul4) transform_wide<B, kChmMul4, true>(cr, table, in_addr, t);
+        else if (chm == kChmMono) transform_wide<B, kChmMono, true>(cr, table, in_addr, t);
+        else transform_wide<B, kChmOther, true>(cr, table, in_addr, t);
+    } else {
+        if (chm == kChmStereo) transform_wide<B, kChmStereo, false>(cr, table, in_addr, t);
+        else if (chm == kChmMul4) transform_wide<B, kChmMul4, false>(cr, table, in_addr, t);
+        else if (chm == kChmMono) transform_wide<B, kChmMono, false>(cr, table, in_addr, t);
+        else transform_wide<B, kChmOther, false>(cr, table, in_addr, t);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// storing a finished image: `bytes` bytes at shared address s_addr -> global dst, by ONE warp.
-// Fast path (s_addr == dst mod 16): head/tail bytes + one TMA bulk store.  Otherwise a register funnel path.
+// storing a finished image: `bytes` bytes at shared address s_addr (ANY byte address) -> global dst, by ONE warp.
+// The <= 15 bytes before the destination's first 16-byte boundary and after its last go out as byte stores.  The
+// interior leaves with ONE TMA bulk store when image and destination agree mod 16; otherwise every lane assembles
+// 16-byte destination words from two 128-bit shared-memory loads (word offset by a warp-uniform switch, byte offset by
+// a funnel shift) and writes them with coalesced 128-bit streaming stores.
 
 __device__ __forceinline__ void store_ragged(uint32_t s_addr, uint8_t* dst, uint32_t from, uint32_t to, uint32_t lane)
 {
     // at most 15 bytes
     const uint32_t i = from + lane;
     if (i < to) dst[i] = (uint8_t)lds8(s_addr + i);
+}
+
+__device__ __forceinline__ uint4 cut_vector(const uint4& a, const uint4& b, uint32_t word_off, uint32_t bit_off)
+{
+    uint4 v;
+    switch (word_off) {
+    case 0:
+        v.x = __funnelshift_r(a.x, a.y, bit_off); v.y = __funnelshift_r(a.y, a.z, bit_off);
+        v.z = __funnelshift_r(a.z, a.w, bit_off); v.w = __funnelshift_r(a.w, b.x, bit_off);
+        break;
+    case 1:
+        v.x = __funnelshift_r(a.y, a.z, bit_off); v.y = __funnelshift_r(a.z, a.w, bit_off);
+        v.z = __funnelshift_r(a.w, b.x, bit_off); v.w = __funnelshift_r(b.x, b.y, bit_off);
+        break;
+    case 2:
+        v.x = __funnelshift_r(a.z, a.w, bit_off); v.y = __funnelshift_r(a.w, b.x, bit_off);
+        v.z = __funnelshift_r(b.x, b.y, bit_off); v.w = __funnelshift_r(b.y, b.z, bit_off);
+        break;
+    default:
+        v.x = __funnelshift_r(a.w, b.x, bit_off); v.y = __funnelshift_r(b.x, b.y, bit_off);
+        v.z = __funnelshift_r(b.y, b.z, bit_off); v.w = __funnelshift_r(b.z, b.w, bit_off);
+        break;
+    }
+    return v;
 }
 
 __device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, uint32_t bytes, uint32_t lane)
@@ -909,25 +926,20 @@ __device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, 
     const uint32_t tail_at = head_n + (words << 4);
     store_ragged(s_addr, dst, 0, head_n, lane);
     store_ragged(s_addr, dst, tail_at, bytes, lane);
-    if (((s_addr + head_n) & 15u) == 0) {
+    const uint32_t base = s_addr + head_n;
+    if ((base & 15u) == 0) {
         if (lane == 0 && words != 0) {
-            tma_store(dst + head_n, s_addr + head_n, words << 4);
+            tma_store(dst + head_n, base, words << 4);
         }
     } else {
-        // destination and image disagree mod 16 (dst not 4-byte aligned): realign through registers
-        const uint32_t base = s_addr + head_n;
-        const uint32_t wbase = base & ~3u;
-        const uint32_t fshift = (base & 3u) * 8u;
+        const uint32_t abase = base & ~15u;
+        const uint32_t word_off = (base & 15u) >> 2;
+        const uint32_t bit_off = (base & 3u) * 8u;
         uint4* d4 = reinterpret_cast<uint4*>(dst + head_n);
         for (uint32_t w = lane; w < words; w += 32) {
-            const uint32_t a = wbase + 16u * w;
-            const uint32_t a0 = lds32(a), a1 = lds32(a + 4), a2 = lds32(a + 8), a3 = lds32(a + 12), a4 = lds32(a + 16);
-            uint4 v;
-            v.x = __funnelshift_r(a0, a1, fshift);
-            v.y = __funnelshift_r(a1, a2, fshift);
-            v.z = __funnelshift_r(a2, a3, fshift);
-            v.w = __funnelshift_r(a3, a4, fshift);
-            stg128_stream(d4 + w, v);
+            const uint4 a = lds128(abase + 16u * w);
+            const uint4 b = lds128(abase + 16u * w + 16u); // at most 16 bytes past the image: inside the slot (kSlotBack)
+            stg128_stream(d4 + w, cut_vector(a, b, word_off, bit_off));
         }
     }
 }

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t decode_chunk(const KernelParams& p, const ui
     r.mode = (ramped ? kModeRamped : 0u) | (in_le ? kModeInLe : 0u) | (out_le ? kModeOutLe : 0u)
            | ((channels == 6) ? kModeTag6 : 0u) | (transform ? kModeTransform : 0u);
     const uint32_t chm = channels == 2 ? kChmStereo : ((channels & 3u) == 0 ? kChmMul4 : (channels == 1 ? kChmMono : kChmOther));
-    const bool aligned = r.head == 0 && (dst & 15u) == 0; // the image starts on a 16-byte boundary and stays where it is
+    const bool aligned = r.head == 0; // the image starts on a 16-byte boundary of its slot
     r.variant = (B - 1u) | (chm << 2) | (aligned ? 16u : 0u);
     make_ramp_const(r, d.ramp_start, d.ramp_end, dv.frames);
     return 0;
@@ -352,10 +352,14 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
         // ------------------------------------------------------------------ consumers: one warp per chunk
         const uint32_t cw = warp - 1;
         const uint32_t table = smem_u32(&sm.table2[0]);
-#if OHP_DEFER_RELEASE
+        // Deferred release: a consumer hands its slot back when it takes its NEXT chunk, so that the bulk store drains
+        // while the ticket is fetched.  OHP_DEFER_RELEASE 0: never, 1: always, 2: in the serial-placement instantiation
+        // only -- measured (profiles/README.md, round 2): with the ring kept nearly full by large uniform chunks
+        // (configs[1], 12 in flight) it is worth +2 %, where the loader places by prefix sum into a ring with room it
+        // costs 0.5-1.7 % (slots come back later and the loader is what sets the pace there).
+        constexpr bool kDefer = OHP_DEFER_RELEASE == 1 || (OHP_DEFER_RELEASE == 2 && SERIAL_PLACE);
         constexpr uint32_t kNoPending = 0xffffffffu;
-        uint32_t pending = kNoPending; // barrier pair of the chunk whose slot this warp has yet to hand back
-#endif
+        [[maybe_unused]] uint32_t pending = kNoPending; // barrier pair of the chunk whose slot this warp has yet to hand back
 #if OHP_DYNAMIC
         for (;;) {
             unsigned long long ticket = 0;
@@ -367,18 +371,17 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
             const uint32_t bs = (uint32_t)(it % kBarPairs);
             const uint32_t ph = (uint32_t)(it / kBarPairs) & 1u;
-#if OHP_DEFER_RELEASE
-            // Experiment (off): the previous chunk's slot is handed back only now, so that its bulk store drains while the
-            // ticket is fetched.  It MUST be handed back before this warp blocks: the loader reclaims in order, and the
-            // chunk waited for may be the one that needs that very slot.
-            if (pending != kNoPending) {
-                const bool ready = __all_sync(0xffffffffu, mbar_test(smem_u32(&sm.full[bs]), ph));
-                if (!ready) {
-                    if (lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
-                    pending = kNoPending;
+            if constexpr (kDefer) {
+                // The previous chunk's slot MUST be handed back before this warp blocks: the loader reclaims in order, and
+                // the chunk waited for may be the one that needs that very slot.
+                if (pending != kNoPending) {
+                    const bool ready = __all_sync(0xffffffffu, mbar_test(smem_u32(&sm.full[bs]), ph));
+                    if (!ready) {
+                        if (lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
+                        pending = kNoPending;
+                    }
                 }
             }
-#endif
 #if OHP_CONSUMER_POLL == 0
             OHP_ACC(w_full, mbar_wait(smem_u32(&sm.full[bs]), ph, p.status));
 #elif OHP_CONSUMER_POLL == 1
@@ -390,12 +393,12 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 __syncwarp();
             }
 #endif
-#if OHP_DEFER_RELEASE
-            if (pending != kNoPending) { // the data was there already: the store had the ticket fetch to drain in
-                if (lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
-                pending = kNoPending;
+            if constexpr (kDefer) {
+                if (pending != kNoPending) { // the data was there already: the store had the ticket fetch to drain in
+                    if (lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
+                    pending = kNoPending;
+                }
             }
-#endif
             const uint32_t sl = (uint32_t)(it & (kRecSlots - 1));
             const ChunkRec& cr = sm.rec[sl];
             const uint32_t kind = cr.kind;
@@ -403,12 +406,11 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 uint8_t* dst = reinterpret_cast<uint8_t*>((uint64_t)cr.dst_lo | ((uint64_t)cr.dst_hi << 32));
                 const uint32_t head = cr.head;
                 const uint32_t in_addr = ring + sm.ring_off[sl] + kSlotFront;          // 16-byte aligned; image at +head
-                // the output image goes where it is congruent to the destination mod 16, at or just below the input
-                const uint32_t image = in_addr + head - ((head - cr.dst_lo) & 15u);
-                const uint32_t out_addr = image & ~3u;                                 // word stores; == image unless dst is odd
+                // where the finished image will start: a transform writes it back from the slot's 16-byte boundary, a
+                // verbatim chunk stays where it landed (the store takes an image at any byte address)
+                uint32_t out_addr = in_addr;
                 const uint32_t fmt = cr.out_fmt;
                 const uint32_t B = (cr.variant & 3u) + 1u;
-                const uint32_t g_begin = 0, g_end = (cr.units + 3u) >> 2, b_begin = 0, b_end = cr.out_bytes;
                 if (kind == kSilenceConv) {
                     silence_to_smem(in_addr, cr.bytes, cr.channels, lane);
                     __syncwarp();
@@ -418,16 +420,14 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
 #endif
                 if (fmt <= OHP_OUT_PACKED_LE) {
                     if (cr.mode & kModeTransform) {
-                        if (g_begin < g_end) {
-                            switch (cr.variant & 3u) {
-                            case 0: transform_dispatch<1>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
-                            case 1: transform_dispatch<2>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
-                            case 2: transform_dispatch<3>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
-                            default: transform_dispatch<4>(cr, table, in_addr, out_addr, lane, g_begin, g_end); break;
-                            }
+                        switch (cr.variant & 3u) {
+                        case 0: transform_dispatch<1>(cr, table, in_addr, lane); break;
+                        case 1: transform_dispatch<2>(cr, table, in_addr, lane); break;
+                        case 2: transform_dispatch<3>(cr, table, in_addr, lane); break;
+                        default: transform_dispatch<4>(cr, table, in_addr, lane); break;
                         }
-                    } else if (out_addr != in_addr + head) {
-                        shift_chunk(in_addr, head, out_addr, cr.bytes, lane);
+                    } else {
+                        out_addr = in_addr + head; // Msg.cpp:2782-2784: the bytes as they are
                     }
                 } else if (fmt == OHP_OUT_PLANAR32_BE) {
                     convert_planar32(cr, table, in_addr, dst, cr.aux * 4u, lane);
@@ -461,10 +461,10 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 w_fence += tx2 - tx1;
 #endif
                 // the finished image sits at out_addr: one TMA bulk store for its 16-byte aligned interior when out_addr is
-                // congruent to dst mod 16, a register funnel otherwise (destination not 4-byte aligned).  The planar sink
-                // has already written global memory itself.
-                if (fmt != OHP_OUT_PLANAR32_BE && b_begin < b_end) {
-                    store_image_warp(out_addr + b_begin, dst + b_begin, b_end - b_begin, lane);
+                // congruent to dst mod 16, 128-bit loads cut to the destination's alignment + streaming stores otherwise.
+                // The planar sink has already written global memory itself.
+                if (fmt != OHP_OUT_PLANAR32_BE && cr.out_bytes != 0) {
+                    store_image_warp(out_addr, dst, cr.out_bytes, lane);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -473,17 +473,15 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                     const long long ts = clock64();
                     w_issue += ts - tx2;
 #endif
-#if !OHP_DEFER_RELEASE
-                    tma_wait_read<0>(); // the slot can be reused once the bulk store has READ it
+                    if constexpr (!kDefer) {
+                        tma_wait_read<0>(); // the slot can be reused once the bulk store has READ it
 #ifdef OHP_PROFILE_WAITS
-                    w_store += clock64() - ts;
+                        w_store += clock64() - ts;
 #endif
-                    mbar_arrive(smem_u32(&sm.empty[bs]));
-#endif
+                        mbar_arrive(smem_u32(&sm.empty[bs]));
+                    }
                 }
-#if OHP_DEFER_RELEASE
-                pending = bs;
-#endif
+                if constexpr (kDefer) pending = bs;
                 __syncwarp();
             } else {
                 if (kind == kSilence) {
@@ -494,9 +492,9 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 if (lane == 0) mbar_arrive(smem_u32(&sm.empty[bs]));
             }
         }
-#if OHP_DEFER_RELEASE
-        if (pending != kNoPending && lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
-#endif
+        if constexpr (kDefer) {
+            if (pending != kNoPending && lane == 0) { tma_wait_read<0>(); mbar_arrive(smem_u32(&sm.empty[pending])); }
+        }
         if (lane == 0) {
             tma_wait_all<0>(); // every bulk store complete before the CTA (and its shared memory) goes away
             if (cw == 0) { OHP_FLUSH(5, w_full); OHP_FLUSH(6, w_store); OHP_FLUSH(9, w_xform); OHP_FLUSH(10, w_fence); OHP_FLUSH(11, w_issue); }

@@ -36,21 +36,23 @@ class BatchPcmReader : public media::IPlayableReader, public media::IInputArena
 public:
     BatchPcmReader(int aDevice, uint64_t aInCapacityBytes, uint64_t aOutCapacityBytes)
         : iCtx(nullptr), iIn(nullptr), iOut(nullptr), iInCapacity(aInCapacityBytes), iOutCapacity(aOutCapacityBytes)
-        , iInUsed(0), iOutUsed(0)
+        , iInUsed(0), iOutUsed(0), iPins(0)
     {
         const int rc = ohp_create(aDevice, &iCtx);
         if (rc != OHP_OK) throw OhpError(rc, std::string("ohp_create: ") + ohp_last_error(nullptr));
-        Check(ohp_host_alloc(iCtx, iInCapacity ? iInCapacity : 16, reinterpret_cast<void**>(&iIn)), "ohp_host_alloc");
-        Check(ohp_host_alloc(iCtx, iOutCapacity ? iOutCapacity : 16, reinterpret_cast<void**>(&iOut)), "ohp_host_alloc");
+        try {
+            Check(ohp_host_alloc(iCtx, iInCapacity ? iInCapacity : 16, reinterpret_cast<void**>(&iIn)), "ohp_host_alloc");
+            Check(ohp_host_alloc(iCtx, iOutCapacity ? iOutCapacity : 16, reinterpret_cast<void**>(&iOut)), "ohp_host_alloc");
+        }
+        catch (...) {
+            Release(); // a constructor that throws runs no destructor
+            throw;
+        }
     }
     ~BatchPcmReader()
     {
         for (auto& q : iQueue) q.playable->RemoveRef();
-        if (iCtx) {
-            if (iIn) ohp_host_free(iCtx, iIn);
-            if (iOut) ohp_host_free(iCtx, iOut);
-            ohp_destroy(iCtx);
-        }
+        Release();
     }
     BatchPcmReader(const BatchPcmReader&) = delete;
     BatchPcmReader& operator=(const BatchPcmReader&) = delete;
@@ -59,13 +61,20 @@ public:
     // (for instance decoded straight into Reserve()d space) is used in place.
     uint64_t Stage(const Brx& aData) override
     {
-        if (aData.Ptr() >= iIn && aData.Ptr() + aData.Bytes() <= iIn + iInCapacity) {
+        // in place only inside what Reserve() has handed out: anything above iInUsed is not part of the batch
+        if (aData.Ptr() >= iIn && aData.Ptr() + aData.Bytes() <= iIn + iInUsed) {
             return (uint64_t)(aData.Ptr() - iIn);
         }
         uint8_t* p = Reserve(aData.Bytes());
         std::memcpy(p, aData.Ptr(), aData.Bytes());
         return (uint64_t)(p - iIn);
     }
+    // IInputArena: one pin per live message that refers to staged bytes (msg_model.h).  The arena is only recycled
+    // while no pin is held, so a message created but not yet Add()ed, a split remainder or a playable the caller kept
+    // across a Flush() still finds its audio where it was staged.
+    void Pin() override { iPins++; }
+    void Unpin() override { OHP_ASSERT(iPins != 0); iPins--; }
+    uint64_t Pins() const { return iPins; }
     // Pinned, 16-byte aligned space inside the input arena for the caller to decode into.
     uint8_t* Reserve(uint32_t aBytes)
     {
@@ -117,8 +126,8 @@ public:
         }
         iQueue.clear();
         iDescs.clear();
-        iInUsed = 0;
         iOutUsed = 0;
+        if (iPins == 0) iInUsed = 0; // nobody refers to the staged audio any more: the space can be handed out again
     }
 
     // IPlayableReader: MsgPlayable::Read() on a single playable (drop-in, synchronous, does not take the reference).
@@ -126,13 +135,17 @@ public:
     {
         OHP_ASSERT(iQueue.empty()); // mixing queued and synchronous reads would reorder deliveries
         aPlayable.AddRef();
-        Add(&aPlayable, aProcessor);
-        const uint64_t keepIn = iInUsed;
-        Flush();
-        iInUsed = keepIn; // the playable's audio stays staged: the caller may Split() and read again
+        try {
+            Add(&aPlayable, aProcessor);
+        }
+        catch (...) {
+            aPlayable.RemoveRef();
+            throw;
+        }
+        Flush(); // the caller's own reference keeps the arena pinned: it may Split() and read again
     }
-    // Forget staged audio (call once the messages that refer to it are gone).
-    void ResetArena() { OHP_ASSERT(iQueue.empty()); iInUsed = 0; }
+    // Forget staged audio; only legal once every message that refers to it is gone.
+    void ResetArena() { OHP_ASSERT(iQueue.empty()); OHP_ASSERT(iPins == 0); iInUsed = 0; }
     ohp_context* Context() { return iCtx; }
 
 private:
@@ -152,12 +165,23 @@ private:
         iQueue.clear();
         iDescs.clear();
         iOutUsed = 0;
+        if (iPins == 0) iInUsed = 0;
+    }
+    void Release()
+    {
+        if (iCtx) {
+            if (iIn) ohp_host_free(iCtx, iIn);
+            if (iOut) ohp_host_free(iCtx, iOut);
+            ohp_destroy(iCtx);
+        }
+        iCtx = nullptr; iIn = iOut = nullptr;
     }
 private:
     ohp_context* iCtx;
     uint8_t* iIn;
     uint8_t* iOut;
     uint64_t iInCapacity, iOutCapacity, iInUsed, iOutUsed;
+    uint64_t iPins; // live messages referring to staged bytes
     std::vector<ohp_chunk_desc> iDescs;
     std::vector<Pending> iQueue;
 };

@@ -129,6 +129,7 @@ MsgAudioPcm* MsgFactory::CreateMsgAudioPcm(uint64_t aArenaOffset, uint32_t aByte
     OHP_ASSERT(subsamples % aChannels == 0);
     const uint32_t jps = Jiffies::PerSample(aSampleRate);
     MsgAudioPcm* msg = Take<MsgAudioPcm>(iFreePcm);
+    PinArena(); // dropped in MsgAudioPcm::Recycle
     msg->Initialise(aSampleRate, aBitDepth, aChannels);
     msg->iSize = (subsamples / aChannels) * jps;
     if (msg->iSize == 0) {
@@ -237,7 +238,11 @@ uint32_t MsgAudio::MedianRampMultiplier()
 // ------------------------------------------------------------------------------------------------
 // MsgAudioPcm
 
-MsgAudio* MsgAudioPcm::Allocate() { return iFactory.Take<MsgAudioPcm>(iFactory.iFreePcm); }
+MsgAudio* MsgAudioPcm::Allocate()
+{
+    iFactory.PinArena(); // the split remainder refers to the same staged bytes
+    return iFactory.Take<MsgAudioPcm>(iFactory.iFreePcm);
+}
 
 void MsgAudioPcm::SplitCompleted(MsgAudio& aRemaining)
 {
@@ -251,6 +256,7 @@ void MsgAudioPcm::SplitCompleted(MsgAudio& aRemaining)
 
 void MsgAudioPcm::Recycle()
 {
+    iFactory.UnpinArena();
     iNextFree = iFactory.iFreePcm;
     iFactory.iFreePcm = this;
 }
@@ -276,6 +282,8 @@ MsgPlayable* MsgAudioPcm::CreatePlayable()
         p->iEndian = iEndian;
         p->iRamp = iRamp;
         p->iAttenuation = iAttenuation;
+        iFactory.PinArena();
+        p->iPinned = true;
     }
     else {
         // muted audio is replaced by silence and its ramp dropped (Msg.cpp:2252-2257)
@@ -362,6 +370,10 @@ MsgPlayable* MsgPlayable::Split(uint32_t aBytes)
     // Reference quirk kept for parity: MsgPlayablePcm::SplitCompleted (Msg.cpp:2803-2807) passes on the audio
     // but not iAttenuation, so the second part plays at unity (what Clear() left in the pooled object).
     rest->iAttenuation = MsgAudioPcm::kUnityAttenuation;
+    if (!iSilence) {
+        iFactory.PinArena();
+        rest->iPinned = true;
+    }
     if (iRamp.IsEnabled()) {
         try {
             rest->iRamp = iRamp.Split(aBytes, iSize);
@@ -406,6 +418,10 @@ void MsgPlayable::Read(IPcmProcessor& aProcessor)
 
 void MsgPlayable::Recycle()
 {
+    if (iPinned) {
+        iPinned = false;
+        iFactory.UnpinArena();
+    }
     iNextFree = iFactory.iFreePlayable;
     iFactory.iFreePlayable = this;
 }

@@ -300,6 +300,7 @@ private:
     AudioDataEndian iEndian;
     media::Ramp iRamp;
     uint32_t iAttenuation;
+    bool iPinned = false;  // holds a pin on the factory's input arena (PCM playables only)
 };
 
 // Hook through which MsgPlayable::Read reaches the GPU (implemented by BatchPcmReader).
@@ -317,6 +318,11 @@ public:
     virtual ~IInputArena() {}
     // Returns the arena offset now holding aData (copied, or located in place if it already lies inside).
     virtual uint64_t Stage(const Brx& aData) = 0;
+    // Every live MsgAudioPcm / PCM MsgPlayable holds one pin on the arena (taken when the message is created or split
+    // off, dropped when it is recycled): the arena must not hand the staged bytes out again while a pin is held --
+    // the counterpart of the reference's ref-counted DecodedAudio cell (Msg.cpp:2260, 2732).
+    virtual void Pin() {}
+    virtual void Unpin() {}
 };
 
 class MsgFactory
@@ -342,6 +348,8 @@ public:
 private:
     template <class T> T* Take(Msg*& aFreeList);
     MsgPlayable* TakePlayable() { return Take<MsgPlayable>(iFreePlayable); }
+    void PinArena() { if (iArena != nullptr) iArena->Pin(); }
+    void UnpinArena() { if (iArena != nullptr) iArena->Unpin(); }
 private:
     IInputArena* iArena;
     IPlayableReader* iReader;

@@ -27,6 +27,9 @@ class NullArena : public IInputArena
 {
 public:
     uint64_t Stage(const Brx& aData) override { const uint64_t at = iUsed; iUsed += (aData.Bytes() + 15u) & ~15u; return at; }
+    void Pin() override { pins++; }
+    void Unpin() override { pins--; }
+    long pins = 0; // live messages that refer to staged audio
 private:
     uint64_t iUsed = 0;
 };
@@ -91,13 +94,35 @@ static void SuiteMsgModel()
     MsgAudio* rest = msg->Split(10 * jps + 100);
     TEST(msg->Jiffies() == 10 * jps + 100);
     TEST(rest->Jiffies() == 54 * jps - 100);
+    TEST(arena.pins == 2);                    // both halves refer to the staged cell (Msg.cpp:2279-2285)
     MsgPlayable* p1 = msg->CreatePlayable();
     MsgPlayable* p2 = rest->CreatePlayable();
+    TEST(arena.pins == 2);                    // the playables took the messages' place (Msg.cpp:2260)
     TEST(p1->Bytes() == 10 * 4);
     TEST(p2->Bytes() == 54 * 4);              // offset rounded down to frame 10, size extended by what the offset lost
     TEST(p2->Descriptor(0, 0).src_off == p1->Descriptor(0, 0).src_off + 40);
     p1->RemoveRef();
+    TEST(arena.pins == 1);
     p2->RemoveRef();
+    TEST(arena.pins == 0);
+    {
+        // muted audio becomes a silence playable that refers to no audio; silence never pins; MsgPlayable::Split pins
+        MsgAudioPcm* m2 = factory.CreateMsgAudioPcm(Brn(data, 256), 2, 44100, 16, AudioDataEndian::Big, 0);
+        m2->SetMuted();
+        MsgPlayable* q = m2->CreatePlayable();
+        TEST(q->IsSilence() && arena.pins == 0);
+        q->RemoveRef();
+        uint32_t sj = 100 * jps;
+        MsgPlayable* sp = factory.CreateMsgSilence(sj, 44100, 16, 2)->CreatePlayable();
+        MsgPlayable* sp2 = sp->Split(40);
+        TEST(arena.pins == 0);
+        sp->RemoveRef(); sp2->RemoveRef();
+        MsgPlayable* a = factory.CreateMsgAudioPcm(Brn(data, 256), 2, 44100, 16, AudioDataEndian::Big, 0)->CreatePlayable();
+        MsgPlayable* b = a->Split(40);
+        TEST(arena.pins == 2);
+        a->RemoveRef(); b->RemoveRef();
+        TEST(arena.pins == 0);
+    }
     // 1-jiffy split -> 0 bytes
     msg = factory.CreateMsgAudioPcm(Brn(data, 256), 2, 44100, 16, AudioDataEndian::Big, 0);
     rest = msg->Split(1);
@@ -247,6 +272,33 @@ static void SuiteGpuRead(const char* aOraclePath)
         TEST(sinks[s].silences == 2);
         TEST(sinks[s].all.size() == expect[s].size());
         TEST(sinks[s].all == expect[s]);
+    }
+    // arena lifetime: audio staged before a Flush() and read after it is still where it was staged; the arena is only
+    // recycled once nothing refers to it
+    {
+        TEST(reader.Pins() == 0);
+        uint8_t a[96], b[96], c[96];
+        std::memset(a, 0x11, sizeof a); std::memset(b, 0x22, sizeof b); std::memset(c, 0x33, sizeof c);
+        MsgAudioPcm* keep = factory.CreateMsgAudioPcm(Brn(a, sizeof a), 2, 48000, 24, AudioDataEndian::Big, 0); // staged, not added yet
+        ProcessorPcmBuf pa, pb, pc;
+        reader.Add(factory.CreateMsgAudioPcm(Brn(b, sizeof b), 2, 48000, 24, AudioDataEndian::Big, 0)->CreatePlayable(), pb);
+        reader.Flush();
+        TEST(reader.Pins() == 1);
+        TEST(pb.Buf() == std::vector<uint8_t>(b, b + sizeof b));
+        reader.Add(factory.CreateMsgAudioPcm(Brn(c, sizeof c), 2, 48000, 24, AudioDataEndian::Big, 0)->CreatePlayable(), pc); // must not land on keep's bytes
+        MsgPlayable* kp = keep->CreatePlayable();
+        MsgPlayable* kp2 = kp->Split(48);
+        reader.Add(kp, pa);
+        reader.Flush();
+        TEST(pc.Buf() == std::vector<uint8_t>(c, c + sizeof c));
+        TEST(pa.Buf() == std::vector<uint8_t>(a, a + 48));
+        TEST(reader.Pins() == 1);             // the split remainder is still out
+        TEST_THROWS(reader.ResetArena(), AssertionFailed);
+        reader.Add(kp2, pa);
+        reader.Flush();
+        TEST(pa.Buf() == std::vector<uint8_t>(a + 48, a + 96));
+        TEST(reader.Pins() == 0);
+        reader.ResetArena();
     }
     // drop-in synchronous MsgPlayable::Read
     {

@@ -52,14 +52,8 @@ def check_workload(ctx, port, w, device=True, host=True):
         assert np.array_equal(got, want), "device path: " + describe_first_diff(got, want, sched.chunks)
     if host:
         got = run_host(ctx, sched.chunks, inp, w.out_bytes)
-        # the host path may clobber uncovered gap bytes inside a slice's span; compare covered bytes only
-        covered = want != 0xA5
-        ob = abi.chunk_out_bytes(sched.chunks)
-        mask = np.zeros(w.out_bytes, dtype=bool)
-        for d, n in zip(sched.chunks, ob):
-            mask[int(d["dst_off"]):int(d["dst_off"]) + int(n)] = True
-        assert np.array_equal(got[mask], want[mask]), "host path differs from oracle"
-        del covered
+        # every byte: what no chunk covers (gaps between streams) must still hold the caller's fill
+        assert np.array_equal(got, want), "host path: " + describe_first_diff(got, want, sched.chunks)
     return sched
 
 
@@ -151,6 +145,47 @@ def test_every_alignment_of_source_and_destination(ctx, port, bits, le):
     want = oracle_out(port, descs, inp, out_bytes)
     got = run_device(ctx, descs, inp, out_bytes)
     assert np.array_equal(got, want), describe_first_diff(got, want, descs)
+
+
+def test_host_paths_leave_uncovered_output_bytes_alone(ctx, port):
+    """ohp_process_host / ohp_run_streams_host copy back what chunks cover and nothing else: holes of every size between
+    chunks and between streams -- inside a slice, across slices, with descriptors in any order -- read afterwards as
+    the caller left them (never as stale device memory)."""
+    rng = np.random.default_rng(5)
+    specs = []
+    for k in range(200):
+        ch = int(rng.integers(1, 5))
+        frames = int(rng.integers(1, 200))
+        specs.append(dict(bytes=frames * ch * 3, bit_depth=24, channels=ch, flags=abi.F_RAMP_ENABLED if k % 2 else 0,
+                          ramp_start=int(rng.integers(0, 16385)), ramp_end=int(rng.integers(0, 16385)),
+                          src_pad=int(rng.integers(0, 3)), dst_pad=int(rng.choice((0, 0, 1, 3, 17, 4095, 4097, 70000)))))
+    descs, in_bytes, out_bytes = pack_chunks(specs)
+    inp = port.fill_pcm(in_bytes, 11)
+    want = oracle_out(port, descs, inp, out_bytes, fill=0x5A)
+    for order in (np.arange(len(descs)), np.arange(len(descs))[::-1], rng.permutation(len(descs))):
+        d = np.ascontiguousarray(descs[order])
+        got = run_host(ctx, d, inp, out_bytes, fill=0x5A)
+        assert np.array_equal(got, want), describe_first_diff(got, want, descs)
+    # several slices (a slice closes after 48 MB moved), streams 100 bytes apart in the output, descriptors backwards
+    w = W.config2(n_streams=8, seconds=6.5)
+    w.streams["dst_base"] += np.arange(8, dtype=np.uint64) * 100
+    out_bytes = w.out_bytes + 800
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    sched = capi.schedule_build(w.streams, w.events)
+    want = oracle_out(port, sched.chunks, inp, out_bytes, fill=0x5A)
+    got = run_host(ctx, np.ascontiguousarray(sched.chunks[::-1]), inp, out_bytes, fill=0x5A)
+    assert np.array_equal(got, want), describe_first_diff(got, want, sched.chunks)
+    # the whole-stage call, streams up to 15 bytes apart and two of them far away
+    w = W.mixed(n_streams=40, seed=21, max_frames=3000)
+    w.streams["dst_base"][20:] += 100000
+    w.streams["dst_base"][30:] += 5000
+    out_bytes = w.out_bytes + 105000
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    sched = capi.schedule_build(w.streams, w.events)
+    want = oracle_out(port, sched.chunks, inp, out_bytes, fill=0x5A)
+    got = np.full(out_bytes, 0x5A, dtype=np.uint8)
+    ctx.run_streams_host(w.streams, w.events, inp, got)
+    assert np.array_equal(got, want), describe_first_diff(got, want, sched.chunks)
 
 
 def test_known_answers_from_the_reference_tests(ctx, port):
@@ -367,10 +402,11 @@ def _compare_whole(ctx, port, descs, inp, out_bytes):
     assert rc == 0, "oracle rejected chunk %d" % (-rc - 1)
     got = run_device(ctx, descs, inp, out_bytes, fill=0)
     assert np.array_equal(got, want), describe_first_diff(got, want, descs)
-    got = np.zeros(out_bytes, dtype=np.uint8)
+    got = np.full(out_bytes, 0x5A, dtype=np.uint8)
     ctx.process_host(descs, inp, got)
-    m = covered_mask(descs, out_bytes)  # ohp_process_host leaves bytes no chunk covers unspecified
+    m = covered_mask(descs, out_bytes)
     assert np.array_equal(got[m], want[m]), "host path differs from the oracle"
+    assert (got[~m] == 0x5A).all(), "ohp_process_host wrote bytes no chunk covers (planar output is strided)"
 
 
 def test_planar32_sink_flywheel_input(ctx, port):
