@@ -60,6 +60,32 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
                          const uint8_t* h_in, uint64_t in_bytes, uint8_t* h_out, uint64_t out_bytes,
                          uint64_t* h_stream_out_bytes, uint64_t* total_chunks);
 
+/*
+ * The same stage for a batch that is already RESIDENT IN HBM: stream specs, ramp events and PCM in device memory in,
+ * every stream's output bytes in device memory out -- both schedule passes and the ramp + convert kernel, enqueued on
+ * `stream` (NULL = the context's own).  The descriptors live in a buffer the context owns and reuses.  The call
+ * returns once everything is enqueued; it blocks the host only for the chunk total the count pass hands back (the
+ * context's descriptor buffer has to be large enough before the second pass starts).  ohp_sync(ctx, stream) waits and
+ * reports device-side errors.
+ *   d_stream_out_bytes (n_streams, device, may be NULL): bytes each stream produced at d_out + dst_base.
+ *   total_chunks (host, may be NULL): playables read.
+ * Errors as ohp_run_streams_host.
+ */
+int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                           const ohp_ramp_event* d_events, size_t n_events,
+                           const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
+                           uint64_t* d_stream_out_bytes, uint64_t* total_chunks, void* stream);
+
+/*
+ * Synthetic PCM for benchmarks and tests, generated in place in HBM: stream s of the batch receives, at d_in +
+ * src_base, total_frames * frame bytes of the splitmix64 sequence seeded with seed_base | (first_stream_id + s)
+ * (8 bytes per step, little-endian).  A stream's bytes depend on its GLOBAL id only, so they are the same wherever the
+ * stream is sharded to and the same the CPU reference arm generates (oracle/: ohpo_fill_pcm with that seed).
+ * Asynchronous on `stream`.
+ */
+int ohp_fill_streams_device(ohp_context* ctx, uint8_t* d_in, uint64_t in_bytes, const ohp_stream_spec* d_streams,
+                            size_t n_streams, uint64_t seed_base, uint64_t first_stream_id, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,13 @@ def cuda_lib():
             L.ohp_run_streams_host.restype = C.c_int
             L.ohp_run_streams_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
                                                C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        if hasattr(L, "ohp_run_streams_device"):
+            L.ohp_run_streams_device.restype = C.c_int
+            L.ohp_run_streams_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
+                                                 C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+            L.ohp_fill_streams_device.restype = C.c_int
+            L.ohp_fill_streams_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64,
+                                                  C.c_void_p]
         L.ohp_set_timing.restype = C.c_int
         L.ohp_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.ohp_last_kernel_ms.restype = C.c_double
@@ -432,6 +439,21 @@ class Context:
                                                  _ptr(inp) if inp.size else None, inp.size, _ptr(out), out.size,
                                                  _ptr(outb) if len(streams) else None, C.byref(total)))
         return outb, int(total.value)
+
+    def run_streams_device(self, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
+                           d_stream_out_bytes=0, stream=None):
+        """ohp_run_streams_device: the whole stage for a batch resident in HBM (raw device addresses); asynchronous on
+        `stream` apart from the chunk total it reads back.  Returns the number of playables."""
+        total = C.c_uint64(0)
+        self._check(self._L.ohp_run_streams_device(self._h, C.c_void_p(d_streams), n_streams, C.c_void_p(d_events), n_events,
+                                                   C.c_void_p(d_in), in_bytes, C.c_void_p(d_out), out_bytes,
+                                                   C.c_void_p(d_stream_out_bytes), C.byref(total), C.c_void_p(stream or 0)))
+        return int(total.value)
+
+    def fill_streams_device(self, d_in, in_bytes, d_streams, n_streams, seed_base, first_stream_id=0, stream=None):
+        """ohp_fill_streams_device: seeded synthetic PCM per stream, generated in HBM."""
+        self._check(self._L.ohp_fill_streams_device(self._h, C.c_void_p(d_in), in_bytes, C.c_void_p(d_streams), n_streams,
+                                                    C.c_uint64(seed_base), C.c_uint64(first_stream_id), C.c_void_p(stream or 0)))
 
     def set_timing(self, enabled):
         self._check(self._L.ohp_set_timing(self._h, int(bool(enabled))))

@@ -1004,6 +1004,49 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
     return read_status(ctx, st);
 }
 
+// The whole stage for a batch resident in HBM (include/ohp_schedule_device.h).
+int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                           const ohp_ramp_event* d_events, size_t n_events,
+                           const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
+                           uint64_t* d_stream_out_bytes, uint64_t* total_chunks, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (total_chunks) *total_chunks = 0;
+    if (n_streams == 0) return OHP_OK;
+    if (!d_streams || !d_out || (!d_in && in_bytes) || (n_events && !d_events)) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int rc;
+    if ((rc = grow(ctx, ctx->d_begin, ctx->d_begin_cap, (uint64_t)(n_streams + 1) * sizeof(uint64_t))) != OHP_OK) return rc;
+    uint64_t total = 0;
+    if ((rc = ohp_schedule_count_device(ctx, d_streams, n_streams, d_events, n_events, ctx->d_begin, d_stream_out_bytes, &total, st)) != OHP_OK) return rc;
+    if (total_chunks) *total_chunks = total;
+    if (total > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) {
+        // the buffer may still be read by a launch enqueued earlier on another stream
+        OHP_CUDA(ctx, cudaDeviceSynchronize());
+        if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, total * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+    }
+    if ((rc = ohp_schedule_emit_device(ctx, d_streams, n_streams, d_events, n_events, ctx->d_begin, ctx->d_descs, nullptr, st)) != OHP_OK) return rc;
+    return launch(ctx, ctx->d_descs, (size_t)total, d_in, in_bytes, d_out, out_bytes, st);
+}
+
+int ohp_fill_streams_device(ohp_context* ctx, uint8_t* d_in, uint64_t in_bytes, const ohp_stream_spec* d_streams,
+                            size_t n_streams, uint64_t seed_base, uint64_t first_stream_id, void* stream)
+{
+    if (!ctx) return OHP_E_INVALID_ARG;
+    if (n_streams == 0) return OHP_OK;
+    if (!d_in || !d_streams) return fail(ctx, OHP_E_INVALID_ARG, "null device pointer");
+    (void)in_bytes; // the caller laid the streams out inside the arena (ohp_run_streams_* checks every stream's span)
+    OHP_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    uint64_t grid = (uint64_t)ctx->sm_count * 8u;
+    if (grid > n_streams) grid = n_streams;
+    fill_streams_kernel<<<(unsigned)grid, 256, 0, st>>>(d_in, d_streams, n_streams, seed_base, first_stream_id);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return OHP_OK;
+}
+
 // Flywheel ramp generator (include/ohp_flywheel.h) ---------------------------------------------------------------
 
 uint32_t ohp_flywheel_out_bytes(const ohp_flywheel_job* job)

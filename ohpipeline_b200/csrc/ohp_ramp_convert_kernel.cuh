@@ -5,6 +5,7 @@
 #pragma once
 
 #include "ohp_kernels.cuh"
+#include "../../include/ohp_schedule.h"
 
 namespace ohp {
 
@@ -543,6 +544,36 @@ __global__ void __launch_bounds__(256) checksum_kernel(const uint8_t* __restrict
             sums[s] = total;
         }
         __syncthreads();
+    }
+}
+
+// Synthetic PCM for benchmarks and tests: stream s's bytes are the splitmix64 sequence (public-domain constants) seeded
+// with seed_base | (first_stream_id + s), eight bytes per step, little-endian -- a function of the stream's global id
+// only, so a stream reads the same wherever it is sharded to, and the CPU reference arm can generate the same bytes.
+// One CTA per stream (grid-stride); a thread writes 16 bytes at a time.
+__global__ void __launch_bounds__(256) fill_streams_kernel(uint8_t* __restrict__ in, const ohp_stream_spec* __restrict__ streams,
+                                                           uint64_t n_streams, uint64_t seed_base, uint64_t first_stream_id)
+{
+    for (uint64_t s = blockIdx.x; s < n_streams; s += gridDim.x) {
+        const ohp_stream_spec sp = streams[s];
+        const uint64_t bytes = sp.total_frames * (uint64_t)(sp.channels * (sp.bit_depth >> 3));
+        uint8_t* dst = in + sp.src_base;
+        const uint64_t seed = seed_base | (first_stream_id + s);
+        auto word = [seed](uint64_t j) -> uint64_t { // the j-th 8-byte step of the sequence
+            uint64_t z = seed + (j + 1u) * 0x9E3779B97F4A7C15ull;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            return z ^ (z >> 31);
+        };
+        const bool vec = (reinterpret_cast<uint64_t>(dst) & 15u) == 0;
+        const uint64_t pairs = vec ? bytes >> 4 : 0;
+        for (uint64_t v = threadIdx.x; v < pairs; v += blockDim.x) {
+            const uint64_t a = word(2 * v), b = word(2 * v + 1);
+            reinterpret_cast<uint4*>(dst)[v] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+        }
+        for (uint64_t i = (pairs << 4) + threadIdx.x; i < bytes; i += blockDim.x) {
+            dst[i] = (uint8_t)(word(i >> 3) >> (8u * (i & 7u)));
+        }
     }
 }
 

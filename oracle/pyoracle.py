@@ -193,6 +193,18 @@ class Port(_Lib):
         self.lib.ohpo_fill_pcm(_ptr(buf), buf.size, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF))
         return buf
 
+    def fill_streams(self, streams, in_bytes, seed_base, first_stream_id=0):
+        """The bytes ohp_fill_streams_device generates: stream s = ohpo_fill_pcm seeded seed_base | (first_stream_id + s)
+        at its src_base.  Bytes between streams are zero."""
+        buf = np.zeros(int(in_bytes), dtype=np.uint8)
+        base = buf.ctypes.data
+        for s in range(len(streams)):
+            sp = streams[s]
+            n = int(sp["total_frames"]) * int(sp["channels"]) * (int(sp["bit_depth"]) // 8)
+            seed = (int(seed_base) | (int(first_stream_id) + s)) & 0xFFFFFFFFFFFFFFFF
+            self.lib.ohpo_fill_pcm(C.c_void_p(base + int(sp["src_base"])), C.c_uint64(n), C.c_uint64(seed))
+        return buf
+
     def unpack_to_be(self, src, bits, little_endian):
         src = np.ascontiguousarray(src, dtype=np.uint8)
         dst = np.empty_like(src)
@@ -284,9 +296,9 @@ class Ref(_Lib):
     def hardware_threads(self):
         return int(self.lib.ref_hardware_threads())
 
-    def run(self, streams, events, inp, out_bytes, threads=1, want_descs=True, want_audio=True):
+    def run(self, streams, events, inp, out_bytes, threads=1, want_descs=True, want_audio=True, want_sizes=False):
         """The real MsgFactory -> SetRamp -> CreatePlayable -> Read(ProcessorPcmBufTest) path.
-        Returns (rc, out, chunks, info)."""
+        Returns (rc, out, chunks, info); with want_sizes (needs want_descs) also each stream's output bytes."""
         streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
         events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
         inp = np.ascontiguousarray(inp, dtype=np.uint8)
@@ -296,8 +308,8 @@ class Ref(_Lib):
                                        _ptr(out) if want_audio else None,
                                        C.byref(res) if want_descs else None, threads)
         if rc != 0:
-            return rc, None, None, None
-        chunks = info = None
+            return (rc, None, None, None, None) if want_sizes else (rc, None, None, None)
+        chunks = info = outb = None
         if want_descs:
-            chunks, info, _, _ = self._collect(res, len(streams), self._free_result)
-        return 0, out, chunks, info
+            chunks, info, _, outb = self._collect(res, len(streams), self._free_result)
+        return (0, out, chunks, info, outb) if want_sizes else (0, out, chunks, info)

@@ -39,3 +39,39 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     assert r.returncode != 0
     assert r.stdout.strip() == ""          # no number without the CUDA path
     assert "no CUDA device" in r.stderr or "no CPU fallback" in r.stderr
+
+
+def test_the_bench_check_agrees_with_the_port_on_a_mixed_batch():
+    """bench.py compares each rank's per-stream checksums with the reference's own code run on a sample of streams fed the
+    per-stream seeded bytes.  Here the C port stands in for the GPU (same arena layout, same fill, same checksum ranges):
+    the sample's checksums must come out the same -- packed little-endian streams included, which the linked reference
+    reads through its big-endian sink."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from ohpipeline_b200 import workloads
+    from oracle import pyoracle
+    port = pyoracle.Port()
+    w = workloads.config4(n_streams=48, seconds=0.05, seed=9)
+    w.key = "config4"
+    first_id = 1000
+    inp = port.fill_streams(w.streams, w.in_bytes, bench.seed_base("config4"), first_id)
+    rc, chunks, _, _, outb = port.schedule_run(w.streams, w.events)
+    assert rc == 0
+    rc, out = port.process_chunks(chunks, inp, w.out_bytes)
+    assert rc == 0
+    offs = np.concatenate([w.streams["dst_base"], [w.out_bytes]]).astype(np.uint64)
+    range_len = offs[1:] - offs[:-1]
+    # what ohp_checksums_device would return for an arena that started zeroed
+    arena = np.zeros(w.out_bytes, dtype=np.uint8)
+    for s in range(len(w.streams)):
+        lo = int(w.streams["dst_base"][s])
+        arena[lo:lo + int(outb[s])] = out[lo:lo + int(outb[s])]
+    gpu_like = np.array([port.checksum(arena[int(offs[s]):int(offs[s + 1])]) for s in range(len(w.streams))], dtype=np.uint64)
+    picks = np.unique(np.linspace(0, len(w.streams) - 1, 20).astype(np.int64))
+    assert (w.streams["out_fmt"][picks] == 1).any(), "sample holds no packed little-endian stream"
+    want, kind, ok_sizes = bench.reference_stream_checksums(w, picks, first_id, outb, range_len, threads=2)
+    assert ok_sizes and np.array_equal(gpu_like[picks], want), kind
+    # a different global stream id is a different stream
+    other, _, _ = bench.reference_stream_checksums(w, picks, first_id + 1, outb, range_len, threads=2)
+    assert not np.array_equal(other, want)

@@ -207,3 +207,77 @@ def test_whole_stage_call_reports_what_the_parts_report(ctx):
     # the context is still usable
     outb, total = ctx.run_streams_host(w.streams, w.events, inp, out)
     assert total == len(capi.schedule_build(w.streams, w.events).chunks)
+
+
+@pytest.mark.parametrize("make", [
+    lambda: workloads.config4(n_streams=80, seconds=0.12, seed=9),
+    lambda: workloads.mixed(n_streams=64, seed=35, max_frames=4000),
+    lambda: workloads.config2(n_streams=24, seconds=0.4),
+], ids=["config4", "mixed", "config2"])
+def test_whole_stage_for_a_batch_resident_in_hbm(ctx, port, make):
+    """ohp_fill_streams_device + ohp_run_streams_device: the per-stream seeded bytes are the ones the oracle's generator
+    gives, and specs + events + PCM in HBM come back as the bytes the oracle computes, every stream's size included.
+    Twice, with a second batch in between: the context reuses its descriptor buffer."""
+    import torch
+    w = make()
+    seed_base, first_id = 9 << 32, 12345
+    d_streams = torch.from_numpy(w.streams.view(np.uint8).copy()).cuda()
+    d_events = (torch.from_numpy(w.events.view(np.uint8).copy()).cuda() if len(w.events)
+                else torch.zeros(32, dtype=torch.uint8, device="cuda"))
+    d_in = torch.zeros(w.in_bytes + 16, dtype=torch.uint8, device="cuda")
+    d_out = torch.full((w.out_bytes + 16,), 0x5A, dtype=torch.uint8, device="cuda")
+    d_outb = torch.zeros(len(w.streams), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.fill_streams_device(d_in.data_ptr(), w.in_bytes, d_streams.data_ptr(), len(w.streams), seed_base, first_id)
+    ctx.sync()
+    inp = port.fill_streams(w.streams, w.in_bytes, seed_base, first_id)
+    assert np.array_equal(d_in.cpu().numpy()[:w.in_bytes], inp), "the GPU and the CPU arm would not see the same PCM"
+    rc, want, chunks, _ = port.run(w.streams, w.events, inp, w.out_bytes)
+    assert rc == 0
+    host = capi.schedule_build(w.streams, w.events)
+    mask = covered_mask(chunks, w.out_bytes)
+    for round_ in range(2):
+        total = ctx.run_streams_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events),
+                                       d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes, d_outb.data_ptr())
+        ctx.sync()
+        assert total == len(chunks)
+        assert np.array_equal(d_outb.cpu().numpy().view(np.uint64), host.stream_out_bytes)
+        got = d_out.cpu().numpy()[:w.out_bytes]
+        assert np.array_equal(got[mask], want[mask])
+        assert (got[~mask] == 0x5A).all(), "bytes no chunk covers were written"
+        if round_ == 0:
+            other = workloads.config5(n_streams=300, seconds=0.05)   # more chunks: the descriptor buffer has to grow
+            o_in = torch.zeros(other.in_bytes + 16, dtype=torch.uint8, device="cuda")
+            o_out = torch.zeros(other.out_bytes + 16, dtype=torch.uint8, device="cuda")
+            o_s = torch.from_numpy(other.streams.view(np.uint8).copy()).cuda()
+            o_e = torch.from_numpy(other.events.view(np.uint8).copy()).cuda()
+            torch.cuda.synchronize()
+            n_other = ctx.run_streams_device(o_s.data_ptr(), len(other.streams), o_e.data_ptr(), len(other.events),
+                                             o_in.data_ptr(), other.in_bytes, o_out.data_ptr(), other.out_bytes)
+            ctx.sync()
+            assert n_other == len(capi.schedule_build(other.streams, other.events).chunks)
+            d_out.fill_(0x5A)
+            torch.cuda.synchronize()
+
+
+def test_whole_stage_device_call_reports_errors(ctx):
+    import torch
+    w = workloads.config5(n_streams=4, seconds=0.02)
+    bad = w.streams.copy()
+    bad["sample_rate"][1] = 12345
+    d_in = torch.zeros(w.in_bytes + 16, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(w.out_bytes + 16, dtype=torch.uint8, device="cuda")
+    d_e = torch.from_numpy(w.events.view(np.uint8).copy()).cuda()
+    d_bad = torch.from_numpy(bad.view(np.uint8).copy()).cuda()
+    d_ok = torch.from_numpy(w.streams.view(np.uint8).copy()).cuda()
+    torch.cuda.synchronize()
+    with pytest.raises(capi.OhpError) as e:
+        ctx.run_streams_device(d_bad.data_ptr(), 4, d_e.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes)
+    assert e.value.status == abi.E_INVALID_ARG and "stream 1" in str(e.value)
+    # a stream reaching outside the output arena is caught chunk by chunk on the device and reported by the sync
+    ctx.run_streams_device(d_ok.data_ptr(), 4, d_e.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes // 2)
+    with pytest.raises(capi.OhpError) as e:
+        ctx.sync()
+    assert e.value.status == abi.E_OUT_OF_RANGE
+    assert ctx.run_streams_device(d_ok.data_ptr(), 4, d_e.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes) > 0
+    ctx.sync()
