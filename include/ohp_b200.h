@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define OHP_ABI_VERSION 1u
+#define OHP_ABI_VERSION 2u
 
 /* Ramp::kMax / Ramp::kMin (Msg.h:257-258) */
 #define OHP_RAMP_MAX 16384u
@@ -58,6 +58,9 @@ typedef enum ohp_status {
     OHP_E_NO_MEMORY = 6
 } ohp_status;
 
+/* ohp_chunk_desc::aux for OHP_OUT_PACKED_LE */
+#define OHP_LE_APPEND 1u
+
 /* chunk flags */
 #define OHP_F_RAMP_ENABLED     0x01u /* Ramp::IsEnabled() (selects the lossy 16-bit path, Msg.cpp:2761) */
 #define OHP_F_SILENCE          0x02u /* MsgPlayableSilence: zeros, ramp ignored (Msg.cpp:2874-2893)      */
@@ -67,7 +70,11 @@ typedef enum ohp_status {
 typedef enum ohp_out_fmt {
     OHP_OUT_PACKED_BE = 0,   /* ProcessorPcmBufTest: verbatim packed big-endian (ProcessorAudioUtils.cpp:31-52)            */
     OHP_OUT_PACKED_LE = 1,   /* ProcessorPcmSwpEndianPacked: per-subsample byte swap, 8/16/24 only
-                                (Tests/TestCodecInteractiveMain.cpp:546-590); fragments are appended                       */
+                                (Tests/TestCodecInteractiveMain.cpp:546-590).  aux = 0: what that sink HOLDS after the read,
+                                to the letter -- its SwapEndianness16/24 overwrite where ProcessorPcmBufTest appends, so of a
+                                ramped 16/24-bit playable (read in fragments of <= 256 bytes, Msg.cpp:2761-2780) only the last
+                                fragment is left, and that is all the chunk writes; aux = OHP_LE_APPEND: every fragment, in
+                                order (what the stream-level calls and MsgPlayable::Descriptor use)                        */
     OHP_OUT_PLANAR32_BE = 2, /* FlywheelInput: planar, 4 bytes/subsample, left-justified BE (StarvationRamper.cpp:117-186);
                                 aux = frames per channel plane                                                             */
     OHP_OUT_FROM32_BE = 3,   /* RampGenerator: 32-bit BE in -> packed aux-bit BE out (StarvationRamper.cpp:281-326)        */

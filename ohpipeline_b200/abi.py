@@ -5,7 +5,7 @@ headers exactly -- tests/test_abi.py checks sizeof/offsetof against the built li
 """
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RAMP_MAX = 16384          # Ramp::kMax, OpenHome/Media/Pipeline/Msg.h:257
 RAMP_MIN = 0
@@ -29,6 +29,7 @@ OUT_PACKED_LE = 1
 OUT_PLANAR32_BE = 2
 OUT_FROM32_BE = 3
 OUT_SONGCAST = 4
+LE_APPEND = 1  # aux of OUT_PACKED_LE: every fragment (0: what the reference's sink holds after the read)
 
 # Ramp::EDirection
 DIR_NONE, DIR_UP, DIR_DOWN, DIR_MUTE = range(4)
@@ -104,6 +105,12 @@ def chunk_out_bytes(descs: np.ndarray) -> np.ndarray:
     frames = nbytes // np.maximum(b * ch, 1)
     out = nbytes.copy()
     fmt = descs["out_fmt"]
+    # ProcessorPcmSwpEndianPacked to the letter (aux 0): of a ramped 16/24-bit playable only the last <= 256-byte fragment
+    fb = np.maximum(b * ch, 1)
+    spf = np.maximum(256 // fb, 1)
+    last = (frames - (np.maximum(frames, 1) - 1) // spf * spf) * fb
+    ramped = (descs["flags"] & F_RAMP_ENABLED) != 0
+    out = np.where((fmt == OUT_PACKED_LE) & (descs["aux"] == 0) & ramped & (b >= 2) & (frames > 0), last, out)
     out = np.where(fmt == OUT_PLANAR32_BE, frames * ch * 4, out)
     out = np.where(fmt == OUT_FROM32_BE, (nbytes // 4) * (descs["aux"].astype(np.uint64) // 8), out)
     out = np.where(fmt == OUT_SONGCAST, frames * np.minimum(ch, 2) * np.minimum(b, 3), out)

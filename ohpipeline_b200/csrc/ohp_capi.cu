@@ -669,7 +669,7 @@ int ohp_process_host(ohp_context* ctx, const ohp_chunk_desc* h_descs, size_t n, 
     CopyBackPlan plan(h_out);
     const DrainOnExit drain(ctx, ctx->stream);
     auto add_ranges = [&](RangeSet& set, const ohp_chunk_desc& d) {
-        if (d.out_fmt <= OHP_OUT_PACKED_LE) { set.Add(d.dst_off, d.bytes); return; }
+        if (d.out_fmt == OHP_OUT_PACKED_BE) { set.Add(d.dst_off, d.bytes); return; }
         DescDerived dv;
         (void)check_desc(d, in_bytes, out_bytes, &dv);
         if (d.out_fmt == OHP_OUT_PLANAR32_BE) {

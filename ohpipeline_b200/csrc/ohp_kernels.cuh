@@ -167,7 +167,15 @@ __host__ __device__ inline uint32_t check_desc_fields(const DescFields& d, uint6
     case OHP_OUT_PACKED_BE:
         break;
     case OHP_OUT_PACKED_LE:                                                   // TestCodecInteractiveMain.cpp:546-567
-        if (silence || B > 3) return 1u;
+        if (silence || B > 3 || d.aux > OHP_LE_APPEND) return 1u;
+        if (d.aux != OHP_LE_APPEND && (d.flags & OHP_F_RAMP_ENABLED) && B >= 2 && frames != 0) {
+            // SwapEndianness16/24 overwrite (TestCodecInteractiveMain.cpp:570-590): the sink is left holding the last of the
+            // fragments MsgPlayablePcm::ReadBlock made, 256 / frame bytes frames each (Msg.cpp:2765-2779)
+            const uint32_t per_fragment = 256u / frame_bytes;
+            const uint32_t last = frames - ((frames - 1u) / per_fragment) * per_fragment;
+            o.out_bytes = last * frame_bytes;
+            o.out_extent = o.out_bytes;
+        }
         break;
     case OHP_OUT_PLANAR32_BE:                                                 // StarvationRamper.cpp:90-111
         if (d.aux < frames) return 1u;
@@ -226,6 +234,7 @@ static_assert(sizeof(ChunkRec) == 80, "ChunkRec is 80 bytes (16-byte multiple)")
 constexpr uint32_t kModeRamped = 1u, kModeInLe = 2u, kModeOutLe = 4u, kModeTag6 = 8u, kModeTransform = 16u;
 // how the four subsamples of a unit map to frames
 constexpr uint32_t kChmOther = 0u, kChmMono = 1u, kChmStereo = 2u, kChmMul4 = 3u;
+constexpr uint32_t kChmAny = 4u; // decided at run time (mono or the general two-frame case): ONE instantiation for every channel count
 
 struct __align__(128) SharedStorage
 {
@@ -550,7 +559,7 @@ __device__ __forceinline__ void process_unit(const UnitCtx& cx, const RampRegs& 
     if (cx.ramped) {
         uint32_t m[4];
         uint32_t chan0 = 0;
-        if (CHM == kChmMono) {
+        if (CHM == kChmMono || (CHM == kChmAny && cx.channels == 1u)) {
 #pragma unroll
             for (int j = 0; j < 4; j++) m[j] = ramp_mult2(rr, 4u * u + j);
         } else if (CHM == kChmStereo) {
@@ -561,7 +570,7 @@ __device__ __forceinline__ void process_unit(const UnitCtx& cx, const RampRegs& 
             chan0 = 4u * u - f0 * cx.channels;
             m[0] = m[1] = m[2] = m[3] = ramp_mult2(rr, f0);
         } else {
-            // channels >= 3, not a multiple of 4: the unit touches frame f0 and possibly f0+1
+            // two channels or more: the unit touches frame f0 and possibly f0+1
             const uint32_t f0 = __umulhi(4u * u, cx.ch_magic);
             chan0 = 4u * u - f0 * cx.channels;
             const uint32_t ma = ramp_mult2(rr, f0);
@@ -581,7 +590,7 @@ __device__ __forceinline__ void process_unit(const UnitCtx& cx, const RampRegs& 
             if (B == 4) {
                 // bytes: hi, lo, 00, channel tag on 6-channel audio (Msg.cpp:880-891)
                 uint32_t c = chan0 + j;
-                if (CHM == kChmOther) c = (c >= cx.channels) ? c - cx.channels : c;
+                if (CHM == kChmOther || CHM == kChmAny) c = (c >= cx.channels) ? c - cx.channels : c;
                 v = (v & 0xffff0000u) | (cx.tag6 ? (c << 4) : 0u);
             }
             o[j] = v;
@@ -863,21 +872,20 @@ __device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint
     }
 }
 
+// Few, fat instantiations on purpose.  A batch of mixed formats has every one of them hot at the same time (16 consumer
+// warps per SM, each in whatever its chunk needs), and the SM's instruction caches hold only so much: with one instantiation
+// per (depth, channel layout, alignment) -- 32 functions, 143 KB of SASS -- the mixed-format BASELINE config ran at 0.53 of the
+// copy peak, instruction fetch bound (profiles/README.md, round 2).  So: the two layouts the uniform configs are made of
+// (stereo, channel counts that are multiples of four) keep their lean aligned instantiation; everything else -- any other
+// channel count, any chunk that does not start on a 16-byte boundary -- shares ONE instantiation per depth.
 template <int B>
 __device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t t)
 {
     const uint32_t chm = (cr.variant >> 2) & 3u;
-    if (cr.variant & 16u) { // head == 0
-        if (chm == kChmStereo) transform_wide<B, kChmStereo, true>(cr, table, in_addr, t);
-        else if (chm == kChmMul4) transform_wide<B, kChmMul4, true>(cr, table, in_addr, t);
-        else if (chm == kChmMono) transform_wide<B, kChmMono, true>(cr, table, in_addr, t);
-        else transform_wide<B, kChmOther, true>(cr, table, in_addr, t);
-    } else {
-        if (chm == kChmStereo) transform_wide<B, kChmStereo, false>(cr, table, in_addr, t);
-        else if (chm == kChmMul4) transform_wide<B, kChmMul4, false>(cr, table, in_addr, t);
-        else if (chm == kChmMono) transform_wide<B, kChmMono, false>(cr, table, in_addr, t);
-        else transform_wide<B, kChmOther, false>(cr, table, in_addr, t);
-    }
+    const bool aligned = (cr.variant & 16u) != 0; // head == 0
+    if (aligned && chm == kChmStereo) transform_wide<B, kChmStereo, true>(cr, table, in_addr, t);
+    else if (aligned && chm == kChmMul4) transform_wide<B, kChmMul4, true>(cr, table, in_addr, t);
+    else transform_wide<B, kChmAny, false>(cr, table, in_addr, t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -932,6 +940,10 @@ __device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, 
             tma_store(dst + head_n, base, words << 4);
         }
     } else {
+#ifdef OHP_EXPERIMENT_TMA_ANYWAY /* TIMING EXPERIMENT ONLY (wrong bytes): what would the cut-to-alignment path cost if it were one bulk store? */
+        if (lane == 0 && words != 0) tma_store(dst + head_n, base & ~15u, words << 4);
+        return;
+#endif
         const uint32_t abase = base & ~15u;
         const uint32_t word_off = (base & 15u) >> 2;
         const uint32_t bit_off = (base & 3u) * 8u;

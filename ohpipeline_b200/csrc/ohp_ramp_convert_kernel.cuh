@@ -465,7 +465,9 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
                 // congruent to dst mod 16, 128-bit loads cut to the destination's alignment + streaming stores otherwise.
                 // The planar sink has already written global memory itself.
                 if (fmt != OHP_OUT_PLANAR32_BE && cr.out_bytes != 0) {
-                    store_image_warp(out_addr, dst, cr.out_bytes, lane);
+                    // (the packed little-endian sink to the letter keeps the tail of a ramped image only)
+                    const uint32_t skip = fmt == OHP_OUT_PACKED_LE ? cr.bytes - cr.out_bytes : 0u;
+                    store_image_warp(out_addr + skip, dst, cr.out_bytes, lane);
                 }
                 __syncwarp();
                 if (lane == 0) {

@@ -90,14 +90,15 @@ int ParseWav(Reader& r, uint32_t aMaxBitDepth, ohp_container_info& o)
 // CodecAiffBase::DetermineRate (AiffBase.cpp:149-186): the 80-bit extended field's exponent and top 32 mantissa bits
 uint32_t DetermineRate(uint32_t aExponent, uint32_t aMantissa)
 {
+    // The reference shifts a 32-bit value by whatever the exponent gives, 32 and more included -- undefined in C++, and on
+    // the x86 and ARM64 targets it is built for the hardware takes the count modulo 32.  A damaged exponent therefore still
+    // yields a rate there (0x020e reads like 0x400e); the same here, so that both accept and refuse the same headers.
     uint32_t rate;
     if (aExponent < 0x4013) { // kUnder65kHz (AiffBase.h:38 -- despite its name the switch-over is at 2^20 Hz)
-        const uint32_t sh = 0x401e - aExponent;
-        rate = sh < 32 ? aMantissa >> sh : 0;
+        rate = aMantissa >> ((0x401eu - aExponent) & 31u);
     }
     else {
-        const uint32_t sh = aExponent - 0x4007;
-        rate = sh < 32 ? aMantissa >> sh : 0;
+        rate = aMantissa >> ((aExponent - 0x4007u) & 31u);
     }
     if (rate == 22255) rate = 22050;      // old Macintosh rates
     else if (rate == 11127) rate = 11025;

@@ -406,7 +406,7 @@ ohp_chunk_desc MsgPlayable::Descriptor(uint64_t aDstOffset, uint32_t aOutFmt) co
     d.flags = (uint8_t)((iRamp.IsEnabled() ? OHP_F_RAMP_ENABLED : 0u) | (iSilence ? OHP_F_SILENCE : 0u)
                         | ((!iSilence && iEndian == AudioDataEndian::Little) ? OHP_F_IN_LITTLE_ENDIAN : 0u));
     d.out_fmt = (uint8_t)aOutFmt;
-    d.aux = 0;
+    d.aux = aOutFmt == OHP_OUT_PACKED_LE ? OHP_LE_APPEND : 0; // a reader hands each playable's fragments on in order
     return d;
 }
 

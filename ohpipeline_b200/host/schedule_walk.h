@@ -247,7 +247,7 @@ OHP_HD void emit_desc(const StreamCtx& cx, const Playable& p, uint64_t aIndex, u
     const uint32_t w4 = p.size;
     const uint32_t w5 = (p.ramp.start & 0xffffu) | (p.ramp.end << 16);
     const uint32_t w6 = (p.atten & 0xffffu) | (cx.bits << 16) | (cx.channels << 24);
-    const uint32_t w7 = flags | (cx.out_fmt << 8);
+    const uint32_t w7 = flags | (cx.out_fmt << 8) | (cx.out_fmt == OHP_OUT_PACKED_LE ? OHP_LE_APPEND << 16 : 0u); // aux: as MsgPlayable::Descriptor
 #if defined(__CUDA_ARCH__)
     uint4* out = reinterpret_cast<uint4*>(cx.descs + aIndex);
     out[0] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)dst, (uint32_t)(dst >> 32));

@@ -298,8 +298,15 @@ uint32_t ohpo_chunk_out_bytes(const ohp_chunk_desc* d)
     if (b == 0 || d->channels == 0) return 0;
     const uint32_t frames = d->bytes / (b * d->channels);
     switch (d->out_fmt) {
-    case OHP_OUT_PACKED_BE:
-    case OHP_OUT_PACKED_LE: return d->bytes;
+    case OHP_OUT_PACKED_BE: return d->bytes;
+    case OHP_OUT_PACKED_LE:
+        if (d->aux != OHP_LE_APPEND && (d->flags & OHP_F_RAMP_ENABLED) && b >= 2 && frames != 0) {
+            /* SwapEndianness16/24 set the sink's size to the fragment's (TestCodecInteractiveMain.cpp:570-590): after the
+             * read it holds the LAST of the fragments ReadBlock made, 256 / frame bytes frames each (Msg.cpp:2765-2779) */
+            const uint32_t per_fragment = 256u / (b * d->channels);
+            return (frames - ((frames - 1u) / per_fragment) * per_fragment) * b * d->channels;
+        }
+        return d->bytes;
     case OHP_OUT_PLANAR32_BE: return frames * d->channels * 4u;
     case OHP_OUT_FROM32_BE: return (d->bytes / 4u) * (d->aux / 8u);
     case OHP_OUT_SONGCAST: return frames * (d->channels < 2 ? d->channels : 2u) * (b < 3 ? b : 3u);
@@ -322,6 +329,13 @@ static int sink_write(const ohp_chunk_desc* d, const uint8_t* be, uint32_t n, in
     case OHP_OUT_PACKED_LE:
         /* ProcessorPcmSwpEndianPacked, TestCodecInteractiveMain.cpp:546-590 (32-bit and silence ASSERT) */
         if (silence) return -1;
+        if (d->aux > OHP_LE_APPEND) return -1;
+        {
+            /* aux 0: only what the sink is left holding (see ohpo_chunk_out_bytes) */
+            const uint32_t keep = ohpo_chunk_out_bytes(d);
+            be += n - keep;
+            n = keep;
+        }
         if (b == 1) { memcpy(out, be, n); return 0; }
         if (b == 2) { for (uint32_t i = 0; i < n; i += 2) { out[i] = be[i + 1]; out[i + 1] = be[i]; } return 0; }
         if (b == 3) { for (uint32_t i = 0; i < n; i += 3) { out[i] = be[i + 2]; out[i + 1] = be[i + 1]; out[i + 2] = be[i]; } return 0; }
@@ -666,7 +680,7 @@ static void emit(run* r, const playable* p)
     d->flags = (uint8_t)((p->ramp.enabled ? OHP_F_RAMP_ENABLED : 0) | (p->kind == MSG_SILENCE ? OHP_F_SILENCE : 0) |
                          ((sp->in_little_endian && p->kind == MSG_PCM) ? OHP_F_IN_LITTLE_ENDIAN : 0));
     d->out_fmt = (uint8_t)sp->out_fmt;
-    d->aux = 0;
+    d->aux = sp->out_fmt == OHP_OUT_PACKED_LE ? OHP_LE_APPEND : 0;
     ci->direction = p->ramp.direction;
     ci->jiffies = p->jiffies;
     r->out_bytes += p->size;

@@ -286,6 +286,33 @@ class Ref(_Lib):
         n = f(rate, channels, bits, _ptr(frames), len(frames), _ptr(out), len(out))
         return None if n < 0 else out[:n].copy()
 
+    def process_chunks_sinks(self, descs, inp, out_bytes, fill=0):
+        """MsgPlayable::Read of every descriptor through the REAL sink its out_fmt names (ProcessorPcmBufTest, the extracted
+        ProcessorPcmSwpEndianPacked, the extracted Songcast Sender).  Returns (rc, out, bytes each chunk's sink was left holding)."""
+        descs = np.ascontiguousarray(descs, dtype=abi.CHUNK_DESC)
+        inp = np.ascontiguousarray(inp, dtype=np.uint8)
+        out = np.full(int(out_bytes), fill, dtype=np.uint8)
+        sizes = np.zeros(len(descs), dtype=np.uint32)
+        f = self.lib.ref_process_chunks_sinks
+        f.restype = C.c_int64
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        rc = f(_ptr(descs), len(descs), _ptr(inp), inp.size, _ptr(out), out.size, _ptr(sizes))
+        return int(rc), out, sizes
+
+    def container_decode(self, data, max_bit_depth=32):
+        """The reference's own CodecWav / CodecAifc / CodecAiff on the container bytes, behind a fake CodecController.
+        Returns (ohp_container_status, CONTAINER_INFO record, OutputAudioPcm byte counts (AIFF / AIFC only))."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        info = np.zeros(1, dtype=abi.CONTAINER_INFO)
+        cap = max(16, len(buf) // 64 + 16)
+        reads = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32(0)
+        f = self.lib.ref_container_decode
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        rc = f(_ptr(buf) if buf.size else None, buf.size, max_bit_depth, _ptr(info), _ptr(reads), cap, C.byref(n))
+        return int(rc), info[0], reads[:min(n.value, cap)].copy()
+
     def _free_result(self, res_ref):
         res = res_ref._obj
         self._libc_free(res.chunks)

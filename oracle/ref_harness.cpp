@@ -133,6 +133,7 @@ public:
             d.bit_depth = (uint8_t)iSpec.bit_depth;
             d.channels = (uint8_t)iSpec.channels;
             d.out_fmt = (uint8_t)iSpec.out_fmt;
+            d.aux = iSpec.out_fmt == OHP_OUT_PACKED_LE ? OHP_LE_APPEND : 0;
             d.flags = p->Ramp().IsEnabled() ? OHP_F_RAMP_ENABLED : 0;
             if (pcm != nullptr) {
                 d.src_off = iSpec.src_base + iFactory.cellSrc[pcm->iAudioData] + pcm->iOffset;

@@ -72,6 +72,29 @@ inline const Brx& Brx::Empty()
     return kEmpty;
 }
 
+// heap-allocated, read-only once set (MimeTypeList.h holds one)
+class Brh : public Brx
+{
+public:
+    Brh() : Brx(0), iPtr(nullptr) {}
+    explicit Brh(const Brx& aBrx) : Brx(0), iPtr(nullptr) { Set(aBrx); }
+    explicit Brh(const TChar* aStr) : Brx(0), iPtr(nullptr) { Set(Brn(aStr)); }
+    ~Brh() override { std::free(iPtr); }
+    void Set(const Brx& aBrx)
+    {
+        std::free(iPtr);
+        iPtr = (TByte*)std::malloc(aBrx.Bytes() ? aBrx.Bytes() : 1);
+        if (aBrx.Bytes() > 0) std::memcpy(iPtr, aBrx.Ptr(), aBrx.Bytes());
+        iBytes = aBrx.Bytes();
+    }
+    void Set(const TChar* aStr) { Set(Brn(aStr)); }
+    const TByte* Ptr() const override { return iPtr; }
+private:
+    Brh(const Brh&);
+    Brh& operator=(const Brh&);
+    TByte* iPtr;
+};
+
 class Bwx : public Brx
 {
 public:

@@ -22,9 +22,10 @@ public:
 #define kApplication5 5
 #define kApplication6 6
 #define kApplication34 34
-#define LOG(x, ...) do { } while (0)
-#define LOG_DEBUG(x, ...) do { } while (0)
-#define LOG_INFO(x, ...) do { } while (0)
-#define LOG_WARNING(x, ...) do { } while (0)
-#define LOG_ERROR(x, ...) do { OpenHome::Log::Print(__VA_ARGS__); } while (0)
-#define LOG_TRACE(x, ...) do { } while (0)
+// plain brace blocks, as in ohNet: some call sites in the reference carry no trailing semicolon (CodecController.cpp:421)
+#define LOG(x, ...) { }
+#define LOG_DEBUG(x, ...) { }
+#define LOG_INFO(x, ...) { }
+#define LOG_WARNING(x, ...) { }
+#define LOG_ERROR(x, ...) { OpenHome::Log::Print(__VA_ARGS__); }
+#define LOG_TRACE(x, ...) { }

@@ -28,7 +28,8 @@ def test_cuda_library_exports_every_declared_symbol():
 def test_cuda_library_exports_the_device_schedule_builder():
     lib = capi.cuda_lib()
     names = declared_functions("ohp_schedule_device.h")
-    assert names == ["ohp_run_streams_host", "ohp_schedule_count_device", "ohp_schedule_emit_device"]
+    assert names == ["ohp_fill_streams_device", "ohp_run_streams_device", "ohp_run_streams_host", "ohp_schedule_count_device",
+                     "ohp_schedule_emit_device"]
     for n in names:
         assert hasattr(lib, n), n
 

@@ -287,7 +287,8 @@ def test_empty_batch_and_zero_byte_chunks(ctx, port):
 
 
 def test_packed_le_output_is_byte_swapped_be_output(ctx, port):
-    """P2 (ProcessorPcmSwpEndianPacked) == per-subsample byte reversal of P1, for 8/16/24-bit."""
+    """P2 (ProcessorPcmSwpEndianPacked) with every fragment kept (aux = OHP_LE_APPEND) == per-subsample byte reversal of P1,
+    for 8/16/24-bit."""
     for bits in (8, 16, 24):
         b = bits // 8
         frames, ch = 777, 3
@@ -295,10 +296,37 @@ def test_packed_le_output_is_byte_swapped_be_output(ctx, port):
         inp = port.fill_pcm(n + 16, bits)
         outs = {}
         for fmt in (abi.OUT_PACKED_BE, abi.OUT_PACKED_LE):
-            d = make_desc(bytes=n, bit_depth=bits, channels=ch, flags=abi.F_RAMP_ENABLED, ramp_start=9000, ramp_end=100, out_fmt=fmt)
+            d = make_desc(bytes=n, bit_depth=bits, channels=ch, flags=abi.F_RAMP_ENABLED, ramp_start=9000, ramp_end=100, out_fmt=fmt,
+                          aux=abi.LE_APPEND if fmt == abi.OUT_PACKED_LE else 0)
             outs[fmt] = run_device(ctx, d, inp, n)
             assert np.array_equal(outs[fmt], oracle_out(port, d, inp, n))
         assert np.array_equal(outs[abi.OUT_PACKED_LE].reshape(-1, b)[:, ::-1], outs[abi.OUT_PACKED_BE].reshape(-1, b))
+
+
+def test_packed_le_sink_to_the_letter(ctx, port):
+    """aux = 0: the chunk writes what the reference's ProcessorPcmSwpEndianPacked is left holding after the read -- all of an
+    8-bit or unramped playable, the last <= 256-byte fragment of a ramped 16/24-bit one (its SwapEndianness16/24 overwrite,
+    TestCodecInteractiveMain.cpp:570-590).  The port this compares with is pinned against the class itself
+    (tests/test_reference_sinks_codecs.py)."""
+    rng = np.random.default_rng(40)
+    specs = []
+    for k in range(300):
+        bits = int(rng.choice((8, 16, 24)))
+        ch = int(rng.integers(1, 9))
+        fb = ch * bits // 8
+        frames = int(rng.choice((1, 2, 256 // fb, 256 // fb + 1, 2 * (256 // fb), int(rng.integers(1, 9216 // fb + 1)))))
+        specs.append(dict(bytes=frames * fb, bit_depth=bits, channels=ch,
+                          flags=(abi.F_RAMP_ENABLED if k % 3 else 0) | (abi.F_IN_LITTLE_ENDIAN if k % 5 == 0 else 0),
+                          ramp_start=int(rng.integers(0, 16385)), ramp_end=int(rng.integers(0, 16385)),
+                          out_fmt=abi.OUT_PACKED_LE, aux=int(k % 7 == 0), src_pad=int(rng.integers(0, 5)), dst_pad=int(rng.integers(0, 5))))
+    descs, in_bytes, out_bytes = pack_chunks(specs)
+    inp = port.fill_pcm(in_bytes, 41)
+    assert (abi.chunk_out_bytes(descs) < descs["bytes"]).any()
+    want = oracle_out(port, descs, inp, out_bytes)
+    got = run_device(ctx, descs, inp, out_bytes)
+    assert np.array_equal(got, want), describe_first_diff(got, want, descs)
+    got = run_host(ctx, descs, inp, out_bytes)
+    assert np.array_equal(got, want), describe_first_diff(got, want, descs)
 
 
 def test_device_rejects_bad_descriptors_loudly(ctx):
