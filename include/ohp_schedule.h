@@ -44,8 +44,27 @@ typedef enum ohp_event_op {
     OHP_EV_UNMUTE = 4,          /* stage returns to running at Ramp::kMax                            */
     OHP_EV_SET_ATTENUATION = 5, /* arg = MsgAudioPcm::SetAttenuation value for following PCM msgs (Attenuator.cpp:55-58) */
     OHP_EV_INSERT_SILENCE = 6,  /* arg = jiffies; a MsgSilence enters the chain ahead of the next PCM msg */
-    OHP_EV_MAX_MSG_JIFFIES = 7  /* arg = jiffies; stage splits larger msgs first (StarvationRamper kMaxAudioOutJiffies,
+    OHP_EV_MAX_MSG_JIFFIES = 7, /* arg = jiffies; stage splits larger msgs first (StarvationRamper kMaxAudioOutJiffies,
                                    StarvationRamper.cpp:802-805); 0 disables                          */
+    /* The calls and messages the reference's own elements react to.  A stage driven by these IS that element: its state
+     * machine, including what a MsgSilence or a MsgHalt passing through does to a ramp in progress (ops 1-4 above are the
+     * bare "ramp from the current value over arg jiffies" idiom every element shares, and ramp MsgSilence like audio).
+     * tests/test_elements_vs_reference.py runs them beside the Ramper, Muter and StarvationRamper objects themselves.     */
+    OHP_EV_RAMPER_STREAM = 8,   /* a MsgDecodedStream reaches a Ramper (Ramper.cpp:72-93): arg != 0 -- IsRampApplicable --
+                                   starts its ramp up from Ramp::kMin over arg jiffies, arg = 0 leaves it at Ramp::kMax.
+                                   A MsgSilence (Ramper.cpp:106-112) or MsgHalt (:65-70) ends the ramp there and then    */
+    OHP_EV_MUTER_MUTE = 9,      /* Muter::Mute() with iRampDuration = arg (Muter.cpp:57-99): at once while halted, else a
+                                   ramp down from Ramp::kMax; called during a ramp up it turns the ramp round where it is
+                                   (remaining = arg - remaining).  Where the reference ASSERTS (already muting) so does this */
+    OHP_EV_MUTER_UNMUTE = 10,   /* Muter::Unmute() (Muter.cpp:101-137), the mirror image; from muted: ramp up from Ramp::kMin,
+                                   or straight to running while halted                                                    */
+    OHP_EV_HALT = 11,           /* a MsgHalt passes the stage and the animator acknowledges it at once: a Ramper stops
+                                   ramping; a Muter ramping down goes straight to muted and is halted until the next audio
+                                   (Muter.cpp:159-167, 264-290)                                                           */
+    OHP_EV_STARVATION = 12      /* the StarvationRamper's reservoir runs dry (StarvationRamper.cpp:622-673): if it is running,
+                                   or ramping up and audible, the flywheel ramp plays (generated audio: ohp_flywheel.h; not part
+                                   of this stream's output), a MsgHalt follows, and the audio after it ramps up from Ramp::kMin
+                                   over arg jiffies (iRampUpJiffies).  The stage also holds messages to kMaxAudioOutJiffies = 5 ms */
 } ohp_event_op;
 
 typedef struct ohp_ramp_event {

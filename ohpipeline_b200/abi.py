@@ -42,6 +42,11 @@ EV_UNMUTE = 4
 EV_SET_ATTENUATION = 5
 EV_INSERT_SILENCE = 6
 EV_MAX_MSG_JIFFIES = 7
+EV_RAMPER_STREAM = 8
+EV_MUTER_MUTE = 9
+EV_MUTER_UNMUTE = 10
+EV_HALT = 11
+EV_STARVATION = 12
 
 CHUNK_DESC = np.dtype([
     ("src_off", "<u8"), ("dst_off", "<u8"), ("bytes", "<u4"),

@@ -858,7 +858,7 @@ __device__ __noinline__ void convert_songcast(const ChunkRec& cr, uint32_t table
 
 // Fill `bytes` bytes at shared address a (16-byte aligned) with what MsgPlayableSilence::ReadBlock would emit:
 // used when silence goes to a sink that converts it (planar / Songcast).
-__device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint32_t channels, uint32_t lane)
+__device__ __noinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint32_t channels, uint32_t lane)
 {
     const uint32_t vecs = (bytes + 15u) >> 4;
     for (uint32_t v = lane; v < vecs; v += 32) {
@@ -872,12 +872,51 @@ __device__ __forceinline__ void silence_to_smem(uint32_t a, uint32_t bytes, uint
     }
 }
 
-// Few, fat instantiations on purpose.  A batch of mixed formats has every one of them hot at the same time (16 consumer
-// warps per SM, each in whatever its chunk needs), and the SM's instruction caches hold only so much: with one instantiation
-// per (depth, channel layout, alignment) -- 32 functions, 143 KB of SASS -- the mixed-format BASELINE config ran at 0.53 of the
-// copy peak, instruction fetch bound (profiles/README.md, round 2).  So: the two layouts the uniform configs are made of
-// (stereo, channel counts that are multiples of four) keep their lean aligned instantiation; everything else -- any other
-// channel count, any chunk that does not start on a 16-byte boundary -- shares ONE instantiation per depth.
+// The general path: any channel count, the image anywhere in its slot.  One unit (four subsamples) per lane per step, word
+// loads realigned with a funnel shift -- a quarter of the work per step of the group path above, and a quarter of its CODE:
+// that is the point.  A batch of mixed formats has every instantiation hot at the same time (16 consumer warps per SM, each
+// in whatever its chunk needs) and the SM's instruction caches are small (L0 ~6 KB, L1.5 32 KB): with one group-wide
+// instantiation per (depth, channel layout, alignment) -- 32 functions, 143 KB of SASS -- the mixed-format BASELINE config
+// ran at 0.53 of the copy peak with "no instruction" as its first stall reason (4.5 stalled warps per issue,
+// profiles/r02_config4_wide_ncu_summary.txt).  So the two layouts the uniform configs consist of (stereo, channel counts
+// that are multiples of four, image on a 16-byte boundary) keep their lean group-wide instantiation, and everything else
+// shares ONE small instantiation per depth.
+// In place: the output image starts at in_addr, at or below the input image (in_addr + head), so a step's stores never
+// reach bytes a LATER step still has to read; inside a step every lane loads before any lane stores (__syncwarp).
+template <int B>
+__device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t lane)
+{
+    UnitCtx cx;
+    RampRegs rr;
+    rr.table = table;
+    load_ctx(cr, cx, rr);
+    const uint32_t units = cr.units;
+    const uint32_t src = in_addr + (cr.head & ~3u);
+    const uint32_t fshift = (cr.head & 3u) * 8u;
+    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        uint32_t raw[B + 1], r[B + 1], w[B];
+        const uint32_t a = src + u * (4u * B);
+        if (u < units) {
+#pragma unroll
+            for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
+        } else {
+#pragma unroll
+            for (int i = 0; i <= B; i++) raw[i] = 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
+        r[B] = 0;
+        process_unit<B, kChmAny>(cx, rr, u, r, w);
+        if (u < units) {
+            const uint32_t d = in_addr + u * (4u * B);
+#pragma unroll
+            for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
+        }
+    }
+}
+
 template <int B>
 __device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t table, uint32_t in_addr, uint32_t t)
 {
@@ -885,7 +924,7 @@ __device__ __forceinline__ void transform_dispatch(const ChunkRec& cr, uint32_t 
     const bool aligned = (cr.variant & 16u) != 0; // head == 0
     if (aligned && chm == kChmStereo) transform_wide<B, kChmStereo, true>(cr, table, in_addr, t);
     else if (aligned && chm == kChmMul4) transform_wide<B, kChmMul4, true>(cr, table, in_addr, t);
-    else transform_wide<B, kChmAny, false>(cr, table, in_addr, t);
+    else transform_any<B>(cr, table, in_addr, t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -926,6 +965,19 @@ __device__ __forceinline__ uint4 cut_vector(const uint4& a, const uint4& b, uint
     return v;
 }
 
+// (out of line: keeps the consumer loop's own code short, see transform_any)
+__device__ __noinline__ void store_words_cut(uint32_t base, uint4* d4, uint32_t words, uint32_t lane)
+{
+    const uint32_t abase = base & ~15u;
+    const uint32_t word_off = (base & 15u) >> 2;
+    const uint32_t bit_off = (base & 3u) * 8u;
+    for (uint32_t w = lane; w < words; w += 32) {
+        const uint4 a = lds128(abase + 16u * w);
+        const uint4 b = lds128(abase + 16u * w + 16u); // at most 16 bytes past the image: inside the slot (kSlotBack)
+        stg128_stream(d4 + w, cut_vector(a, b, word_off, bit_off));
+    }
+}
+
 __device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, uint32_t bytes, uint32_t lane)
 {
     const uint32_t lead = (uint32_t)((16u - (reinterpret_cast<uint64_t>(dst) & 15u)) & 15u);
@@ -940,26 +992,14 @@ __device__ __forceinline__ void store_image_warp(uint32_t s_addr, uint8_t* dst, 
             tma_store(dst + head_n, base, words << 4);
         }
     } else {
-#ifdef OHP_EXPERIMENT_TMA_ANYWAY /* TIMING EXPERIMENT ONLY (wrong bytes): what would the cut-to-alignment path cost if it were one bulk store? */
-        if (lane == 0 && words != 0) tma_store(dst + head_n, base & ~15u, words << 4);
-        return;
-#endif
-        const uint32_t abase = base & ~15u;
-        const uint32_t word_off = (base & 15u) >> 2;
-        const uint32_t bit_off = (base & 3u) * 8u;
-        uint4* d4 = reinterpret_cast<uint4*>(dst + head_n);
-        for (uint32_t w = lane; w < words; w += 32) {
-            const uint4 a = lds128(abase + 16u * w);
-            const uint4 b = lds128(abase + 16u * w + 16u); // at most 16 bytes past the image: inside the slot (kSlotBack)
-            stg128_stream(d4 + w, cut_vector(a, b, word_off, bit_off));
-        }
+        store_words_cut(base, reinterpret_cast<uint4*>(dst + head_n), words, lane);
     }
 }
 
 // MsgPlayableSilence::ReadBlock (Msg.cpp:2874-2893): zeros; with 6 channels every emitted block of
 // maxBytes starts with 00 00 00 c0 for c0 = 0x00,0x10..0x70 (32 bytes, whatever the bit depth).
 // Written straight to global memory by the chunk's consumer warp (t = lane).
-__device__ __forceinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint32_t channels, uint32_t B, uint32_t t)
+__device__ __noinline__ void write_silence(uint8_t* dst, uint32_t bytes, uint32_t channels, uint32_t B, uint32_t t)
 {
     const uint32_t block = kMaxChunk - (kMaxChunk % (channels * B));
     const uint32_t lead = (uint32_t)((16u - (reinterpret_cast<uint64_t>(dst) & 15u)) & 15u);

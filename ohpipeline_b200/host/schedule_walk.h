@@ -83,6 +83,8 @@ struct Playable
 };
 
 enum Mode : uint32_t { Running = 0, RampingDown = 1, RampingUp = 2, Muted = 3 };
+// which of the reference's elements a stage is (stage_chain.h: decided by the ops of its events)
+enum Element : uint32_t { Generic = 0, ElemRamper = 1, ElemMuter = 2, ElemStarvation = 3, ElemBad = 4 };
 
 constexpr uint64_t kNever = ~0ull;
 
@@ -93,6 +95,8 @@ struct Stage
     uint64_t pos;
     uint64_t nextAt;   // at_jiffies of this stage's next event (index nextEv), kNever when there is none left
     uint32_t mode, current, remaining, maxMsg, attenuation, nextEv, depth;
+    uint32_t elem;     // Element
+    uint32_t halted;   // Muter::iHalted / StarvationRamper Halted-or-Starting: no PCM has passed since the start or the last halt
 };
 
 struct StreamCtx
@@ -315,7 +319,97 @@ OHP_HD void stage_seek(const StreamCtx& cx, Stage& s, uint32_t stage, uint32_t a
     s.nextAt = i < cx.nEv ? cx.ev[i].at_jiffies : kNever;
 }
 
-OHP_HD void apply_event(Stage& s, uint32_t op, uint32_t arg)
+// stage_chain.h StageElement()
+OHP_HD uint32_t stage_element(const StreamCtx& cx, uint32_t stage)
+{
+    uint32_t elem = Generic;
+    bool bare = false;
+    for (uint32_t i = 0; i < cx.nEv; i++) {
+        const ohp_ramp_event& e = cx.ev[i];
+        if (e.stage != stage) continue;
+        uint32_t of = Generic;
+        switch (e.op) {
+        case OHP_EV_RAMPER_STREAM: of = ElemRamper; break;
+        case OHP_EV_MUTER_MUTE: case OHP_EV_MUTER_UNMUTE: of = ElemMuter; break;
+        case OHP_EV_STARVATION: of = ElemStarvation; break;
+        case OHP_EV_RAMP_DOWN: case OHP_EV_RAMP_UP: case OHP_EV_MUTE: case OHP_EV_UNMUTE: bare = true; break;
+        default: break;
+        }
+        if (of != Generic) {
+            if (elem != Generic && elem != of) return ElemBad;
+            elem = of;
+        }
+    }
+    if (elem != Generic && bare) return ElemBad;
+    return elem;
+}
+
+// stage_chain.h ApplyElementEvent(): false where the reference ASSERTS
+OHP_HD bool apply_element_event(Stage& s, uint32_t op, uint32_t arg)
+{
+    switch (op) {
+    case OHP_EV_RAMPER_STREAM: // Ramper.cpp:72-93
+        if (arg != 0) { s.mode = RampingUp; s.current = core::kRampMin; s.remaining = arg; }
+        else { s.mode = Running; s.current = core::kRampMax; s.remaining = 0; }
+        break;
+    case OHP_EV_MUTER_MUTE: // Muter.cpp:57-99
+        if (s.mode == Running) {
+            if (s.halted) { s.mode = Muted; }
+            else { s.mode = RampingDown; s.remaining = arg; s.current = core::kRampMax; }
+        }
+        else if (s.mode == RampingUp) {
+            if (s.remaining == arg) { s.mode = Muted; }
+            else { s.mode = RampingDown; s.remaining = arg - s.remaining; }
+        }
+        else return false;
+        break;
+    case OHP_EV_MUTER_UNMUTE: // Muter.cpp:101-137
+        if (s.mode == RampingDown) {
+            if (s.remaining == arg) { s.mode = Running; }
+            else { s.mode = RampingUp; s.remaining = arg - s.remaining; }
+        }
+        else if (s.mode == Muted) {
+            if (s.halted) { s.mode = Running; }
+            else { s.mode = RampingUp; s.remaining = arg; s.current = core::kRampMin; }
+        }
+        else return false;
+        break;
+    case OHP_EV_HALT:
+        if (s.elem == ElemRamper) { // Ramper.cpp:65-70
+            if (s.mode == RampingUp) s.mode = Running;
+        }
+        else if (s.elem == ElemMuter) { // Muter.cpp:159-167, 264-280
+            if (s.mode == RampingDown) { s.mode = Muted; s.remaining = 0; s.current = core::kRampMin; }
+            s.halted = 1;
+        }
+        else if (s.elem == ElemStarvation) { // StarvationRamper.cpp:728-736
+            s.mode = Running;
+            s.halted = 1;
+        }
+        break;
+    case OHP_EV_STARVATION: // StarvationRamper.cpp:622-673
+        if ((s.mode == Running && !s.halted) || (s.mode == RampingUp && s.current != core::kRampMin)) {
+            s.mode = RampingUp; s.current = core::kRampMin; s.remaining = arg;
+        }
+        break;
+    default: break;
+    }
+    return true;
+}
+
+// stage_chain.h ElementSeesSilence()
+OHP_HD void element_sees_silence(Stage& s)
+{
+    if (s.elem == ElemRamper) { // Ramper.cpp:106-112
+        s.mode = Running; s.current = core::kRampMax; s.remaining = 0;
+    }
+    else if (s.elem == ElemMuter) { // Muter.cpp:188-208
+        if (s.mode == RampingDown) { s.mode = Muted; s.remaining = 0; s.current = core::kRampMin; }
+        else if (s.mode == RampingUp) { s.mode = Running; s.remaining = 0; s.current = core::kRampMax; }
+    }
+}
+
+OHP_HD bool apply_event(Stage& s, uint32_t op, uint32_t arg)
 {
     switch (op) {
     case OHP_EV_RAMP_DOWN:
@@ -330,8 +424,9 @@ OHP_HD void apply_event(Stage& s, uint32_t op, uint32_t arg)
     case OHP_EV_UNMUTE: s.mode = Running; s.current = core::kRampMax; s.remaining = 0; break;
     case OHP_EV_SET_ATTENUATION: s.attenuation = arg; break;
     case OHP_EV_MAX_MSG_JIFFIES: s.maxMsg = arg; break;
-    default: break;
+    default: return apply_element_event(s, op, arg);
     }
+    return true;
 }
 
 OHP_HD bool push_msg(Stage& s, Packed* aRow, const Msg& m)
@@ -346,7 +441,7 @@ OHP_HD uint32_t stage_process(const StreamCtx& cx, Stage& s, uint32_t stage, Pac
 {
     while (s.nextAt <= s.pos) {
         const ohp_ramp_event& e = cx.ev[s.nextEv];
-        apply_event(s, e.op, e.arg);
+        if (!apply_event(s, e.op, e.arg)) return kErrAssert;
         stage_seek(cx, s, stage, s.nextEv + 1);
     }
     Msg rest;
@@ -355,7 +450,7 @@ OHP_HD uint32_t stage_process(const StreamCtx& cx, Stage& s, uint32_t stage, Pac
         if (msg.silence) at -= at % cx.jps; // silence only splits on sample blocks
         if (at == 0) {
             const ohp_ramp_event& e = cx.ev[s.nextEv];
-            apply_event(s, e.op, e.arg);
+            if (!apply_event(s, e.op, e.arg)) return kErrAssert;
             stage_seek(cx, s, stage, s.nextEv + 1);
         }
         else {
@@ -372,6 +467,14 @@ OHP_HD uint32_t stage_process(const StreamCtx& cx, Stage& s, uint32_t stage, Pac
     }
     if (!msg.silence && s.attenuation != OHP_UNITY_ATTENUATION) {
         msg.atten = s.attenuation;
+    }
+    if (s.elem != Generic) {
+        if (msg.silence) { // the element reacts, the message is handed on untouched
+            element_sees_silence(s);
+            s.pos += msg.size;
+            return kOk;
+        }
+        s.halted = 0;
     }
     if (s.mode == RampingDown || s.mode == RampingUp) {
         if (s.remaining > 0) {
@@ -667,6 +770,7 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
         Stage& s = st[i];
         s.pos += posJiffies;
         if (s.mode == RampingDown || s.mode == RampingUp) { s.mode = rMode; s.current = rCurrent; s.remaining = rRemaining; }
+        if (s.elem != Generic) s.halted = 0; // PCM has passed
     }
     return n;
 }
@@ -687,9 +791,18 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
     for (int i = 0; i < kStages; i++) {
         st[i].pos = 0; st[i].mode = Running; st[i].current = core::kRampMax; st[i].remaining = 0; st[i].maxMsg = 0;
         st[i].attenuation = OHP_UNITY_ATTENUATION; st[i].depth = 0;
+        st[i].elem = stage_element(cx, (uint32_t)i);
+        st[i].halted = 1;
+        if (st[i].elem == ElemStarvation) st[i].maxMsg = 5u * OHP_JIFFIES_PER_MS; // kMaxAudioOutJiffies, StarvationRamper.cpp:376
         stage_seek(cx, st[i], (uint32_t)i, 0);
     }
     if (cx.jps == 0 || cx.frameBytes == 0) return kErrSpec;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < kStages; i++) {
+        if (st[i].elem == ElemBad) return kErrSpec;
+    }
     if (sp.chunk_frames == 0 || sp.chunk_frames * cx.frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return kErrSpec;
 
     // stage_chain.h Feed(0, item)

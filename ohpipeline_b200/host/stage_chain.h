@@ -43,6 +43,8 @@ class StageChain
         bool silence;
     };
     enum Mode { Running = 0, RampingDown = 1, RampingUp = 2, Muted = 3 };
+    // which of the reference's elements a stage is (decided by the ops of its events, see StageElement below)
+    enum Element { Generic = 0, ElemRamper = 1, ElemMuter = 2, ElemStarvation = 3, ElemBad = 4 };
     struct Stage
     {
         std::deque<Item> queue;
@@ -53,6 +55,8 @@ class StageChain
         uint32_t attenuation = OHP_UNITY_ATTENUATION;
         uint64_t pos = 0;
         uint32_t nextEv = 0;
+        Element elem = Generic;
+        bool halted = true; // Muter::iHalted / StarvationRamper's Halted-or-Starting: no PCM has passed since the start or the last halt
     };
 
 public:
@@ -78,6 +82,11 @@ public:
     {
         if (iJps == 0 || iFrameBytes == 0) return -2;
         if (iSpec.chunk_frames == 0 || iSpec.chunk_frames * iFrameBytes > OHP_MAX_PCM_CHUNK_BYTES) return -2;
+        for (unsigned i = 0; i < OHP_MAX_STAGES; i++) {
+            iStages[i].elem = StageElement(i);
+            if (iStages[i].elem == ElemBad) return -2;
+            if (iStages[i].elem == ElemStarvation) iStages[i].maxMsg = 5 * OHP_JIFFIES_PER_MS; // kMaxAudioOutJiffies, StarvationRamper.cpp:376
+        }
         uint64_t frame = 0;
         uint64_t srcJiffies = 0;
         uint32_t silEv = 0;
@@ -116,6 +125,95 @@ private:
         }
         return false;
     }
+    // A stage whose events use an element's own ops IS that element from the first message on; the bare ramp ops
+    // (OHP_EV_RAMP_DOWN ... OHP_EV_UNMUTE) do not mix with them, two different elements' ops neither.
+    Element StageElement(unsigned aStage) const
+    {
+        Element elem = Generic;
+        bool bare = false;
+        for (uint32_t i = 0; i < iNumEvents; i++) {
+            const ohp_ramp_event& e = iEvents[i];
+            if (e.stage != aStage) continue;
+            Element of = Generic;
+            switch (e.op) {
+            case OHP_EV_RAMPER_STREAM: of = ElemRamper; break;
+            case OHP_EV_MUTER_MUTE: case OHP_EV_MUTER_UNMUTE: of = ElemMuter; break;
+            case OHP_EV_STARVATION: of = ElemStarvation; break;
+            case OHP_EV_RAMP_DOWN: case OHP_EV_RAMP_UP: case OHP_EV_MUTE: case OHP_EV_UNMUTE: bare = true; break;
+            default: break;
+            }
+            if (of != Generic) {
+                if (elem != Generic && elem != of) return ElemBad;
+                elem = of;
+            }
+        }
+        if (elem != Generic && bare) return ElemBad;
+        return elem;
+    }
+    // The element's own calls and control messages.  Returns false where the reference ASSERTS.
+    static bool ApplyElementEvent(Stage& s, const ohp_ramp_event& e)
+    {
+        switch (e.op) {
+        case OHP_EV_RAMPER_STREAM: // Ramper::ProcessMsg(MsgDecodedStream), Ramper.cpp:72-93
+            if (e.arg != 0) { s.mode = RampingUp; s.current = Api::kRampMin; s.remaining = e.arg; }
+            else { s.mode = Running; s.current = Api::kRampMax; s.remaining = 0; }
+            break;
+        case OHP_EV_MUTER_MUTE: // Muter::Mute, Muter.cpp:57-99 (eMuting and eMuted differ in who is told when, not in the audio)
+            if (s.mode == Running) {
+                if (s.halted) { s.mode = Muted; }
+                else { s.mode = RampingDown; s.remaining = e.arg; s.current = Api::kRampMax; }
+            }
+            else if (s.mode == RampingUp) {
+                if (s.remaining == e.arg) { s.mode = Muted; }
+                else { s.mode = RampingDown; s.remaining = e.arg - s.remaining; }
+            }
+            else return false;
+            break;
+        case OHP_EV_MUTER_UNMUTE: // Muter::Unmute, Muter.cpp:101-137
+            if (s.mode == RampingDown) {
+                if (s.remaining == e.arg) { s.mode = Running; }
+                else { s.mode = RampingUp; s.remaining = e.arg - s.remaining; }
+            }
+            else if (s.mode == Muted) {
+                if (s.halted) { s.mode = Running; }
+                else { s.mode = RampingUp; s.remaining = e.arg; s.current = Api::kRampMin; }
+            }
+            else return false;
+            break;
+        case OHP_EV_HALT:
+            if (s.elem == ElemRamper) { // Ramper::ProcessMsg(MsgHalt), Ramper.cpp:65-70
+                if (s.mode == RampingUp) s.mode = Running;
+            }
+            else if (s.elem == ElemMuter) { // Muter::ProcessMsg(MsgHalt) -> BeginHalting, then Halted(), Muter.cpp:159-167, 264-280
+                if (s.mode == RampingDown) { s.mode = Muted; s.remaining = 0; s.current = Api::kRampMin; }
+                s.halted = true;
+            }
+            else if (s.elem == ElemStarvation) { // StarvationRamper::ProcessMsgOut(MsgHalt), StarvationRamper.cpp:728-736
+                s.mode = Running;
+                s.halted = true;
+            }
+            break;
+        case OHP_EV_STARVATION: // StarvationRamper::Pull on an empty reservoir, StarvationRamper.cpp:622-673
+            if ((s.mode == Running && !s.halted) || (s.mode == RampingUp && s.current != Api::kRampMin)) {
+                s.mode = RampingUp; s.current = Api::kRampMin; s.remaining = e.arg;
+            }
+            break;
+        default: break;
+        }
+        return true;
+    }
+    // What a MsgSilence passing through does to the element (the message itself is handed on untouched).
+    static void ElementSeesSilence(Stage& s)
+    {
+        if (s.elem == ElemRamper) { // Ramper.cpp:106-112
+            s.mode = Running; s.current = Api::kRampMax; s.remaining = 0;
+        }
+        else if (s.elem == ElemMuter) { // Muter.cpp:188-208
+            if (s.mode == RampingDown) { s.mode = Muted; s.remaining = 0; s.current = Api::kRampMin; }
+            else if (s.mode == RampingUp) { s.mode = Running; s.remaining = 0; s.current = Api::kRampMax; }
+        }
+        // StarvationRamper::ProcessMsgOut(MsgSilence), StarvationRamper.cpp:893-911: a ramp up in progress waits for the next audio
+    }
     static void ApplyEvent(Stage& s, const ohp_ramp_event& e)
     {
         switch (e.op) {
@@ -131,7 +229,7 @@ private:
         case OHP_EV_UNMUTE: s.mode = Running; s.current = Api::kRampMax; s.remaining = 0; break;
         case OHP_EV_SET_ATTENUATION: s.attenuation = e.arg; break;
         case OHP_EV_MAX_MSG_JIFFIES: s.maxMsg = e.arg; break;
-        default: break;
+        default: Api::Assert(ApplyElementEvent(s, e)); break;
         }
     }
     void Process(unsigned aStage, Item& aItem)
@@ -160,6 +258,14 @@ private:
         }
         if (!aItem.silence && s.attenuation != OHP_UNITY_ATTENUATION) {
             static_cast<typename Api::MsgAudioPcm*>(msg)->SetAttenuation(s.attenuation);
+        }
+        if (s.elem != Generic) {
+            if (aItem.silence) {
+                ElementSeesSilence(s);
+                s.pos += msg->Jiffies();
+                return;
+            }
+            s.halted = false; // Muter::ProcessAudio, Muter.cpp:212; StarvationRamper::ProcessMsgOut(MsgAudioPcm), StarvationRamper.cpp:797-799
         }
         if (s.mode == RampingDown || s.mode == RampingUp) {
             if (s.remaining > 0) {

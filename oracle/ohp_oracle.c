@@ -481,6 +481,8 @@ typedef struct stage {
     uint32_t attenuation;
     uint64_t pos;
     uint32_t next_ev; /* index into the stream's event slice */
+    int elem;         /* 0: the bare ramp idiom; 1 Ramper, 2 Muter, 3 StarvationRamper (by the ops of the stage's events); 4 mixed up */
+    int halted;       /* Muter::iHalted / StarvationRamper Halted-or-Starting: no PCM since the start or the last halt */
 } stage;
 
 typedef struct run {
@@ -712,7 +714,88 @@ static void drive(run* r, const msg* m)
     }
 }
 
-static void apply_event(stage* s, const ohp_ramp_event* e)
+/* Which of the reference's elements a stage is: decided by the ops of its events (include/ohp_schedule.h). */
+static int stage_element(const ohp_ramp_event* ev, uint32_t nev, uint32_t si)
+{
+    int elem = 0, bare = 0;
+    for (uint32_t i = 0; i < nev; i++) {
+        if (ev[i].stage != si) continue;
+        int of = 0;
+        switch (ev[i].op) {
+        case OHP_EV_RAMPER_STREAM: of = 1; break;
+        case OHP_EV_MUTER_MUTE: case OHP_EV_MUTER_UNMUTE: of = 2; break;
+        case OHP_EV_STARVATION: of = 3; break;
+        case OHP_EV_RAMP_DOWN: case OHP_EV_RAMP_UP: case OHP_EV_MUTE: case OHP_EV_UNMUTE: bare = 1; break;
+        default: break;
+        }
+        if (of) {
+            if (elem && elem != of) return 4;
+            elem = of;
+        }
+    }
+    return (elem && bare) ? 4 : elem;
+}
+
+/* The elements' own calls and control messages; returns -1 where the reference ASSERTS. */
+static int apply_element_event(stage* s, const ohp_ramp_event* e)
+{
+    switch (e->op) {
+    case OHP_EV_RAMPER_STREAM: /* Ramper::ProcessMsg(MsgDecodedStream), Ramper.cpp:72-93 */
+        if (e->arg != 0) { s->mode = 2; s->current = KMIN; s->remaining = e->arg; }
+        else { s->mode = 0; s->current = KMAX; s->remaining = 0; }
+        break;
+    case OHP_EV_MUTER_MUTE: /* Muter::Mute, Muter.cpp:57-99 */
+        if (s->mode == 0) {
+            if (s->halted) s->mode = 3;
+            else { s->mode = 1; s->remaining = e->arg; s->current = KMAX; }
+        } else if (s->mode == 2) {
+            if (s->remaining == e->arg) s->mode = 3;
+            else { s->mode = 1; s->remaining = e->arg - s->remaining; }
+        } else return -1; /* ASSERTS(), Muter.cpp:88-90 */
+        break;
+    case OHP_EV_MUTER_UNMUTE: /* Muter::Unmute, Muter.cpp:101-137 */
+        if (s->mode == 1) {
+            if (s->remaining == e->arg) s->mode = 0;
+            else { s->mode = 2; s->remaining = e->arg - s->remaining; }
+        } else if (s->mode == 3) {
+            if (s->halted) s->mode = 0;
+            else { s->mode = 2; s->remaining = e->arg; s->current = KMIN; }
+        } else return -1; /* ASSERTS(), Muter.cpp:107-111 */
+        break;
+    case OHP_EV_HALT:
+        if (s->elem == 1) { /* Ramper::ProcessMsg(MsgHalt), Ramper.cpp:65-70 */
+            if (s->mode == 2) s->mode = 0;
+        } else if (s->elem == 2) { /* Muter::ProcessMsg(MsgHalt) -> BeginHalting; the animator reports halted: Muter.cpp:159-167, 264-280 */
+            if (s->mode == 1) { s->mode = 3; s->remaining = 0; s->current = KMIN; }
+            s->halted = 1;
+        } else if (s->elem == 3) { /* StarvationRamper::ProcessMsgOut(MsgHalt), StarvationRamper.cpp:728-736 */
+            s->mode = 0;
+            s->halted = 1;
+        }
+        break;
+    case OHP_EV_STARVATION: /* StarvationRamper::Pull on an empty reservoir, StarvationRamper.cpp:622-673 */
+        if ((s->mode == 0 && !s->halted) || (s->mode == 2 && s->current != KMIN)) {
+            s->mode = 2; s->current = KMIN; s->remaining = e->arg;
+        }
+        break;
+    default: break;
+    }
+    return 0;
+}
+
+/* What a MsgSilence passing through does to the element; the message itself is handed on untouched. */
+static void element_sees_silence(stage* s)
+{
+    if (s->elem == 1) { /* Ramper::ProcessMsg(MsgSilence), Ramper.cpp:106-112 */
+        s->mode = 0; s->current = KMAX; s->remaining = 0;
+    } else if (s->elem == 2) { /* Muter::ProcessMsg(MsgSilence), Muter.cpp:188-208 */
+        if (s->mode == 1) { s->mode = 3; s->remaining = 0; s->current = KMIN; }
+        else if (s->mode == 2) { s->mode = 0; s->remaining = 0; s->current = KMAX; }
+    }
+    /* StarvationRamper::ProcessMsgOut(MsgSilence), StarvationRamper.cpp:893-911: a ramp up in progress waits for the next audio */
+}
+
+static int apply_event(stage* s, const ohp_ramp_event* e)
 {
     switch (e->op) {
     case OHP_EV_RAMP_DOWN:
@@ -727,8 +810,9 @@ static void apply_event(stage* s, const ohp_ramp_event* e)
     case OHP_EV_UNMUTE: s->mode = 0; s->current = KMAX; s->remaining = 0; break;
     case OHP_EV_SET_ATTENUATION: s->attenuation = e->arg; break;
     case OHP_EV_MAX_MSG_JIFFIES: s->max_msg = e->arg; break;
-    default: break;
+    default: return apply_element_event(s, e);
     }
+    return 0;
 }
 
 static int next_stage_event(run* r, int si, uint32_t* idx)
@@ -751,7 +835,7 @@ static void stage_process(run* r, int si, msg* m)
     msg rem;
     /* events due at or before the current position fire first */
     while (next_stage_event(r, si, &ei) && r->ev[ei].at_jiffies <= s->pos) {
-        apply_event(s, &r->ev[ei]);
+        if (apply_event(s, &r->ev[ei])) { r->err = -1; return; }
         s->next_ev = ei + 1;
     }
     /* an event inside this message: Split() there; the remainder is re-queued at the head */
@@ -759,7 +843,7 @@ static void stage_process(run* r, int si, msg* m)
         uint32_t at = (uint32_t)(r->ev[ei].at_jiffies - s->pos);
         if (m->kind == MSG_SILENCE) at -= at % r->jps; /* silence only splits on sample blocks */
         if (at == 0) {
-            apply_event(s, &r->ev[ei]);
+            if (apply_event(s, &r->ev[ei])) { r->err = -1; return; }
             s->next_ev = ei + 1;
         } else {
             if (msg_split(r, m, at, &rem)) { r->err = -1; return; }
@@ -774,6 +858,14 @@ static void stage_process(run* r, int si, msg* m)
     }
     if (m->kind == MSG_PCM && s->attenuation != OHP_UNITY_ATTENUATION) {
         m->attenuation = s->attenuation; /* Attenuator::ProcessMsg, Attenuator.cpp:55-58 */
+    }
+    if (s->elem != 0) {
+        if (m->kind == MSG_SILENCE) {
+            element_sees_silence(s);
+            s->pos += m->size;
+            return;
+        }
+        s->halted = 0; /* Muter::ProcessAudio, Muter.cpp:212; StarvationRamper::ProcessMsgOut(MsgAudioPcm), StarvationRamper.cpp:797-799 */
     }
     if (s->mode == 1 || s->mode == 2) {
         if (s->remaining > 0) {
@@ -829,6 +921,10 @@ static int run_stream(run* r)
         memset(s, 0, sizeof *s);
         s->current = KMAX;
         s->attenuation = OHP_UNITY_ATTENUATION;
+        s->elem = stage_element(r->ev, r->nev, i);
+        s->halted = 1;
+        if (s->elem == 4) return -2;
+        if (s->elem == 3) s->max_msg = 5u * OHP_JIFFIES_PER_MS; /* kMaxAudioOutJiffies, StarvationRamper.cpp:376 */
     }
     r->block_fill = 0;
     r->out_bytes = 0;
