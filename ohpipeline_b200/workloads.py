@@ -372,3 +372,69 @@ def mixed(n_streams=64, seed=4, max_frames=6000, with_silence=True, p2=True):
         evs.append(lst)
         slack.append(extra)
     return _finish("mixed: %d streams, seed %d" % (n_streams, seed), specs, evs, seed=(4 << 32) + seed, slack=slack)
+
+
+def elements(seed, n_streams=24, seconds=0.6, illegal=False):
+    """Streams whose stages ARE the reference's elements (include/ohp_schedule.h, ops 8-12): stage 0 a Ramper (a stream that
+    starts with its 50 ms ramp up, sometimes a second MsgDecodedStream mid-stream, MsgHalt), stage 1 a StarvationRamper
+    (the reservoir runs dry at positions aligned to nothing: ramp up from silence over 50 ms afterwards, messages held to
+    5 ms), stage 2 a Muter (Mute / Unmute in turn, 30 ms ramps, some calls landing inside the ramp the previous one
+    started, MsgHalt while ramping down and while muted), MsgSilence entering at the top now and then (every element reacts
+    to it differently), a driver pulling fixed blocks on some streams.  tests/test_elements_vs_reference.py runs them
+    through the element objects themselves.  illegal: Mute() twice in a row on some streams -- the reference ASSERTS."""
+    rng = np.random.default_rng(seed)
+    specs, evs, slack = [], [], []
+    for i in range(n_streams):
+        rate = int(rng.choice((44100, 48000, 96000, 192000)))
+        bits = int(rng.choice((8, 16, 24, 32)))
+        ch = int(rng.choice((1, 2, 2, 6, 8)))
+        jps = abi.jiffies_per_sample(rate)
+        fb = ch * bits // 8
+        chunk = max_chunk_frames(rate, bits, ch)
+        total = int(rate * seconds * rng.uniform(0.3, 1.0))
+        total_j = total * jps
+        use_silence = rng.random() < 0.4
+        block = int(rng.integers(rate // 1000, rate // 100 + 1)) if rng.random() < 0.3 else 0
+        spec = _spec(rate, bits, ch, bool(rng.integers(0, 2)), chunk, total, abi.OUT_PACKED_BE, block)
+        if rng.random() < 0.25:
+            spec["codec_read_frames"] = abi.MAX_PCM_CHUNK_BYTES // fb
+        q = jps if use_silence else 1   # a MsgSilence cannot be split inside a sample: sample-aligned event grid
+        lst, extra = [], 0
+
+        def at(lo, hi):
+            return int(rng.integers(lo, max(lo + 1, hi))) // q * q
+
+        which = rng.random(3) < 0.7
+        if which[0]:   # Ramper
+            lst.append((0, 0, abi.EV_RAMPER_STREAM, 50 * MS if rng.random() < 0.8 else 0))
+            if rng.random() < 0.4:
+                lst.append((at(0, total_j), 0, abi.EV_RAMPER_STREAM, 50 * MS if rng.random() < 0.7 else 0))
+            if rng.random() < 0.3:
+                lst.append((at(0, 60 * MS), 0, abi.EV_HALT, 0))
+        if which[1]:   # StarvationRamper
+            t = at(0, total_j // 2)
+            for _ in range(int(rng.integers(1, 4))):
+                lst.append((t, 1, abi.EV_STARVATION, 50 * MS))
+                t += at(1, 120 * MS)
+            if rng.random() < 0.3:
+                lst.append((at(0, total_j), 1, abi.EV_HALT, 0))
+        if which[2]:   # Muter
+            t = at(0, total_j // 3)
+            op = abi.EV_MUTER_MUTE
+            for k in range(int(rng.integers(1, 6))):
+                lst.append((t, 2, op, 30 * MS))
+                if illegal and rng.random() < 0.3:
+                    lst.append((t + q, 2, op, 30 * MS))
+                op = abi.EV_MUTER_UNMUTE if op == abi.EV_MUTER_MUTE else abi.EV_MUTER_MUTE
+                t += at(1, 25 * MS) if rng.random() < 0.4 else 30 * MS + at(0, 60 * MS)
+            if rng.random() < 0.4:
+                lst.append((at(0, total_j), 2, abi.EV_HALT, 0))
+        if use_silence:
+            for _ in range(int(rng.integers(1, 4))):
+                sj = int(rng.integers(1, 12 * (rate // 1000) + 1)) * jps
+                lst.append((at(0, total_j) // jps * jps, 0, abi.EV_INSERT_SILENCE, sj))
+                extra += (sj // jps) * fb
+        specs.append(spec)
+        evs.append(lst)
+        slack.append(extra)
+    return _finish("elements %d" % seed, specs, evs, seed=(8 << 32) + seed, slack=slack)

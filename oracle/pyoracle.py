@@ -313,6 +313,39 @@ class Ref(_Lib):
         rc = f(_ptr(buf) if buf.size else None, buf.size, max_bit_depth, _ptr(info), _ptr(reads), cap, C.byref(n))
         return int(rc), info[0], reads[:min(n.value, cap)].copy()
 
+    def elements_run(self, streams, events, inp, out_bytes, want_audio=True):
+        """Every stream through the reference's own element OBJECTS (Ramper, Muter, StarvationRamper; oracle/ref_elements.cpp),
+        driven at the positions the element-level OHP_EV_* events name.  Returns (rc, out, chunks, info, chunk_begin,
+        stream_out_bytes, flywheel messages played per stream); rc -1: the reference ASSERTs, -2: not stageable."""
+        streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+        events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+        inp = np.ascontiguousarray(inp, dtype=np.uint8)
+        out = np.zeros(int(out_bytes), dtype=np.uint8) if want_audio else None
+        gen = np.zeros(max(len(streams), 1), dtype=np.uint32)
+        res = ScheduleResult()
+        f = self.lib.ref_elements_run
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(ScheduleResult), C.c_void_p]
+        rc = f(_ptr(streams), len(streams), _ptr(events), len(events), _ptr(inp), _ptr(out) if want_audio else None, C.byref(res), _ptr(gen))
+        if rc != 0:
+            return rc, None, None, None, None, None, None
+        chunks, info, begin, outb = self._collect(res, len(streams), self._free_result)
+        return 0, out, chunks, info, begin, outb, gen[:len(streams)].copy()
+
+    def volume_ramper(self, enabled, ramps, kinds):
+        """The real VolumeRamper element on one message per ramp (kinds: 0 PCM, 1 silence).  Returns (multipliers handed to
+        IVolumeRamper::ApplyVolumeMultiplier, the ramp each message leaves with)."""
+        r = np.array([tuple(x) for x in ramps], dtype=abi.RAMP)
+        k = np.ascontiguousarray(kinds, dtype=np.uint32)
+        mult = np.zeros(len(r) + 4, dtype=np.uint32)
+        after = np.zeros(len(r), dtype=abi.RAMP)
+        f = self.lib.ref_volume_ramper
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        n = f(int(bool(enabled)), _ptr(r), _ptr(k), len(r), _ptr(mult), _ptr(after))
+        assert n >= 0
+        return mult[:n].copy(), after
+
     def _free_result(self, res_ref):
         res = res_ref._obj
         self._libc_free(res.chunks)

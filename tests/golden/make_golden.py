@@ -39,6 +39,9 @@ def cases():
         w = W.mixed(n_streams=12, seed=seed, max_frames=1500)
         w.streams["out_fmt"] = abi.OUT_PACKED_BE  # the linked reference only has the packed-BE sink
         yield "mixed_%d" % seed, w
+    # recorded from the reference's ELEMENT OBJECTS (Ramper, StarvationRamper, Muter; oracle/ref_elements.cpp), not from the
+    # stage model on the reference's message classes like the ones above
+    yield "elements_11", W.elements(11, n_streams=20, seconds=0.4)
 
 
 def main():
@@ -50,7 +53,10 @@ def main():
         if only and name not in only:
             continue
         inp = port.fill_pcm(w.in_bytes, w.seed)
-        rc, out, chunks, info = ref.run(w.streams, w.events, inp, w.out_bytes, threads=1)
+        if name.startswith("elements"):
+            rc, out, chunks, info, _, _, _ = ref.elements_run(w.streams, w.events, inp, w.out_bytes)
+        else:
+            rc, out, chunks, info = ref.run(w.streams, w.events, inp, w.out_bytes, threads=1)
         assert rc == 0, (name, rc)
         path = os.path.join(HERE, name + ".npz")
         # every chunk's bytes are pinned by a CRC-32; the bytes themselves are kept for small outputs only
