@@ -113,6 +113,11 @@ int    ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams,
 int    ohp_schedule_build_walk(const ohp_stream_spec* streams, size_t n_streams,
                                const ohp_ramp_event* events, size_t n_events,
                                int threads, ohp_schedule** out);
+/* The closed-form upper bound on each stream's playables that ohp_run_streams_device sizes its descriptor regions with
+ * (one walk per stream instead of count + emit); bounds[s] = 0 for a stream the walk refuses.  Exported so that the CPU
+ * suite can hold it against the exact counts. */
+int    ohp_schedule_chunk_bounds(const ohp_stream_spec* streams, size_t n_streams,
+                                 const ohp_ramp_event* events, size_t n_events, uint64_t* bounds);
 size_t ohp_schedule_num_chunks(const ohp_schedule* s);
 const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s);
 const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s);

@@ -130,6 +130,8 @@ def host_lib():
         L.ohp_container_stream_spec.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.ohp_codec_message_frames.restype = C.c_size_t
         L.ohp_codec_message_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ohp_schedule_chunk_bounds.restype = C.c_int
+        L.ohp_schedule_chunk_bounds.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         L.ohp_schedule_num_chunks.restype = C.c_size_t
         L.ohp_schedule_num_chunks.argtypes = [C.c_void_p]
         for name in ("ohp_schedule_chunks", "ohp_schedule_chunk_info", "ohp_schedule_stream_chunk_begin",
@@ -222,6 +224,17 @@ def flywheel_job(rate, channels, bits, src_off=0, dst_off=0):
     j = np.zeros(1, dtype=abi.FLYWHEEL_JOB)
     j[0] = (src_off, dst_off, rate, abi.FLYWHEEL_RAMP_JIFFIES // jps, abi.FLYWHEEL_TRAINING_JIFFIES // jps, channels, bits, 0)
     return j
+
+
+def schedule_chunk_bounds(streams, events):
+    """ohp_schedule_chunk_bounds: the per-stream upper bound on playables ohp_run_streams_device sizes its regions with."""
+    streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+    events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+    out = np.zeros(len(streams), dtype=np.uint64)
+    rc = host_lib().ohp_schedule_chunk_bounds(_ptr(streams), len(streams), _ptr(events) if len(events) else None, len(events), _ptr(out))
+    if rc != 0:
+        raise OhpError(rc, "ohp_schedule_chunk_bounds")
+    return out
 
 
 class Schedule:
@@ -441,14 +454,16 @@ class Context:
         return outb, int(total.value)
 
     def run_streams_device(self, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
-                           d_stream_out_bytes=0, stream=None):
-        """ohp_run_streams_device: the whole stage for a batch resident in HBM (raw device addresses); asynchronous on
-        `stream` apart from the chunk total it reads back.  Returns the number of playables."""
+                           d_stream_out_bytes=0, stream=None, want_total=True):
+        """ohp_run_streams_device: the whole stage for a batch resident in HBM (raw device addresses), enqueued on `stream`.
+        want_total: also wait for the schedule walks and return the number of playables (else None: nothing but the
+        regions' size is waited for)."""
         total = C.c_uint64(0)
         self._check(self._L.ohp_run_streams_device(self._h, C.c_void_p(d_streams), n_streams, C.c_void_p(d_events), n_events,
                                                    C.c_void_p(d_in), in_bytes, C.c_void_p(d_out), out_bytes,
-                                                   C.c_void_p(d_stream_out_bytes), C.byref(total), C.c_void_p(stream or 0)))
-        return int(total.value)
+                                                   C.c_void_p(d_stream_out_bytes), C.byref(total) if want_total else None,
+                                                   C.c_void_p(stream or 0)))
+        return int(total.value) if want_total else None
 
     def fill_streams_device(self, d_in, in_bytes, d_streams, n_streams, seed_base, first_stream_id=0, stream=None):
         """ohp_fill_streams_device: seeded synthetic PCM per stream, generated in HBM."""

@@ -81,6 +81,9 @@ struct ohp_context
     ohp_ramp_event* d_events = nullptr; uint64_t d_events_cap = 0;
     uint64_t* d_begin = nullptr; uint64_t d_begin_cap = 0;
     uint64_t* d_outb = nullptr; uint64_t d_outb_cap = 0;
+    uint64_t* d_counts = nullptr; uint64_t d_counts_cap = 0;  // ohp_run_streams_device: exact playables per stream
+    cudaStream_t sched_stream = nullptr;                         // ... the walks run here, beside ramp_convert_kernel
+    std::vector<cudaEvent_t> sched_events;
     std::vector<uint64_t> h_begin, h_outb;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timing = false;
@@ -394,6 +397,33 @@ static int grow(ohp_context* ctx, T*& ptr, uint64_t& cap, uint64_t need)
     return OHP_OK;
 }
 
+static int schedule_status(ohp_context* ctx, cudaStream_t st)
+{
+    // words [2], [3] of the status block belong to the schedule kernels
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t bits = ctx->h_status[2];
+    if (bits == 0) return OHP_OK;
+    const uint32_t stream_index = 0xffffffffu - ctx->h_status[3];
+    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(uint32_t), st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    char buf[160];
+    if (bits & (1u << sched::kErrSpec)) {
+        std::snprintf(buf, sizeof buf, "stream %u: spec not representable (rate, frame size, chunk size, event slice or sink)", stream_index);
+        return fail(ctx, OHP_E_INVALID_ARG, buf);
+    }
+    if (bits & (1u << sched::kErrAssert)) {
+        std::snprintf(buf, sizeof buf, "stream %u: the reference would ASSERT on this schedule", stream_index);
+        return fail(ctx, OHP_E_INVALID_DESC, buf);
+    }
+    if (bits & (1u << sched::kErrBound)) {
+        std::snprintf(buf, sizeof buf, "stream %u: more playables than its descriptor region holds", stream_index);
+        return fail(ctx, OHP_E_NO_MEMORY, buf);
+    }
+    std::snprintf(buf, sizeof buf, "stream %u: more than %d pending message splits in one stage", stream_index, sched::kStackDepth);
+    return fail(ctx, OHP_E_NO_MEMORY, buf);
+}
+
 static int read_status(ohp_context* ctx, cudaStream_t st)
 {
     OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -408,6 +438,7 @@ static int read_status(ohp_context* ctx, cudaStream_t st)
         std::snprintf(fbuf, sizeof fbuf, "device rejected flywheel job %u (%s)", job - 1, (fly_bits & 1u) ? "invalid" : "out of range");
         return fail(ctx, (fly_bits & 1u) ? OHP_E_INVALID_DESC : OHP_E_OUT_OF_RANGE, fbuf);
     }
+    if (ctx->h_status[2] != 0) return schedule_status(ctx, st); // a walk enqueued by ohp_run_streams_device refused a stream
     const uint32_t bits = ctx->h_status[0];
     if (bits == 0) return OHP_OK;
     const uint32_t first = ctx->h_status[1];
@@ -597,6 +628,9 @@ int ohp_destroy(ohp_context* ctx)
     if (ctx->d_events) (void)cudaFree(ctx->d_events);
     if (ctx->d_begin) (void)cudaFree(ctx->d_begin);
     if (ctx->d_outb) (void)cudaFree(ctx->d_outb);
+    if (ctx->d_counts) (void)cudaFree(ctx->d_counts);
+    if (ctx->sched_stream) { (void)cudaStreamSynchronize(ctx->sched_stream); (void)cudaStreamDestroy(ctx->sched_stream); }
+    for (cudaEvent_t e : ctx->sched_events) (void)cudaEventDestroy(e);
     if (ctx->h_status) (void)cudaFreeHost(ctx->h_status);
     if (ctx->ev_start) (void)cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) (void)cudaEventDestroy(ctx->ev_stop);
@@ -806,28 +840,6 @@ int ohp_memcpy_d2h(ohp_context* ctx, void* hptr, const void* dptr, uint64_t byte
 
 // Device-side schedule builder (include/ohp_schedule_device.h) -------------------------------------------------
 
-static int schedule_status(ohp_context* ctx, cudaStream_t st)
-{
-    // words [2], [3] of the status block belong to the schedule kernels
-    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    OHP_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint32_t bits = ctx->h_status[2];
-    if (bits == 0) return OHP_OK;
-    const uint32_t stream_index = 0xffffffffu - ctx->h_status[3];
-    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_status + 2, 0, 2 * sizeof(uint32_t), st));
-    OHP_CUDA(ctx, cudaStreamSynchronize(st));
-    char buf[160];
-    if (bits & (1u << sched::kErrSpec)) {
-        std::snprintf(buf, sizeof buf, "stream %u: spec not representable (rate, frame size, chunk size, event slice or sink)", stream_index);
-        return fail(ctx, OHP_E_INVALID_ARG, buf);
-    }
-    if (bits & (1u << sched::kErrAssert)) {
-        std::snprintf(buf, sizeof buf, "stream %u: the reference would ASSERT on this schedule", stream_index);
-        return fail(ctx, OHP_E_INVALID_DESC, buf);
-    }
-    std::snprintf(buf, sizeof buf, "stream %u: more than %d pending message splits in one stage", stream_index, sched::kStackDepth);
-    return fail(ctx, OHP_E_NO_MEMORY, buf);
-}
 
 // Threads per stream in the schedule kernels: a warp while warps-per-stream still fit the GPU a few times over, else one
 // thread.  OHP_SCHED_TEAM=1|32 pins it (experiments).
@@ -1005,6 +1017,33 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
 }
 
 // The whole stage for a batch resident in HBM (include/ohp_schedule_device.h).
+//
+// ONE walk per stream: a closed-form upper bound (sched::stream_chunk_bound) gives every stream a region of the context's
+// descriptor buffer, the walk writes what the stream has and zero-fills the rest of its region (a zero-byte descriptor is
+// a playable MsgPlayable::Read does nothing for, and costs ramp_convert_kernel a record and a ticket).  No count pass, and
+// the only host round trip is for the regions' total (bound + scan are a few microseconds of GPU time).  The batch goes in
+// slices of streams: while ramp_convert_kernel works on slice k on the caller's stream, the walk of slice k + 1 runs next
+// to it on the context's schedule stream (a latency-bound kernel of a few hundred warps: it fits beside the two
+// ramp_convert CTAs of an SM).  A stream that outgrows its region (none of the shapes this repo generates does, the bound
+// is held against the exact counts in tests/test_schedule_walk.py) sends the whole call through the two-pass path.
+static int run_streams_device_two_pass(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                                       const ohp_ramp_event* d_events, size_t n_events,
+                                       const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
+                                       uint64_t* d_stream_out_bytes, uint64_t* total_chunks, cudaStream_t st)
+{
+    int rc;
+    uint64_t total = 0;
+    if ((rc = ohp_schedule_count_device(ctx, d_streams, n_streams, d_events, n_events, ctx->d_begin, d_stream_out_bytes, &total, st)) != OHP_OK) return rc;
+    if (total_chunks) *total_chunks = total;
+    if (total > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) {
+        // the buffer may still be read by a launch enqueued earlier on another stream
+        OHP_CUDA(ctx, cudaDeviceSynchronize());
+        if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, total * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+    }
+    if ((rc = ohp_schedule_emit_device(ctx, d_streams, n_streams, d_events, n_events, ctx->d_begin, ctx->d_descs, nullptr, st)) != OHP_OK) return rc;
+    return launch(ctx, ctx->d_descs, (size_t)total, d_in, in_bytes, d_out, out_bytes, st);
+}
+
 int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                            const ohp_ramp_event* d_events, size_t n_events,
                            const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
@@ -1018,16 +1057,92 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     int rc;
     if ((rc = grow(ctx, ctx->d_begin, ctx->d_begin_cap, (uint64_t)(n_streams + 1) * sizeof(uint64_t))) != OHP_OK) return rc;
-    uint64_t total = 0;
-    if ((rc = ohp_schedule_count_device(ctx, d_streams, n_streams, d_events, n_events, ctx->d_begin, d_stream_out_bytes, &total, st)) != OHP_OK) return rc;
-    if (total_chunks) *total_chunks = total;
-    if (total > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) {
-        // the buffer may still be read by a launch enqueued earlier on another stream
-        OHP_CUDA(ctx, cudaDeviceSynchronize());
-        if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, total * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+    if ((rc = grow(ctx, ctx->d_counts, ctx->d_counts_cap, (uint64_t)n_streams * sizeof(uint64_t))) != OHP_OK) return rc;
+    const char* one_walk_env = std::getenv("OHP_ONE_WALK"); // OHP_ONE_WALK=0: count + scan + emit as in round 1
+    const bool one_walk = !one_walk_env || std::atoi(one_walk_env) != 0;
+    if (!one_walk) {
+        return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
+                                           d_stream_out_bytes, total_chunks, st);
     }
-    if ((rc = ohp_schedule_emit_device(ctx, d_streams, n_streams, d_events, n_events, ctx->d_begin, ctx->d_descs, nullptr, st)) != OHP_OK) return rc;
-    return launch(ctx, ctx->d_descs, (size_t)total, d_in, in_bytes, d_out, out_bytes, st);
+    // 1. regions: bound per stream, exclusive scan, their offsets to the host (the one synchronisation of the call)
+    sched::bound_kernel<<<(unsigned)((n_streams + 127) / 128), 128, 0, st>>>(d_streams, n_streams, d_events, n_events, ctx->d_begin);
+    OHP_CUDA(ctx, cudaGetLastError());
+    sched::scan_kernel<<<1, 1024, 0, st>>>(ctx->d_begin, n_streams);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    ctx->h_begin.resize(n_streams + 1);
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_begin.data(), ctx->d_begin, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t regions = ctx->h_begin[n_streams];
+    if (regions > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) {
+        OHP_CUDA(ctx, cudaDeviceSynchronize());
+        if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, regions * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+    }
+    // 2. slices of streams, about equal in descriptors; the walk of each on the schedule stream, its ramp_convert launch on
+    //    the caller's stream behind it
+    uint64_t kSliceChunks = 1u << 19;
+    if (const char* e = std::getenv("OHP_SLICE_CHUNKS")) { // tests: several slices on a small batch
+        const long v = std::atol(e);
+        if (v > 0) kSliceChunks = (uint64_t)v;
+    }
+    size_t n_slices = (size_t)((regions + kSliceChunks - 1) / kSliceChunks);
+    if (n_slices > 8) n_slices = 8;
+    if (n_slices < 1) n_slices = 1;
+    if (ctx->sched_events.size() < n_slices + 1) {
+        while (ctx->sched_events.size() < n_slices + 1) {
+            cudaEvent_t e;
+            OHP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->sched_events.push_back(e);
+        }
+    }
+    if (!ctx->sched_stream) OHP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sched_stream, cudaStreamNonBlocking));
+    // the schedule stream starts behind whatever the caller's stream holds so far (specs, events and PCM may just have arrived)
+    OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[n_slices], st));
+    OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_events[n_slices], 0));
+    const int team = schedule_team(n_streams);
+    size_t lo = 0;
+    for (size_t k = 0; k < n_slices; k++) {
+        // streams [lo, hi): up to the next multiple of regions / n_slices descriptors
+        const uint64_t want = regions * (k + 1) / n_slices;
+        size_t hi = (size_t)(std::upper_bound(ctx->h_begin.begin() + lo, ctx->h_begin.begin() + n_streams, want) - ctx->h_begin.begin());
+        if (hi <= lo) hi = lo + 1;
+        if (hi > n_streams || k + 1 == n_slices) hi = n_streams;
+        sched::ScheduleParams p{};
+        p.streams = d_streams; p.n_streams = hi - lo; p.events = d_events; p.n_events = n_events;
+        p.chunk_begin = ctx->d_begin; p.descs = ctx->d_descs; p.info = nullptr;
+        p.status = ctx->d_status + 2;
+        p.first_stream = lo; p.counts_out = ctx->d_counts; p.out_bytes = d_stream_out_bytes;
+        if (team == 32) sched::schedule_kernel<true, 32><<<sched::schedule_grid(hi - lo, 32), sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
+        else sched::schedule_kernel<true, 1><<<sched::schedule_grid(hi - lo, 1), sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
+        OHP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[k], ctx->sched_stream));
+        OHP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sched_events[k], 0));
+        const uint64_t c_lo = ctx->h_begin[lo], c_hi = ctx->h_begin[hi];
+        if ((rc = launch(ctx, ctx->d_descs + c_lo, (size_t)(c_hi - c_lo), d_in, in_bytes, d_out, out_bytes, st)) != OHP_OK) return rc;
+        lo = hi;
+        if (lo == n_streams) break;
+    }
+    if (total_chunks) {
+        // the exact number of playables: wait for the walks (not for ramp_convert_kernel), add the streams' counts up
+        OHP_CUDA(ctx, cudaStreamSynchronize(ctx->sched_stream));
+        ctx->h_outb.resize(n_streams);
+        OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_outb.data(), ctx->d_counts, n_streams * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->sched_stream));
+        OHP_CUDA(ctx, cudaStreamSynchronize(ctx->sched_stream));
+        const int src = schedule_status(ctx, ctx->sched_stream);
+        if (src == OHP_E_NO_MEMORY && ctx->error.find("region") != std::string::npos) {
+            // a stream outgrew its region: nothing wrong with the batch, take the exact two-pass path
+            OHP_CUDA(ctx, cudaStreamSynchronize(st));
+            (void)read_status(ctx, st);
+            return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
+                                               d_stream_out_bytes, total_chunks, st);
+        }
+        if (src != OHP_OK) return src;
+        uint64_t total = 0;
+        for (size_t s2 = 0; s2 < n_streams; s2++) total += ctx->h_outb[s2];
+        *total_chunks = total;
+    }
+    return OHP_OK;
 }
 
 int ohp_fill_streams_device(ohp_context* ctx, uint8_t* d_in, uint64_t in_bytes, const ohp_stream_spec* d_streams,

@@ -28,7 +28,22 @@ struct ScheduleParams
     ohp_chunk_desc* descs;     // EMIT
     ohp_chunk_info* info;      // EMIT, may be null
     uint32_t* status;          // [0] error bits (1 << code), [1] 0xffffffff - lowest failing stream (atomicMax; 0 = none)
+    // ONE-WALK mode (regions from stream_chunk_bound): EMIT also reports what COUNT would have, and fills each region's tail
+    uint64_t first_stream;     // the slice [first_stream, first_stream + n_streams) of the batch is walked
+    uint64_t* counts_out;      // [all streams] exact playables per stream (null: two-pass mode)
 };
+
+constexpr uint32_t kErrBound = 4u; // a stream has more playables than stream_chunk_bound allowed for: the caller takes two passes
+
+// Regions for the one-walk mode: bound[s] playables at most for stream s (scanned into region offsets afterwards).
+__global__ void __launch_bounds__(128) bound_kernel(const ohp_stream_spec* __restrict__ streams, uint64_t n_streams,
+                                                    const ohp_ramp_event* __restrict__ events, uint64_t n_events, uint64_t* __restrict__ bound)
+{
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    bound[s] = stream_chunk_bound(streams[s], events, n_events);
+}
+
 
 // TEAM threads walk one stream: TEAM = 32 (a warp per stream: no divergence between streams, 32 descriptors per bulk
 // step written side by side) when streams are few enough for that to fill the GPU, TEAM = 1 (a thread per stream) when
@@ -37,14 +52,24 @@ template <bool EMIT, int TEAM>
 __global__ void __launch_bounds__(128) schedule_kernel(const ScheduleParams p)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t s = t / TEAM;
+    const uint64_t local = t / TEAM;
     const uint32_t lane = (uint32_t)(t % TEAM);
-    if (s >= p.n_streams) return;
+    if (local >= p.n_streams) return;
+    const uint64_t s = p.first_stream + local;
     const ohp_stream_spec sp = p.streams[s];
     uint64_t nChunks, outBytes;
     ohp_chunk_desc* descs = EMIT ? p.descs + p.chunk_begin[s] : nullptr;
     ohp_chunk_info* info = (EMIT && p.info) ? p.info + p.chunk_begin[s] : nullptr;
-    const uint32_t rc = run_stream<EMIT, TEAM, true>(sp, p.events, p.n_events, descs, info, nChunks, outBytes, lane);
+    const bool regions = EMIT && p.counts_out != nullptr;
+    const uint64_t limit = regions ? p.chunk_begin[s + 1] - p.chunk_begin[s] : ~0ull;
+    uint32_t rc = run_stream<EMIT, TEAM, true>(sp, p.events, p.n_events, descs, info, nChunks, outBytes, lane, limit);
+    if (regions) {
+        if (rc == kOk && nChunks > limit) rc = kErrBound;
+        // the rest of the region: zero-byte descriptors (all lanes of the team, two 128-bit stores each)
+        const uint64_t from = rc == kOk ? nChunks : 0;
+        uint4* d4 = reinterpret_cast<uint4*>(descs);
+        for (uint64_t i = 2 * from + lane; i < 2 * limit; i += TEAM) d4[i] = make_uint4(0, 0, 0, 0);
+    }
     if (lane != 0) return;
     if (rc != kOk) {
         atomicOr(&p.status[0], 1u << rc);
@@ -52,6 +77,10 @@ __global__ void __launch_bounds__(128) schedule_kernel(const ScheduleParams p)
     }
     if (!EMIT) {
         p.chunk_count[s] = nChunks;
+        if (p.out_bytes) p.out_bytes[s] = outBytes;
+    }
+    else if (regions) {
+        p.counts_out[s] = rc == kOk ? nChunks : 0;
         if (p.out_bytes) p.out_bytes[s] = outBytes;
     }
 }

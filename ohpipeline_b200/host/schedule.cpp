@@ -223,6 +223,14 @@ int ohp_schedule_build_walk(const ohp_stream_spec* streams, size_t n_streams, co
     return OHP_OK;
 }
 
+int ohp_schedule_chunk_bounds(const ohp_stream_spec* streams, size_t n_streams,
+                              const ohp_ramp_event* events, size_t n_events, uint64_t* bounds)
+{
+    if ((n_streams && (!streams || !bounds)) || (n_events && !events)) return OHP_E_INVALID_ARG;
+    for (size_t s = 0; s < n_streams; s++) bounds[s] = ohp::sched::stream_chunk_bound(streams[s], events, n_events);
+    return OHP_OK;
+}
+
 size_t ohp_schedule_num_chunks(const ohp_schedule* s) { return s ? s->chunks.size() : 0; }
 const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s) { return s ? s->chunks.data() : nullptr; }
 const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s) { return s ? s->info.data() : nullptr; }

@@ -112,6 +112,7 @@ struct StreamCtx
     uint64_t nChunks, outBytes;
     ohp_chunk_desc* descs; // EMIT: this stream's first descriptor
     ohp_chunk_info* info;  // EMIT, may be null
+    uint64_t limit;        // EMIT: descriptors this stream may write (its region when regions come from stream_chunk_bound)
 };
 
 // MsgAudio::Split (+ SplitCompleted): m keeps the first aJiffies, rest gets what follows.
@@ -252,6 +253,7 @@ OHP_HD void emit_desc(const StreamCtx& cx, const Playable& p, uint64_t aIndex, u
     const uint32_t w5 = (p.ramp.start & 0xffffu) | (p.ramp.end << 16);
     const uint32_t w6 = (p.atten & 0xffffu) | (cx.bits << 16) | (cx.channels << 24);
     const uint32_t w7 = flags | (cx.out_fmt << 8) | (cx.out_fmt == OHP_OUT_PACKED_LE ? OHP_LE_APPEND << 16 : 0u); // aux: as MsgPlayable::Descriptor
+    if (aIndex >= cx.limit) return; // never outside the stream's region; the caller compares the count with the limit afterwards
 #if defined(__CUDA_ARCH__)
     uint4* out = reinterpret_cast<uint4*>(cx.descs + aIndex);
     out[0] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), (uint32_t)dst, (uint32_t)(dst >> 32));
@@ -890,7 +892,7 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
 template <bool EMIT, int STRIDE = 1, bool BULK = true>
 OHP_HD uint32_t run_stream(const ohp_stream_spec& sp, const ohp_ramp_event* aEvents, uint64_t aNumEvents,
                            ohp_chunk_desc* aDescs, ohp_chunk_info* aInfo, uint64_t& aNumChunks, uint64_t& aOutBytes,
-                           uint32_t aLane = 0)
+                           uint32_t aLane = 0, uint64_t aLimit = ~0ull)
 {
     aNumChunks = 0;
     aOutBytes = 0;
@@ -913,11 +915,71 @@ OHP_HD uint32_t run_stream(const ohp_stream_spec& sp, const ohp_ramp_event* aEve
     cx.outBytes = 0;
     cx.descs = EMIT ? aDescs : nullptr;
     cx.info = EMIT ? aInfo : nullptr;
+    cx.limit = aLimit;
     const uint32_t rc = walk_stream<EMIT, STRIDE, BULK>(sp, cx);
     if (rc != kOk) return rc;
     aNumChunks = cx.nChunks;
     aOutBytes = cx.outBytes;
     return kOk;
+}
+
+// An UPPER BOUND on the playables of a stream, in closed form from its spec and events -- what lets the descriptors be
+// built in ONE walk: every stream gets a region of this many descriptors, writes what it has and zero-fills the rest
+// (a zero-byte descriptor is a playable MsgPlayable::Read does nothing for, Msg.cpp:2649).  Counted:
+//   * the messages the codec delivers (behind a block-reading codec: the pieces CodecController cuts, which
+//     DecodedAudioAggregator only ever merges), one per MsgSilence;
+//   * a stage that holds messages to a size smaller than the largest message there is: at most total / cap more;
+//   * per event: the message it falls inside is split (1) and the ramp it starts ends inside a message (1); a MsgHalt, a
+//     MsgDecodedStream or a call that turns a ramp round costs no more than that;
+//   * two ramps running against each other cross in at most one message (Ramp::Set's split fragment, Msg.cpp:637-699),
+//     and a message takes one ramp from each stage it passes: one per pair of events on DIFFERENT stages;
+//   * a driver pulling fixed blocks cuts at every block boundary of the stream's output.
+// 0 for a stream the walk will refuse anyway.  tests/test_schedule_walk.py holds it against the exact counts.
+OHP_HD uint64_t stream_chunk_bound(const ohp_stream_spec& sp, const ohp_ramp_event* aEvents, uint64_t aNumEvents)
+{
+    if ((uint64_t)sp.first_event + sp.num_events > aNumEvents) return 0;
+    const uint32_t jps = core::jiffies_per_sample_or_zero(sp.sample_rate);
+    const uint64_t frameBytes = (uint64_t)sp.channels * (sp.bit_depth / 8u);
+    if (jps == 0 || frameBytes == 0 || sp.chunk_frames == 0 || frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return 0;
+    const ohp_ramp_event* ev = aEvents + sp.first_event;
+    uint64_t msgs = (sp.total_frames + sp.chunk_frames - 1) / sp.chunk_frames;
+    uint64_t largest = (uint64_t)sp.chunk_frames * jps;           // jiffies of the largest message that can enter a stage
+    if (sp.codec_read_frames != 0) {
+        msgs += (sp.total_frames + sp.codec_read_frames - 1) / sp.codec_read_frames + 1;
+        const uint64_t cell = (OHP_MAX_PCM_CHUNK_BYTES / frameBytes) * jps;
+        if (cell > largest) largest = cell;
+    }
+    uint64_t frames = sp.total_frames, nEv = 0;
+    uint32_t cap[kStages];
+    uint64_t perStage[kStages];
+    for (int i = 0; i < kStages; i++) { cap[i] = 0; perStage[i] = 0; }
+    for (uint32_t i = 0; i < sp.num_events; i++) {
+        const ohp_ramp_event& e = ev[i];
+        if (e.op == OHP_EV_INSERT_SILENCE) {
+            msgs++;
+            frames += e.arg / jps + 1;
+            if (e.arg > largest) largest = e.arg;
+            continue;
+        }
+        nEv++;
+        if (e.stage >= (uint32_t)kStages) continue;
+        perStage[e.stage]++;
+        uint32_t c = 0;
+        if (e.op == OHP_EV_MAX_MSG_JIFFIES) c = e.arg;
+        else if (e.op == OHP_EV_STARVATION) c = 5u * OHP_JIFFIES_PER_MS;
+        if (c != 0 && (cap[e.stage] == 0 || c < cap[e.stage])) cap[e.stage] = c;
+    }
+    const uint64_t total = frames * jps;
+    uint64_t bound = msgs;
+    for (int i = 0; i < kStages; i++) {
+        if (cap[i] != 0 && largest > cap[i]) bound += total / (cap[i] < jps ? jps : cap[i]) + 1;
+    }
+    bound += 2u * nEv;
+    for (int i = 0; i < kStages; i++) {
+        for (int j = i + 1; j < kStages; j++) bound += perStage[i] * perStage[j];
+    }
+    if (sp.driver_block_frames != 0) bound += frames / sp.driver_block_frames + 1;
+    return bound + 4;
 }
 
 } // namespace sched

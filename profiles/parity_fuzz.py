@@ -24,7 +24,8 @@ def main():
     ctx = capi.Context(0)
     gens = [("mixed", lambda s: workloads.mixed(n_streams=96, seed=s, max_frames=5000)),
             ("steady_edges", lambda s: workloads.steady_edges(s, n_streams=96)),
-            ("config4", lambda s: workloads.config4(n_streams=64, seconds=0.1, seed=s))]
+            ("config4", lambda s: workloads.config4(n_streams=64, seconds=0.1, seed=s)),
+            ("elements", lambda s: workloads.elements(s, n_streams=48, seconds=0.4, illegal=(s % 4 == 0)))]
     tot = {g: {"workloads": 0, "streams": 0, "chunks": 0, "bytes_checked": 0, "asserting_streams_dropped": 0} for g, _ in gens}
     failures = []
     t0 = time.time()

@@ -64,6 +64,16 @@ def test_device_schedule_matches_host_on_mixed_workloads(ctx, seed):
     assert check_both(ctx, workloads.mixed(n_streams=96, seed=seed, max_frames=5000)) is not None
 
 
+@pytest.mark.parametrize("seed", [1, 5, 6])
+def test_device_walk_is_the_element_model(ctx, seed):
+    """Stages that ARE the reference's elements (Ramper, StarvationRamper, Muter: ops 8-12 of include/ohp_schedule.h): the walk
+    the GPU runs against the host model, which tests/test_elements_vs_reference.py holds against the element objects
+    themselves (and tests/golden/elements_11.npz, recorded from those objects, is among the golden files above)."""
+    assert check_both(ctx, workloads.elements(seed, n_streams=64)) is not None
+    # Mute() twice in a row: the reference ASSERTS, host and device refuse alike
+    assert check_both(ctx, workloads.elements(seed, n_streams=64, illegal=True)) is None
+
+
 def test_device_schedule_many_streams(ctx):
     """More streams than one wave of threads; ragged event slices; one partial warp."""
     assert check_both(ctx, workloads.mixed(n_streams=3001, seed=22, max_frames=700)) is not None
@@ -258,6 +268,44 @@ def test_whole_stage_for_a_batch_resident_in_hbm(ctx, port, make):
             assert n_other == len(capi.schedule_build(other.streams, other.events).chunks)
             d_out.fill_(0x5A)
             torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("mode", ["sliced", "two_pass"])
+def test_whole_stage_device_call_in_slices_and_in_two_passes(ctx, port, mode, monkeypatch):
+    """The one-walk path cut into many slices (the walk of slice k + 1 beside ramp_convert_kernel on slice k), and the
+    round-1 count + scan + emit path it falls back to: same bytes, same sizes, same count."""
+    import torch
+    if mode == "sliced":
+        monkeypatch.setenv("OHP_SLICE_CHUNKS", "700")
+    else:
+        monkeypatch.setenv("OHP_ONE_WALK", "0")
+    for w in (workloads.config4(n_streams=120, seconds=0.12, seed=3), workloads.elements(4, n_streams=60), workloads.config5(n_streams=90, seconds=0.1)):
+        inp = port.fill_pcm(w.in_bytes, w.seed)
+        rc, want, chunks, _ = port.run(w.streams, w.events, inp, w.out_bytes)
+        assert rc == 0
+        host = capi.schedule_build(w.streams, w.events)
+        d_streams = torch.from_numpy(w.streams.view(np.uint8).copy()).cuda()
+        d_events = torch.from_numpy(w.events.view(np.uint8).copy()).cuda()
+        d_in = torch.from_numpy(inp).cuda()
+        d_out = torch.full((w.out_bytes + 16,), 0x5A, dtype=torch.uint8, device="cuda")
+        d_outb = torch.zeros(len(w.streams), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        total = ctx.run_streams_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events),
+                                       d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes, d_outb.data_ptr())
+        ctx.sync()
+        assert total == len(chunks)
+        assert np.array_equal(d_outb.cpu().numpy().view(np.uint64), host.stream_out_bytes)
+        got = d_out.cpu().numpy()[:w.out_bytes]
+        mask = covered_mask(chunks, w.out_bytes)
+        assert np.array_equal(got[mask], want[mask]) and (got[~mask] == 0x5A).all()
+        # fully asynchronous (no chunk total asked for): same bytes
+        d_out.fill_(0x5A)
+        torch.cuda.synchronize()
+        assert ctx.run_streams_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes,
+                                      d_out.data_ptr(), w.out_bytes, 0, None, want_total=False) is None
+        ctx.sync()
+        got = d_out.cpu().numpy()[:w.out_bytes]
+        assert np.array_equal(got[mask], want[mask]) and (got[~mask] == 0x5A).all()
 
 
 def test_whole_stage_device_call_reports_errors(ctx):

@@ -211,8 +211,13 @@ def test_container_parser_matches_the_reference_codecs(ref):
 def test_container_parser_matches_the_reference_codecs_on_truncated_files(ref):
     for data in corpus()[:9] + corpus()[21:24]:
         for cut in list(range(0, min(len(data), 120))) + [len(data) - 1, len(data) - 7]:
-            if cut >= 0:
+            if cut >= 12:
                 same_verdict(ref, data[:cut])
+            elif cut >= 0:
+                # CodecAiffBase::Recognise compares all 12 bytes of its stack buffer however few the stream delivered
+                # (AiffBase.cpp:25-32; CodecWav checks the count, Wav.cpp:93): below 12 bytes the reference's answer depends on
+                # what the stack held before.  Here such a stream is simply not recognised.
+                assert capi.container_parse(data[:cut])[0] == abi.CONTAINER_E_UNRECOGNISED
 
 
 def test_container_parser_matches_the_reference_codecs_on_mutated_headers(ref):

@@ -142,3 +142,35 @@ def test_ramp_lengths_of_the_pipeline_elements(rate, bits):
                 assert (before["flags"] & quiet).all() and not (after["flags"] & (abi.F_RAMP_ENABLED | quiet)).any() and len(after)
             # the bytes in front of the ramp are whole samples: the split at a mid-sample jiffy rounds down (Msg.cpp:2236-2240)
             assert int(before["bytes"].sum()) == (start // jps) * 2 * bits // 8
+
+
+def test_closed_form_bound_covers_every_stream():
+    """ohp_run_streams_device builds the descriptors in ONE walk per stream into regions sized by a closed-form upper bound
+    (sched::stream_chunk_bound): the bound must hold for every stream of every generator, and stay close where streams are
+    long (padding descriptors cost the hot path a record and a ticket each)."""
+    from ohpipeline_b200 import workloads as W
+    cases = [W.config1(6.2), W.config2(8, 1.0), W.config3(48, 1.0), W.config4(200, 0.25), W.config5(32, 1.0), W.all_rates()]
+    cases += [W.mixed(64, s, 4000) for s in range(6)] + [W.steady_edges(s, 64) for s in range(4)]
+    cases += [W.elements(s, 32, illegal=(s % 2 == 0)) for s in range(4)] + [W.config4(64, 0.1, seed=s) for s in range(4)]
+    streams = 0
+    for w in cases:
+        bounds = capi.schedule_chunk_bounds(w.streams, w.events)
+        exact = 0
+        for k in range(len(w.streams)):
+            st = w.streams[k:k + 1].copy()
+            ev = w.events[int(st[0]["first_event"]):int(st[0]["first_event"]) + int(st[0]["num_events"])]
+            st[0]["first_event"] = 0
+            try:
+                n = len(capi.schedule_build(st, ev, walk=True).chunks)
+            except capi.OhpError:
+                continue                      # the reference ASSERTs: no descriptors either way
+            assert n <= int(bounds[k]), (w.name, k, n, int(bounds[k]))
+            exact += n
+            streams += 1
+        if w.name.startswith(("config2", "config3", "config5")):
+            assert int(bounds.sum()) <= 1.06 * exact, (w.name, int(bounds.sum()), exact)
+    assert streams > 900
+    # a spec the walk refuses has no region
+    bad = W.config5(2, 0.05)
+    bad.streams["sample_rate"][1] = 12345
+    assert int(capi.schedule_chunk_bounds(bad.streams, bad.events)[1]) == 0
