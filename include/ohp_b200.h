@@ -85,6 +85,7 @@ typedef enum ohp_out_fmt {
  * One MsgPlayable.  32 bytes, 16-byte aligned so a warp can fetch it as two 128-bit loads.
  * `bytes` is the playable's payload size in SOURCE bytes and must be a whole number of
  * frames (bytes % (channels*bit_depth/8) == 0), as MsgPlayable sizes are.
+ * A descriptor whose fields from `bytes` on are all zero is an empty slot: it is skipped, never rejected.
  */
 typedef struct ohp_chunk_desc {
     uint64_t src_off;     /* byte offset of the first payload byte in the input arena; ignored for silence */

@@ -950,8 +950,10 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
     // every stream's spans must lie inside the arenas (the kernel checks each chunk too; this names the stream)
     for (size_t s = 0; s < n_streams; s++) {
         const ohp_stream_spec& sp = h_streams[s];
-        const uint64_t in_len = sp.total_frames * (uint64_t)(sp.channels * (sp.bit_depth / 8u));
-        if (sp.src_base > in_bytes || in_len > in_bytes - sp.src_base || sp.dst_base > out_bytes || ctx->h_outb[s] > out_bytes - sp.dst_base) {
+        const uint64_t frame_bytes = (uint64_t)sp.channels * (sp.bit_depth / 8u);
+        const bool wraps = frame_bytes != 0 && sp.total_frames > UINT64_MAX / frame_bytes;
+        const uint64_t in_len = sp.total_frames * frame_bytes;
+        if (wraps || sp.src_base > in_bytes || in_len > in_bytes - sp.src_base || sp.dst_base > out_bytes || ctx->h_outb[s] > out_bytes - sp.dst_base) {
             char buf[96];
             std::snprintf(buf, sizeof buf, "stream %zu reaches outside the arenas", s);
             return fail(ctx, OHP_E_OUT_OF_RANGE, buf);
@@ -1021,11 +1023,14 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
 // ONE walk per stream: a closed-form upper bound (sched::stream_chunk_bound) gives every stream a region of the context's
 // descriptor buffer, the walk writes what the stream has and zero-fills the rest of its region (a zero-byte descriptor is
 // a playable MsgPlayable::Read does nothing for, and costs ramp_convert_kernel a record and a ticket).  No count pass, and
-// the only host round trip is for the regions' total (bound + scan are a few microseconds of GPU time).  The batch goes in
-// slices of streams: while ramp_convert_kernel works on slice k on the caller's stream, the walk of slice k + 1 runs next
-// to it on the context's schedule stream (a latency-bound kernel of a few hundred warps: it fits beside the two
-// ramp_convert CTAs of an SM).  A stream that outgrows its region (none of the shapes this repo generates does, the bound
-// is held against the exact counts in tests/test_schedule_walk.py) sends the whole call through the two-pass path.
+// the only host round trip is for the regions' total (bound + scan are a few microseconds of GPU time).
+// The batch CAN go in slices of streams (OHP_SLICE_CHUNKS=<descriptors per slice>): ramp_convert_kernel on slice k on the
+// caller's stream while the walk of slice k + 1 runs beside it on the context's schedule stream.  Measured (round 2,
+// profiles/README.md) that loses: a walk takes as long as its longest stream whatever the number of streams (the ramp
+// recurrence is sequential; 1024 or 256 streams of configs[1] both take 0.65 ms), so slicing by streams multiplies the
+// walk time it was meant to hide (configs[1]: 5.07 ms in 4 slices against 4.3 in one).  Default: one slice.
+// A stream that outgrows its region (none of the shapes this repo generates does, the bound is held against the exact
+// counts in tests/test_schedule_walk.py) sends the whole call through the two-pass path.
 static int run_streams_device_two_pass(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                                        const ohp_ramp_event* d_events, size_t n_events,
                                        const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
@@ -1080,8 +1085,8 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
     }
     // 2. slices of streams, about equal in descriptors; the walk of each on the schedule stream, its ramp_convert launch on
     //    the caller's stream behind it
-    uint64_t kSliceChunks = 1u << 19;
-    if (const char* e = std::getenv("OHP_SLICE_CHUNKS")) { // tests: several slices on a small batch
+    uint64_t kSliceChunks = ~0ull;
+    if (const char* e = std::getenv("OHP_SLICE_CHUNKS")) { // experiments and tests
         const long v = std::atol(e);
         if (v > 0) kSliceChunks = (uint64_t)v;
     }

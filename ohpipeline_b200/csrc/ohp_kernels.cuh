@@ -148,6 +148,9 @@ struct DescDerived
 __host__ __device__ inline uint32_t check_desc_fields(const DescFields& d, uint64_t in_bytes, uint64_t out_total, DescDerived& o)
 {
     o.frames = 0; o.out_bytes = 0; o.out_extent = 0;
+    // an all-zero descriptor is an EMPTY SLOT (ohp_run_streams_device pads each stream's region of the descriptor array with
+    // them): nothing to read, nothing to write, nothing to reject
+    if ((d.bytes | d.ramp_start | d.ramp_end | d.attenuation | d.bit_depth | d.channels | d.flags | d.out_fmt | d.aux) == 0) return 0;
     const uint32_t bd = d.bit_depth;
     if (!(bd == 8 || bd == 16 || bd == 24 || bd == 32)) return 1u;           // ConstructPcm ASSERTs, Msg.cpp:349-366
     if (d.channels < 1 || d.channels > 32) return 1u;

@@ -81,7 +81,9 @@ public:
     int Run()
     {
         if (iJps == 0 || iFrameBytes == 0) return -2;
-        if (iSpec.chunk_frames == 0 || iSpec.chunk_frames * iFrameBytes > OHP_MAX_PCM_CHUNK_BYTES) return -2;
+        if (iSpec.channels > 32u) return -2; // ohp_chunk_desc::channels is 8 bits wide and checked against 1..32
+        if (iSpec.chunk_frames == 0 || (uint64_t)iSpec.chunk_frames * iFrameBytes > OHP_MAX_PCM_CHUNK_BYTES) return -2;
+        if (iSpec.total_frames > (~0ull) / iFrameBytes) return -2;
         for (unsigned i = 0; i < OHP_MAX_STAGES; i++) {
             iStages[i].elem = StageElement(i);
             if (iStages[i].elem == ElemBad) return -2;

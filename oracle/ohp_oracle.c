@@ -915,7 +915,8 @@ static int run_stream(run* r)
     if (sp->bit_depth != 8 && sp->bit_depth != 16 && sp->bit_depth != 24 && sp->bit_depth != 32) return -2;
     if (sp->channels == 0 || sp->channels > 32) return -2;
     r->frame_bytes = sp->channels * (sp->bit_depth / 8u);
-    if (sp->chunk_frames == 0 || sp->chunk_frames * r->frame_bytes > CELL_MAX) return -2;
+    if (sp->chunk_frames == 0 || (uint64_t)sp->chunk_frames * r->frame_bytes > CELL_MAX) return -2;
+    if (sp->total_frames > (~0ull) / r->frame_bytes) return -2;
     for (unsigned i = 0; i < OHP_MAX_STAGES; i++) {
         stage* s = &r->st[i];
         memset(s, 0, sizeof *s);

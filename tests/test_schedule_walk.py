@@ -53,7 +53,8 @@ def test_walk_refuses_what_the_class_model_refuses():
     w = workloads.config5(n_streams=4, seconds=0.02)
     for field, index, value, status in (("sample_rate", 2, 12345, abi.E_INVALID_ARG), ("bit_depth", 1, 20, abi.E_INVALID_DESC),
                                         ("out_fmt", 0, abi.OUT_PLANAR32_BE, abi.E_INVALID_ARG),
-                                        ("chunk_frames", 3, 0, abi.E_INVALID_ARG)):
+                                        ("chunk_frames", 3, 0, abi.E_INVALID_ARG), ("channels", 1, 33, abi.E_INVALID_ARG),
+                                        ("channels", 2, 257, abi.E_INVALID_ARG), ("chunk_frames", 0, 0x80000001, abi.E_INVALID_ARG)):
         bad = w.streams.copy()
         bad[field][index] = value
         with pytest.raises(capi.OhpError) as e:
