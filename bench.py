@@ -539,7 +539,7 @@ def main():
                 "traffic": recorded_traffic(main_name, algo_bytes), "peak_source": peak_src,
                 "kernel": "ohp::ramp_convert_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_ms": ms_per_step}
-    from_specs = {"api": "ohp_run_streams_device (specs + events + PCM in HBM -> bytes in HBM: one schedule walk per stream into bounded regions, in slices beside ramp_convert_kernel)",
+    from_specs = {"api": "ohp_run_streams_device (specs + events + PCM in HBM -> bytes in HBM: every stream walked in five stretches on a second stream, ramp_convert_kernel on stretch k beside the walk of stretch k + 1)",
                   "ms_per_step": ms_from_specs, "value": frames_per_step * world / (ms_from_specs * 1e-3), "unit": UNIT,
                   "frac": algo_bytes / (ms_from_specs * 1e-3) / 1e9 / peak, "same_checksums": from_specs_same}
 
@@ -721,7 +721,7 @@ def main():
                     "host_schedule_build_s": (round(host_sched_s, 3) if host_sched_s is not None else None),
                     "device_schedule_build_s": round(schedule_s_main, 4),
                     "inflight_chunks_per_cta": inflight_cap,
-                    "descriptors": "built on the GPU (ohp_schedule_count/emit_device), identical to the host model's"})
+                    "descriptors": "value: built on the GPU before the timed region (ohp_schedule_count_device + ohp_schedule_emit_device), identical to the host model's; value_from_specs: built inside it"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg, "clocks": clocks,

@@ -84,6 +84,10 @@ struct ohp_context
     uint64_t* d_counts = nullptr; uint64_t d_counts_cap = 0;  // ohp_run_streams_device: exact playables per stream
     cudaStream_t sched_stream = nullptr;                         // ... the walks run here, beside ramp_convert_kernel
     std::vector<cudaEvent_t> sched_events;
+    ohp::sched::WalkState* d_walk[2] = {nullptr, nullptr};       // ... where every stream's walk stopped, ping-pong between stretches
+    uint64_t d_walk_cap[2] = {0, 0};
+    uint64_t* d_bases = nullptr;                                 // ... [kMaxStretches + 1] descriptors in front of each stretch
+    uint64_t* h_bases = nullptr;                                 // pinned copy
     std::vector<uint64_t> h_begin, h_outb;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timing = false;
@@ -106,7 +110,12 @@ struct ohp_context
 
 namespace ohp {
 
-constexpr size_t kScheduleWarpTeamMaxStreams = 32768;
+// A warp per stream while the warps still fit the GPU at once (148 SMs x 12 resident warps of schedule_kernel), a thread
+// per stream beyond: with more warps than that the walks go in waves and the 32-fold redundant general path is paid in
+// issue slots (round 2, configs[2]: 2.97 -> 2.80 ms specs-to-bytes, configs[3]: 5.96 -> 4.47 ms; profiles/README.md).
+constexpr size_t kScheduleWarpTeamMaxStreams = 2048;
+constexpr uint32_t kMaxStretches = 12;
+constexpr uint32_t kDefaultStretches = 5;
 
 static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess)
 {
@@ -629,6 +638,10 @@ int ohp_destroy(ohp_context* ctx)
     if (ctx->d_begin) (void)cudaFree(ctx->d_begin);
     if (ctx->d_outb) (void)cudaFree(ctx->d_outb);
     if (ctx->d_counts) (void)cudaFree(ctx->d_counts);
+    if (ctx->d_walk[0]) (void)cudaFree(ctx->d_walk[0]);
+    if (ctx->d_walk[1]) (void)cudaFree(ctx->d_walk[1]);
+    if (ctx->d_bases) (void)cudaFree(ctx->d_bases);
+    if (ctx->h_bases) (void)cudaFreeHost(ctx->h_bases);
     if (ctx->sched_stream) { (void)cudaStreamSynchronize(ctx->sched_stream); (void)cudaStreamDestroy(ctx->sched_stream); }
     for (cudaEvent_t e : ctx->sched_events) (void)cudaEventDestroy(e);
     if (ctx->h_status) (void)cudaFreeHost(ctx->h_status);
@@ -1049,6 +1062,98 @@ static int run_streams_device_two_pass(ohp_context* ctx, const ohp_stream_spec* 
     return launch(ctx, ctx->d_descs, (size_t)total, d_in, in_bytes, d_out, out_bytes, st);
 }
 
+// THE WALK IN STRETCHES, BESIDE ramp_convert_kernel (the default).  A stream's walk is a chain of dependent steps -- it
+// takes as long as the stream is long however many streams there are -- so the way to hide it is not to slice the batch
+// by streams but by TIME: every stream is walked a stretch of its length at a time (1/16, 1/16, 1/8, 1/4, 1/2 of it,
+// sched::stretch_stop_frame), the walks leave their state in HBM between stretches (sched::WalkState), and
+// ramp_convert_kernel runs on stretch k while stretch k + 1 is walked on the schedule stream.  Each stretch is count +
+// scan + emit (the exact two passes: descriptors compact, no padding), laid out behind the previous stretch's by a base
+// the scan carries forward on the device; the host only waits for each stretch's total to size the launch.  What is
+// left in front of ramp_convert_kernel is the walk of the first sixteenth.
+static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
+                                        const ohp_ramp_event* d_events, size_t n_events,
+                                        const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
+                                        uint64_t* d_stream_out_bytes, uint64_t* total_chunks, uint32_t n_stretches, cudaStream_t st,
+                                        bool* overflowed)
+{
+    int rc;
+    *overflowed = false;
+    // room for the descriptors: the closed-form bound, summed on the device (the one host round trip up front)
+    sched::bound_kernel<<<(unsigned)((n_streams + 127) / 128), 128, 0, st>>>(d_streams, n_streams, d_events, n_events, ctx->d_begin);
+    OHP_CUDA(ctx, cudaGetLastError());
+    sched::scan_kernel<<<1, 1024, 0, st>>>(ctx->d_begin, n_streams);
+    OHP_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    if (!ctx->h_bases) OHP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_bases), (kMaxStretches + 2) * sizeof(uint64_t), cudaHostAllocDefault));
+    if (!ctx->d_bases) OHP_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_bases), (kMaxStretches + 1) * sizeof(uint64_t)));
+    OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_bases + kMaxStretches + 1, ctx->d_begin + n_streams, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    OHP_CUDA(ctx, cudaMemsetAsync(ctx->d_bases, 0, sizeof(uint64_t), st));
+    OHP_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t room = ctx->h_bases[kMaxStretches + 1];
+    if (room > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) {
+        OHP_CUDA(ctx, cudaDeviceSynchronize()); // the buffer may still be read by a launch enqueued earlier on another stream
+        if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, room * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+    }
+    for (int k = 0; k < 2; k++) {
+        if ((rc = grow(ctx, ctx->d_walk[k], ctx->d_walk_cap[k], (uint64_t)n_streams * sizeof(sched::WalkState))) != OHP_OK) return rc;
+    }
+    while (ctx->sched_events.size() < 2 * (size_t)n_stretches + 1) {
+        cudaEvent_t e;
+        OHP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->sched_events.push_back(e);
+    }
+    if (!ctx->sched_stream) OHP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sched_stream, cudaStreamNonBlocking));
+    // the schedule stream starts behind whatever the caller's stream holds so far (specs, events and PCM may just have arrived)
+    OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * n_stretches], st));
+    OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_events[2 * n_stretches], 0));
+    const int team = schedule_team(n_streams);
+    const unsigned grid = sched::schedule_grid(n_streams, team);
+    for (uint32_t j = 0; j < n_stretches; j++) {
+        sched::ScheduleParams p{};
+        p.streams = d_streams; p.n_streams = n_streams; p.events = d_events; p.n_events = n_events;
+        p.status = ctx->d_status + 2;
+        p.state_in = j ? ctx->d_walk[j & 1] : nullptr;
+        p.state_out = ctx->d_walk[(j + 1) & 1];
+        p.stretch = j; p.n_stretches = n_stretches;
+        p.chunk_count = ctx->d_begin; p.out_bytes = d_stream_out_bytes;
+        if (team == 32) sched::schedule_kernel<false, 32><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
+        else sched::schedule_kernel<false, 1><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
+        OHP_CUDA(ctx, cudaGetLastError());
+        sched::scan_kernel<<<1, 1024, 0, ctx->sched_stream>>>(ctx->d_begin, n_streams, ctx->d_bases + j);
+        OHP_CUDA(ctx, cudaGetLastError());
+        OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_bases + j + 1, ctx->d_bases + j + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->sched_stream));
+        OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * j], ctx->sched_stream));
+        p.chunk_count = nullptr; p.out_bytes = nullptr; p.state_out = nullptr;
+        p.chunk_begin = ctx->d_begin; p.descs = ctx->d_descs; p.info = nullptr;
+        p.descs_cap = ctx->d_descs_cap / sizeof(ohp_chunk_desc);
+        if (team == 32) sched::schedule_kernel<true, 32><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
+        else sched::schedule_kernel<true, 1><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
+        OHP_CUDA(ctx, cudaGetLastError());
+        OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * j + 1], ctx->sched_stream));
+        ctx->launches += 3;
+    }
+    ctx->h_bases[0] = 0;
+    for (uint32_t j = 0; j < n_stretches; j++) {
+        OHP_CUDA(ctx, cudaEventSynchronize(ctx->sched_events[2 * j]));
+        const uint64_t lo = ctx->h_bases[j], hi = ctx->h_bases[j + 1];
+        if (hi > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) { // more playables than the bound allowed for: nothing was written for them
+            *overflowed = true;
+            break;
+        }
+        if (hi == lo) continue;
+        OHP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sched_events[2 * j + 1], 0));
+        if ((rc = launch(ctx, ctx->d_descs + lo, (size_t)(hi - lo), d_in, in_bytes, d_out, out_bytes, st)) != OHP_OK) return rc;
+    }
+    // a stream the walk refused (spec, ASSERT, stack depth) fails the call
+    const int src = schedule_status(ctx, ctx->sched_stream);
+    if (src != OHP_OK || *overflowed) {
+        OHP_CUDA(ctx, cudaStreamSynchronize(st));
+        return src;
+    }
+    if (total_chunks) *total_chunks = ctx->h_bases[n_stretches];
+    return OHP_OK;
+}
+
 int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                            const ohp_ramp_event* d_events, size_t n_events,
                            const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
@@ -1066,6 +1171,20 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
     const char* one_walk_env = std::getenv("OHP_ONE_WALK"); // OHP_ONE_WALK=0: count + scan + emit as in round 1
     const bool one_walk = !one_walk_env || std::atoi(one_walk_env) != 0;
     if (!one_walk) {
+        return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
+                                           d_stream_out_bytes, total_chunks, st);
+    }
+    uint32_t n_stretches = kDefaultStretches; // OHP_STRETCHES=k: k stretches; 0: the one-walk-into-regions path below
+    if (const char* e = std::getenv("OHP_STRETCHES")) {
+        const long v = std::atol(e);
+        n_stretches = v < 0 ? 0u : (v > (long)kMaxStretches ? kMaxStretches : (uint32_t)v);
+    }
+    if (n_stretches != 0) {
+        bool overflowed = false;
+        rc = run_streams_device_stretched(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
+                                          d_stream_out_bytes, total_chunks, n_stretches, st, &overflowed);
+        if (!overflowed) return rc;
+        if (rc != OHP_OK) return rc;
         return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
                                            d_stream_out_bytes, total_chunks, st);
     }

@@ -31,6 +31,13 @@ struct ScheduleParams
     // ONE-WALK mode (regions from stream_chunk_bound): EMIT also reports what COUNT would have, and fills each region's tail
     uint64_t first_stream;     // the slice [first_stream, first_stream + n_streams) of the batch is walked
     uint64_t* counts_out;      // [all streams] exact playables per stream (null: two-pass mode)
+    // STRETCH mode (n_stretches != 0): every stream is walked from where stretch - 1 stopped to stretch_stop_frame();
+    // COUNT leaves the state for the next stretch in state_out, EMIT re-walks the stretch from state_in.  chunk_count /
+    // chunk_begin are per stretch: descriptors come out compact, stretch after stretch, streams in order inside each.
+    const WalkState* state_in; // [n_streams], null for stretch 0
+    WalkState* state_out;      // [n_streams], COUNT only
+    uint32_t stretch, n_stretches;
+    uint64_t descs_cap;        // EMIT: descriptors the buffer holds; a stream whose stretch would end beyond writes nothing
 };
 
 constexpr uint32_t kErrBound = 4u; // a stream has more playables than stream_chunk_bound allowed for: the caller takes two passes
@@ -58,11 +65,20 @@ __global__ void __launch_bounds__(128) schedule_kernel(const ScheduleParams p)
     const uint64_t s = p.first_stream + local;
     const ohp_stream_spec sp = p.streams[s];
     uint64_t nChunks, outBytes;
-    ohp_chunk_desc* descs = EMIT ? p.descs + p.chunk_begin[s] : nullptr;
-    ohp_chunk_info* info = (EMIT && p.info) ? p.info + p.chunk_begin[s] : nullptr;
+    const bool stretched = p.n_stretches != 0;
+    const WalkState* in = (stretched && p.state_in != nullptr) ? p.state_in + s : nullptr;
+    WalkState* out = (stretched && !EMIT) ? p.state_out + s : nullptr;
+    const uint64_t stop = stretched ? stretch_stop_frame(sp.total_frames, p.stretch, p.n_stretches) : ~0ull;
+    const uint64_t before = (in != nullptr && in->phase != 0) ? in->nChunks : 0; // playables of the stretches in front
+    // EMIT: the walk indexes a stream's playables from its start; this stretch's first one goes to chunk_begin[s]
+    ohp_chunk_desc* descs = EMIT ? p.descs + p.chunk_begin[s] - before : nullptr;
+    ohp_chunk_info* info = (EMIT && p.info) ? p.info + p.chunk_begin[s] - before : nullptr;
     const bool regions = EMIT && p.counts_out != nullptr;
-    const uint64_t limit = regions ? p.chunk_begin[s + 1] - p.chunk_begin[s] : ~0ull;
-    uint32_t rc = run_stream<EMIT, TEAM, true>(sp, p.events, p.n_events, descs, info, nChunks, outBytes, lane, limit);
+    uint64_t limit = regions ? p.chunk_begin[s + 1] - p.chunk_begin[s] : ~0ull;
+    if (EMIT && stretched) { // a refused stream counted 0: it writes nothing
+        limit = p.chunk_begin[s + 1] <= p.descs_cap ? before + (p.chunk_begin[s + 1] - p.chunk_begin[s]) : before;
+    }
+    uint32_t rc = run_stream<EMIT, TEAM, true>(sp, p.events, p.n_events, descs, info, nChunks, outBytes, lane, limit, in, out, stop);
     if (regions) {
         if (rc == kOk && nChunks > limit) rc = kErrBound;
         // the rest of the region: zero-byte descriptors (all lanes of the team, two 128-bit stores each)
@@ -74,9 +90,12 @@ __global__ void __launch_bounds__(128) schedule_kernel(const ScheduleParams p)
     if (rc != kOk) {
         atomicOr(&p.status[0], 1u << rc);
         atomicMax(&p.status[1], 0xffffffffu - (uint32_t)(s > 0xfffffffeull ? 0xfffffffeull : s));
+        if (out != nullptr) { // the call fails; later stretches find this stream over
+            out->phase = 2; out->nChunks = before; out->outBytes = 0;
+        }
     }
     if (!EMIT) {
-        p.chunk_count[s] = nChunks;
+        p.chunk_count[s] = (stretched && rc == kOk) ? nChunks - before : nChunks;
         if (p.out_bytes) p.out_bytes[s] = outBytes;
     }
     else if (regions) {
@@ -93,11 +112,13 @@ inline unsigned schedule_grid(uint64_t n_streams, int team)
 }
 
 // In-place exclusive scan of counts[0..n) into begin[0..n] (begin has n+1 entries; begin[n] = total).  One CTA.
-__global__ void __launch_bounds__(1024) scan_kernel(uint64_t* begin, uint64_t n)
+// base (may be null): base[0] is added to every entry and base[1] = base[0] + total is left for the next scan -- how the
+// stretches of ohp_run_streams_device lay their descriptors out one after the other without the host in between.
+__global__ void __launch_bounds__(1024) scan_kernel(uint64_t* begin, uint64_t n, uint64_t* base = nullptr)
 {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = base ? base[0] : 0;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint64_t base = 0; base < n; base += 1024) {
@@ -125,7 +146,10 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint64_t* begin, uint64_t n)
         if (threadIdx.x == 1023) carry = before + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) begin[n] = carry;
+    if (threadIdx.x == 0) {
+        begin[n] = carry;
+        if (base) base[1] = carry;
+    }
 }
 
 } // namespace sched

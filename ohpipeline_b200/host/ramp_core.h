@@ -57,11 +57,29 @@ OHP_HD bool ramp_is_valid(const RampPod& r)
     }
 }
 
-// (a * b + add) / d in 64 bits, as the reference computes it; 32-bit divide when the numerator fits (the GPU has no
-// 64-bit divider: __udivdi3-style code is ~10x the cost of a 32-bit divide, and most ramp steps fit).
-OHP_HD uint32_t mul_add_div(uint32_t a, uint32_t b, uint32_t add, uint32_t d)
+// (a * b + add) / d in 64 bits, as the reference computes it.  The GPU has no 64-bit divider (a __udivdi3-style call
+// is a dependent chain of some hundreds of cycles, and the ramp recurrence -- one such division per message, each
+// needing the previous one's result -- is what a stream's schedule walk waits on).  On the device: where the caller has 1 / d at hand (aInv: bulk_step knows the divisors of a run before it knows
+// the numerators) and the numerator is below 2^53 (exact in a double), quotient = trunc(num * aInv) corrected by the
+// remainder: the product is off by less than 2^-20 (quotient < 2^32, two roundings of 2^-53 each), so the truncation
+// is at most one off either way and one multiply-subtract settles it -- exact, no rounding assumption left.  Otherwise a
+// 32-bit divide when the numerator fits, the 64-bit one when it does not.  (Computing
+// 1 / d in here instead was measured in code size: 85 inlined reciprocal sequences, +20 % SASS in a kernel that is
+// already larger than the instruction cache.)
+OHP_HD uint32_t mul_add_div(uint32_t a, uint32_t b, uint32_t add, uint32_t d, double aInv = 0.0)
 {
     const uint64_t num = a * (uint64_t)b + add;
+#if defined(__CUDA_ARCH__)
+    if (aInv != 0.0 && (num >> 53) == 0) {
+        uint64_t q = (uint64_t)__double2ll_rz((double)(int64_t)num * aInv);
+        int64_t r = (int64_t)num - (int64_t)(q * d);
+        if (r < 0) { q--; r += d; }
+        else if (r >= (int64_t)d) { q++; r -= d; }
+        if ((uint64_t)r < d) return (uint32_t)q; // always, unless aInv was not 1 / d: then the plain division below
+    }
+#else
+    (void)aInv;
+#endif
     if ((num >> 32) == 0) return (uint32_t)num / d;
     return (uint32_t)(num / d);
 }

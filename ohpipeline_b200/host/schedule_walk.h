@@ -562,6 +562,21 @@ struct Lookahead
     uint32_t head, count;
 };
 
+// A walk can stop between two messages and go on later (ohp_run_streams_device walks every stream a stretch of its
+// length at a time, so that ramp_convert_kernel can start on the first stretch while the rest is still being walked):
+// everything walk_stream keeps between messages.  The stages' stacks are not in here -- they are empty whenever a message
+// has been fed through (see walk_stream).
+struct WalkState
+{
+    Stage st[kStages];
+    Cursor cur;
+    core::CodecSource source;
+    Lookahead la;
+    uint64_t nChunks, outBytes;
+    uint32_t blockFill;
+    uint32_t phase;        // 0: not started, 1: stopped at aStopFrame, 2: the stream is over
+};
+
 OHP_HD void lookahead_fill(core::CodecSource& src, Lookahead& la)
 {
     if (la.head != la.count) return;
@@ -661,7 +676,45 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
     uint32_t minePos[kBulk / STRIDE];   // frames of the run in front of the message
     uint32_t posFrames = 0;
     uint64_t posJiffies = 0;
-    if (!uniform || ramping) {
+    if (uniform && ramping) {
+        // THE RAMP RECURRENCE, LEAN.  Every message of the run is fresh (no ramp of its own), whole, and lies inside
+        // the ramp, so MsgAudio::SetRamp / Ramp::Set (msg_set_ramp / core::ramp_set) come down to
+        //     delta = ceil(distance * size / remaining);  end = current -+ delta;  remaining -= size
+        // with distance = how far the ramp still has to go.  This chain -- message k + 1 starts where k ended -- is
+        // what a stream's walk waits on (one warp per stream: nothing else to issue meanwhile), so nothing but the
+        // chain is left in the loop: the divisors are known up front (what is left of the ramp shrinks by one message
+        // each time), so on the device the warp takes their 32 reciprocals side by side first and a step is one
+        // multiply, one truncation and the exact remainder fix-up (core::mul_add_div).  Anything else -- a step of 0
+        // (the reference ASSERTs: Ramp::DoValidate), the ramp arriving (delta == distance: "finished early",
+        // Msg.cpp:2037-2043) or overshooting -- ends the run in front of that message; the general path decides it.
+        const bool down = rMode == RampingDown;
+        const uint32_t dir = down ? core::kDirDown : core::kDirUp;
+        double myInv = 0.0;
+#if defined(__CUDA_ARCH__)
+        if (STRIDE == kBulk && rRemaining > cx.lane * size) myInv = 1.0 / (double)(rRemaining - cx.lane * size);
+#endif
+        uint32_t done = 0;
+        for (uint32_t k = 0; k < n; k++) {
+            double inv = 0.0;
+#if defined(__CUDA_ARCH__)
+            if (STRIDE == kBulk) inv = __shfl_sync(0xffffffffu, myInv, (int)k);
+#endif
+            const uint32_t distance = down ? rCurrent : core::kRampMax - rCurrent;
+            const uint32_t delta = core::mul_add_div(distance, size, rRemaining - 1, rRemaining, inv);
+            if (delta == 0 || delta >= distance) break;
+            const uint32_t end = down ? rCurrent - delta : rCurrent + delta;
+            if (k % STRIDE == cx.lane) {
+                core::RampPod& r = mine[k / STRIDE];
+                r.start = rCurrent; r.end = end; r.direction = dir; r.enabled = 1;
+            }
+            rCurrent = end;
+            rRemaining -= size;
+            done = k + 1;
+        }
+        n = done;
+        if (n == 0) return 0;
+    }
+    else if (!uniform) {
         const uint32_t dir = rMode == RampingDown ? core::kDirDown : core::kDirUp;
         uint32_t done = 0;
         for (uint32_t k = 0; k < n; k++) {
@@ -777,20 +830,44 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
     return n;
 }
 
+// Where stretch aIndex of aCount ends, as a frame of the source: stretches double in length towards the end of the stream
+// (1/16, 1/16, 1/8, 1/4, 1/2 for five), so that what consumes the descriptors can start after a sixteenth of the walk and
+// every later stretch is walked while a shorter one is being consumed.  The last stretch runs to the end of the stream.
+OHP_HD uint64_t stretch_stop_frame(uint64_t aTotalFrames, uint32_t aIndex, uint32_t aCount)
+{
+    if (aIndex + 1 >= aCount) return ~0ull;
+    const uint32_t shift = aCount - 1 - aIndex; // 2^-shift of the stream lies in front of this stop
+    return shift >= 64 ? 0 : (aTotalFrames >> shift);
+}
+
 // One stream's walk.  The per-stage queues of stage_chain.h only ever grow at the front while a stage is being served
 // and are drained before the stage returns, so each is a stack; Feed()'s recursion becomes: carry the message down
 // the remaining stages (in registers), hand it to the driver, then resume with the top of the deepest non-empty stack.
 // A team of STRIDE threads (device: a warp, or 1; host: 1) walks the stream holding identical state; they differ only
 // in cx.lane, i.e. in which messages of a bulk step they emit.  BULK = false is the message-at-a-time walk alone.
+// aIn / aOut / aStopFrame: the walk in stretches.  aIn (phase 1) is where an earlier call stopped; the walk stops in front
+// of the first message that starts at or after frame aStopFrame of the source and leaves its state in aOut (may be null:
+// a pass that only re-walks a stretch).  The playables' indices and output offsets run on across stretches.
 template <bool EMIT, int STRIDE, bool BULK>
-OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
+OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx, const WalkState* aIn = nullptr, WalkState* aOut = nullptr,
+                            uint64_t aStopFrame = ~0ull)
 {
     Packed stack[kStages][kStackDepth];
     Stage st[kStages];
+    const bool resume = aIn != nullptr && aIn->phase != 0;
+    if (resume && aIn->phase == 2) { // nothing left of this stream
+        cx.nChunks = aIn->nChunks; cx.outBytes = aIn->outBytes;
+        if (aOut != nullptr && cx.lane == 0 && aOut != aIn) *aOut = *aIn;
+        return kOk;
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < kStages; i++) {
+        if (resume) {
+            st[i] = aIn->st[i];
+            continue;
+        }
         st[i].pos = 0; st[i].mode = Running; st[i].current = core::kRampMax; st[i].remaining = 0; st[i].maxMsg = 0;
         st[i].attenuation = OHP_UNITY_ATTENUATION; st[i].depth = 0;
         st[i].elem = stage_element(cx, (uint32_t)i);
@@ -805,7 +882,7 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
     for (int i = 0; i < kStages; i++) {
         if (st[i].elem == ElemBad) return kErrSpec;
     }
-    if (sp.chunk_frames == 0 || sp.chunk_frames * cx.frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return kErrSpec;
+    if (sp.chunk_frames == 0 || (uint64_t)sp.chunk_frames * cx.frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return kErrSpec;
 
     // stage_chain.h Feed(0, item)
     auto feed = [&](const Msg& first) -> uint32_t {
@@ -839,14 +916,34 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
 
     // stage_chain.h Run()
     Cursor cur;
-    cur.frame = 0;
-    cur.srcJiffies = 0;
-    seek_silence(cx, cur, 0);
     core::CodecSource source;
-    core::codec_source_init(source, sp.chunk_frames, sp.codec_read_frames, cx.frameBytes, cx.jps, sp.total_frames);
     Lookahead la;
-    la.head = la.count = 0;
+    if (resume) {
+        cur = aIn->cur; source = aIn->source; la = aIn->la;
+        cx.nChunks = aIn->nChunks; cx.outBytes = aIn->outBytes; cx.blockFill = aIn->blockFill;
+    }
+    else {
+        cur.frame = 0;
+        cur.srcJiffies = 0;
+        seek_silence(cx, cur, 0);
+        core::codec_source_init(source, sp.chunk_frames, sp.codec_read_frames, cx.frameBytes, cx.jps, sp.total_frames);
+        la.head = la.count = 0;
+    }
+    auto leave = [&](uint32_t aPhase) {
+        if (aOut == nullptr || cx.lane != 0) return;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < kStages; i++) aOut->st[i] = st[i];
+        aOut->cur = cur; aOut->source = source; aOut->la = la;
+        aOut->nChunks = cx.nChunks; aOut->outBytes = cx.outBytes; aOut->blockFill = cx.blockFill;
+        aOut->phase = aPhase;
+    };
     for (;;) {
+        if (cur.frame >= aStopFrame) { // the stages' stacks are empty here: every message fed so far went all the way through
+            leave(1);
+            return kOk;
+        }
         if (BULK) {
             uint32_t e;
             const uint32_t n = source.read == 0 ? bulk_step<EMIT, STRIDE, true>(sp, cx, st, source, la, cur, e)
@@ -884,6 +981,7 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
         cur.frame += frames;
         cur.srcJiffies += (uint64_t)frames * cx.jps;
     }
+    leave(2);
     return kOk;
 }
 
@@ -892,7 +990,8 @@ OHP_HD uint32_t walk_stream(const ohp_stream_spec& sp, StreamCtx& cx)
 template <bool EMIT, int STRIDE = 1, bool BULK = true>
 OHP_HD uint32_t run_stream(const ohp_stream_spec& sp, const ohp_ramp_event* aEvents, uint64_t aNumEvents,
                            ohp_chunk_desc* aDescs, ohp_chunk_info* aInfo, uint64_t& aNumChunks, uint64_t& aOutBytes,
-                           uint32_t aLane = 0, uint64_t aLimit = ~0ull)
+                           uint32_t aLane = 0, uint64_t aLimit = ~0ull,
+                           const WalkState* aIn = nullptr, WalkState* aOut = nullptr, uint64_t aStopFrame = ~0ull)
 {
     aNumChunks = 0;
     aOutBytes = 0;
@@ -916,7 +1015,7 @@ OHP_HD uint32_t run_stream(const ohp_stream_spec& sp, const ohp_ramp_event* aEve
     cx.descs = EMIT ? aDescs : nullptr;
     cx.info = EMIT ? aInfo : nullptr;
     cx.limit = aLimit;
-    const uint32_t rc = walk_stream<EMIT, STRIDE, BULK>(sp, cx);
+    const uint32_t rc = walk_stream<EMIT, STRIDE, BULK>(sp, cx, aIn, aOut, aStopFrame);
     if (rc != kOk) return rc;
     aNumChunks = cx.nChunks;
     aOutBytes = cx.outBytes;
@@ -940,7 +1039,7 @@ OHP_HD uint64_t stream_chunk_bound(const ohp_stream_spec& sp, const ohp_ramp_eve
     if ((uint64_t)sp.first_event + sp.num_events > aNumEvents) return 0;
     const uint32_t jps = core::jiffies_per_sample_or_zero(sp.sample_rate);
     const uint64_t frameBytes = (uint64_t)sp.channels * (sp.bit_depth / 8u);
-    if (jps == 0 || frameBytes == 0 || sp.chunk_frames == 0 || frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return 0;
+    if (jps == 0 || frameBytes == 0 || sp.chunk_frames == 0 || (uint64_t)sp.chunk_frames * frameBytes > OHP_MAX_PCM_CHUNK_BYTES) return 0;
     const ohp_ramp_event* ev = aEvents + sp.first_event;
     uint64_t msgs = (sp.total_frames + sp.chunk_frames - 1) / sp.chunk_frames;
     uint64_t largest = (uint64_t)sp.chunk_frames * jps;           // jiffies of the largest message that can enter a stage
