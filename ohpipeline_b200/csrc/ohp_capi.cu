@@ -114,8 +114,8 @@ namespace ohp {
 // per stream beyond: with more warps than that the walks go in waves and the 32-fold redundant general path is paid in
 // issue slots (round 2, configs[2]: 2.97 -> 2.80 ms specs-to-bytes, configs[3]: 5.96 -> 4.47 ms; profiles/README.md).
 constexpr size_t kScheduleWarpTeamMaxStreams = 2048;
-constexpr uint32_t kMaxStretches = 12;
-constexpr uint32_t kDefaultStretches = 5;
+constexpr uint32_t kMaxStretches = 16;
+constexpr uint32_t kDefaultStretches = 8;
 
 static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess)
 {
@@ -890,7 +890,7 @@ int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams
         OHP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }
-    sched::scan_kernel<<<1, 1024, 0, st>>>(d_chunk_begin, n_streams);
+    sched::scan_kernel<<<1, sched::kScanThreads, 0, st>>>(d_chunk_begin, n_streams);
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     uint64_t* h_total = reinterpret_cast<uint64_t*>(ctx->h_status + 14); // 8-byte aligned tail of the pinned status block
@@ -1064,12 +1064,12 @@ static int run_streams_device_two_pass(ohp_context* ctx, const ohp_stream_spec* 
 
 // THE WALK IN STRETCHES, BESIDE ramp_convert_kernel (the default).  A stream's walk is a chain of dependent steps -- it
 // takes as long as the stream is long however many streams there are -- so the way to hide it is not to slice the batch
-// by streams but by TIME: every stream is walked a stretch of its length at a time (1/16, 1/16, 1/8, 1/4, 1/2 of it,
+// by streams but by TIME: every stream is walked a stretch of its length at a time (an eighth of it,
 // sched::stretch_stop_frame), the walks leave their state in HBM between stretches (sched::WalkState), and
 // ramp_convert_kernel runs on stretch k while stretch k + 1 is walked on the schedule stream.  Each stretch is count +
 // scan + emit (the exact two passes: descriptors compact, no padding), laid out behind the previous stretch's by a base
 // the scan carries forward on the device; the host only waits for each stretch's total to size the launch.  What is
-// left in front of ramp_convert_kernel is the walk of the first sixteenth.
+// left in front of ramp_convert_kernel is the walk of the first stretch.
 static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                                         const ohp_ramp_event* d_events, size_t n_events,
                                         const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
@@ -1081,7 +1081,7 @@ static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec*
     // room for the descriptors: the closed-form bound, summed on the device (the one host round trip up front)
     sched::bound_kernel<<<(unsigned)((n_streams + 127) / 128), 128, 0, st>>>(d_streams, n_streams, d_events, n_events, ctx->d_begin);
     OHP_CUDA(ctx, cudaGetLastError());
-    sched::scan_kernel<<<1, 1024, 0, st>>>(ctx->d_begin, n_streams);
+    sched::scan_kernel<<<1, sched::kScanThreads, 0, st>>>(ctx->d_begin, n_streams);
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     if (!ctx->h_bases) OHP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_bases), (kMaxStretches + 2) * sizeof(uint64_t), cudaHostAllocDefault));
@@ -1119,7 +1119,7 @@ static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec*
         if (team == 32) sched::schedule_kernel<false, 32><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
         else sched::schedule_kernel<false, 1><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
         OHP_CUDA(ctx, cudaGetLastError());
-        sched::scan_kernel<<<1, 1024, 0, ctx->sched_stream>>>(ctx->d_begin, n_streams, ctx->d_bases + j);
+        sched::scan_kernel<<<1, sched::kScanThreads, 0, ctx->sched_stream>>>(ctx->d_begin, n_streams, ctx->d_bases + j);
         OHP_CUDA(ctx, cudaGetLastError());
         OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_bases + j + 1, ctx->d_bases + j + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->sched_stream));
         OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * j], ctx->sched_stream));
@@ -1191,7 +1191,7 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
     // 1. regions: bound per stream, exclusive scan, their offsets to the host (the one synchronisation of the call)
     sched::bound_kernel<<<(unsigned)((n_streams + 127) / 128), 128, 0, st>>>(d_streams, n_streams, d_events, n_events, ctx->d_begin);
     OHP_CUDA(ctx, cudaGetLastError());
-    sched::scan_kernel<<<1, 1024, 0, st>>>(ctx->d_begin, n_streams);
+    sched::scan_kernel<<<1, sched::kScanThreads, 0, st>>>(ctx->d_begin, n_streams);
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     ctx->h_begin.resize(n_streams + 1);

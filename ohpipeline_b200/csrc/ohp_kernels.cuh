@@ -75,11 +75,17 @@ namespace ohp {
 #ifndef OHP_DEFER_RELEASE
 #define OHP_DEFER_RELEASE 2 /* 0: never, 1: always, 2: serial-placement instantiation only (see the consumer loop) */
 #endif
+#ifndef OHP_ANY_UNITS
+#define OHP_ANY_UNITS 1     /* 4-subsample units a lane of the compact general transform works on at once; 2 measured
+                               WORSE (configs[3] 0.905 -> 0.87, stress mix 0.40 -> 0.38: +7 KB of code in four functions
+                               that are hot together costs more in instruction fetch than the second chain gains) */
+#endif
 #ifndef OHP_DYNAMIC
 #define OHP_DYNAMIC 1       /* 1: consumer warps take chunks by ticket (first come, first served); 0: chunk k -> warp k % warps */
 #endif
 constexpr uint32_t kIssueWidth = OHP_ISSUE_WIDTH;     // chunks the loader warp can place and start in one round (one per lane)
 constexpr uint32_t kSerialWidth = 8;                  // ... and at most this many per round in serial-placement mode
+constexpr int kAnyUnits = OHP_ANY_UNITS;
 constexpr int kGroupsPerStep = OHP_GROUPS_PER_STEP; // independent 16-subsample groups a lane works on at once
 constexpr uint32_t kChunkBlock = OHP_CHUNK_BLOCK;     // chunks are dealt to CTAs in runs of (up to) this many consecutive chunks
 constexpr uint32_t kMinChunkBlock = 4;                // ... shortened for small batches so that every CTA gets work
@@ -896,26 +902,38 @@ __device__ __noinline__ void transform_any(const ChunkRec& cr, uint32_t table, u
     const uint32_t units = cr.units;
     const uint32_t src = in_addr + (cr.head & ~3u);
     const uint32_t fshift = (cr.head & 3u) * 8u;
-    for (uint32_t u0 = 0; u0 < units; u0 += 32) {
-        const uint32_t u = u0 + lane;
-        uint32_t raw[B + 1], r[B + 1], w[B];
-        const uint32_t a = src + u * (4u * B);
-        if (u < units) {
+    // kAnyUnits units per lane and step, independent of each other (1: see OHP_ANY_UNITS)
+    for (uint32_t u0 = 0; u0 < units; u0 += 32 * kAnyUnits) {
+        uint32_t raw[kAnyUnits][B + 1], r[kAnyUnits][B + 1], w[kAnyUnits][B];
 #pragma unroll
-            for (int i = 0; i <= B; i++) raw[i] = lds32(a + 4u * i);
-        } else {
+        for (int k = 0; k < kAnyUnits; k++) {
+            const uint32_t u = u0 + 32 * k + lane;
+            const uint32_t a = src + u * (4u * B);
+            if (u < units) {
 #pragma unroll
-            for (int i = 0; i <= B; i++) raw[i] = 0;
+                for (int i = 0; i <= B; i++) raw[k][i] = lds32(a + 4u * i);
+            } else {
+#pragma unroll
+                for (int i = 0; i <= B; i++) raw[k][i] = 0;
+            }
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < B; i++) r[i] = __funnelshift_r(raw[i], raw[i + 1], fshift);
-        r[B] = 0;
-        process_unit<B, kChmAny>(cx, rr, u, r, w);
-        if (u < units) {
-            const uint32_t d = in_addr + u * (4u * B);
+        for (int k = 0; k < kAnyUnits; k++) {
+            const uint32_t u = u0 + 32 * k + lane;
 #pragma unroll
-            for (int i = 0; i < B; i++) sts32(d + 4u * i, w[i]);
+            for (int i = 0; i < B; i++) r[k][i] = __funnelshift_r(raw[k][i], raw[k][i + 1], fshift);
+            r[k][B] = 0;
+            process_unit<B, kChmAny>(cx, rr, u, r[k], w[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kAnyUnits; k++) {
+            const uint32_t u = u0 + 32 * k + lane;
+            if (u < units) {
+                const uint32_t d = in_addr + u * (4u * B);
+#pragma unroll
+                for (int i = 0; i < B; i++) sts32(d + 4u * i, w[k][i]);
+            }
         }
     }
 }

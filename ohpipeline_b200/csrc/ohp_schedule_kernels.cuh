@@ -55,8 +55,11 @@ __global__ void __launch_bounds__(128) bound_kernel(const ohp_stream_spec* __res
 // TEAM threads walk one stream: TEAM = 32 (a warp per stream: no divergence between streams, 32 descriptors per bulk
 // step written side by side) when streams are few enough for that to fill the GPU, TEAM = 1 (a thread per stream) when
 // there are so many streams that they alone do.  All lanes of a team hold the same state; see schedule_walk.h.
+#ifndef OHP_SCHED_MIN_BLOCKS
+#define OHP_SCHED_MIN_BLOCKS 1 /* experiments: 5 caps the walk at 96 registers so that 7 of its warps fit beside ramp_convert_kernel */
+#endif
 template <bool EMIT, int TEAM>
-__global__ void __launch_bounds__(128) schedule_kernel(const ScheduleParams p)
+__global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(const ScheduleParams p)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t local = t / TEAM;
@@ -114,15 +117,19 @@ inline unsigned schedule_grid(uint64_t n_streams, int team)
 // In-place exclusive scan of counts[0..n) into begin[0..n] (begin has n+1 entries; begin[n] = total).  One CTA.
 // base (may be null): base[0] is added to every entry and base[1] = base[0] + total is left for the next scan -- how the
 // stretches of ohp_run_streams_device lay their descriptors out one after the other without the host in between.
-__global__ void __launch_bounds__(1024) scan_kernel(uint64_t* begin, uint64_t n, uint64_t* base = nullptr)
+// 256 threads, not 1024: the stretches' scans run while ramp_convert_kernel's persistent CTAs hold two thirds of every
+// SM's registers, and a 1024-thread CTA finds no SM to run on until that kernel ends (measured: the walk of stretch
+// k + 1 then waits for ramp_convert_kernel on stretch k, and the overlap is gone).
+constexpr unsigned kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(uint64_t* begin, uint64_t n, uint64_t* base = nullptr)
 {
-    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t warp_sum[kScanThreads / 32];
     __shared__ uint64_t carry;
     if (threadIdx.x == 0) carry = base ? base[0] : 0;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t base = 0; base < n; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
+    for (uint64_t first = 0; first < n; first += kScanThreads) {
+        const uint64_t i = first + threadIdx.x;
         const uint64_t v = i < n ? begin[i] : 0;
         uint64_t x = v;
         for (int o = 1; o < 32; o <<= 1) {
@@ -132,18 +139,18 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint64_t* begin, uint64_t n,
         if (lane == 31) warp_sum[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            uint64_t w = warp_sum[lane];
-            for (int o = 1; o < 32; o <<= 1) {
+            uint64_t w = lane < kScanThreads / 32 ? warp_sum[lane] : 0;
+            for (int o = 1; o < (int)(kScanThreads / 32); o <<= 1) {
                 const uint64_t y = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= (uint32_t)o) w += y;
             }
-            warp_sum[lane] = w;
+            if (lane < kScanThreads / 32) warp_sum[lane] = w;
         }
         __syncthreads();
         const uint64_t before = carry + (warp ? warp_sum[warp - 1] : 0) + (x - v);
         if (i < n) begin[i] = before;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == kScanThreads - 1) carry = before + v;
         __syncthreads();
     }
     if (threadIdx.x == 0) {

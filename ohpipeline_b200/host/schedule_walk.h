@@ -830,14 +830,14 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
     return n;
 }
 
-// Where stretch aIndex of aCount ends, as a frame of the source: stretches double in length towards the end of the stream
-// (1/16, 1/16, 1/8, 1/4, 1/2 for five), so that what consumes the descriptors can start after a sixteenth of the walk and
-// every later stretch is walked while a shorter one is being consumed.  The last stretch runs to the end of the stream.
+// Where stretch aIndex of aCount ends, as a frame of the source: stretches of equal length; the last one runs to the end
+// of the stream.  (Stretches that double in length -- start the consumer after 1/16 of the walk -- were measured first and
+// lose: beside ramp_convert_kernel only 4 of a stream-per-warp walk's warps fit on an SM, the two passes of stretch
+// k + 1 then take as long as the consumer needs for a stretch half its size, and the pipeline runs at the walk's pace.)
 OHP_HD uint64_t stretch_stop_frame(uint64_t aTotalFrames, uint32_t aIndex, uint32_t aCount)
 {
     if (aIndex + 1 >= aCount) return ~0ull;
-    const uint32_t shift = aCount - 1 - aIndex; // 2^-shift of the stream lies in front of this stop
-    return shift >= 64 ? 0 : (aTotalFrames >> shift);
+    return (aTotalFrames / aCount) * (aIndex + 1); // total_frames < 2^64 / aCount is not assumed
 }
 
 // One stream's walk.  The per-stage queues of stage_chain.h only ever grow at the front while a stage is being served

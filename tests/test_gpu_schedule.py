@@ -270,7 +270,7 @@ def test_whole_stage_for_a_batch_resident_in_hbm(ctx, port, make):
             torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("mode", ["stretches_1", "stretches_3", "stretches_12", "one_walk", "one_walk_sliced", "two_pass"])
+@pytest.mark.parametrize("mode", ["stretches_1", "stretches_3", "stretches_16", "one_walk", "one_walk_sliced", "two_pass"])
 def test_whole_stage_device_call_in_every_mode(ctx, port, mode, monkeypatch):
     """ohp_run_streams_device's default walks every stream in five stretches beside ramp_convert_kernel
     (test_whole_stage_for_a_batch_resident_in_hbm); here the other stretch counts, the one-walk-into-bounded-regions path
