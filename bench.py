@@ -539,7 +539,7 @@ def main():
                 "traffic": recorded_traffic(main_name, algo_bytes), "peak_source": peak_src,
                 "kernel": "ohp::ramp_convert_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_ms": ms_per_step}
-    from_specs = {"api": "ohp_run_streams_device (specs + events + PCM in HBM -> bytes in HBM: every stream walked in five stretches on a second stream, ramp_convert_kernel on stretch k beside the walk of stretch k + 1)",
+    from_specs = {"api": "ohp_run_streams_device (specs + events + PCM in HBM -> bytes in HBM: one schedule walk per stream into regions sized by a closed-form bound, then ramp_convert_kernel)",
                   "ms_per_step": ms_from_specs, "value": frames_per_step * world / (ms_from_specs * 1e-3), "unit": UNIT,
                   "frac": algo_bytes / (ms_from_specs * 1e-3) / 1e9 / peak, "same_checksums": from_specs_same}
 

@@ -115,7 +115,7 @@ namespace ohp {
 // issue slots (round 2, configs[2]: 2.97 -> 2.80 ms specs-to-bytes, configs[3]: 5.96 -> 4.47 ms; profiles/README.md).
 constexpr size_t kScheduleWarpTeamMaxStreams = 2048;
 constexpr uint32_t kMaxStretches = 16;
-constexpr uint32_t kDefaultStretches = 8;
+constexpr uint32_t kDefaultStretches = 0; // the one-walk path; see run_streams_device_stretched for why
 
 static int fail(ohp_context* ctx, int status, const char* what, cudaError_t e = cudaSuccess)
 {
@@ -590,7 +590,15 @@ int ohp_create(int device, ohp_context** out_ctx)
         }                                                                         \
     } while (0)
     OHP_CREATE(cudaSetDevice(device));
-    OHP_CREATE(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        // the compute stream outranks the schedule stream (created on first use, lowest priority): when a stretch's
+        // ramp_convert_kernel and the next stretch's walk become runnable together, the persistent kernel's CTAs are placed
+        // first and the walk takes the registers that are left (one of its CTAs per SM) -- the other way round two walk CTAs
+        // per SM leave room for only one of ramp_convert_kernel's, for as long as there are walks (ohp_run_streams_device)
+        int least = 0, greatest = 0;
+        OHP_CREATE(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        OHP_CREATE(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest));
+    }
     OHP_CREATE(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     OHP_CREATE(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     OHP_CREATE(cudaEventCreate(&ctx->ev_start));
@@ -612,6 +620,17 @@ int ohp_create(int device, ohp_context** out_ctx)
         int per_sm = 0;
         OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedStorage)));
         OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedStorage)));
+        // The schedule kernels run BESIDE ramp_convert_kernel (ohp_run_streams_device walks stretch k + 1 while stretch k is
+        // being converted).  They use no shared memory, and by default ask for the L1-heavy split of an SM's 256 KB; an SM
+        // cannot change its split while CTAs are resident, so their CTAs would wait for ramp_convert_kernel's persistent
+        // CTAs to finish -- for the whole kernel.  Asking for the same split lets them in.
+        OHP_CREATE(cudaFuncSetAttribute(sched::schedule_kernel<false, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        OHP_CREATE(cudaFuncSetAttribute(sched::schedule_kernel<true, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        OHP_CREATE(cudaFuncSetAttribute(sched::schedule_kernel<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        OHP_CREATE(cudaFuncSetAttribute(sched::schedule_kernel<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        OHP_CREATE(cudaFuncSetAttribute(sched::scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        OHP_CREATE(cudaFuncSetAttribute(ramp_convert_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         OHP_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ramp_convert_kernel<false>, kThreads, sizeof(SharedStorage)));
         ctx->ctas_per_sm = per_sm > 0 ? per_sm : 1;
     }
@@ -1062,14 +1081,25 @@ static int run_streams_device_two_pass(ohp_context* ctx, const ohp_stream_spec* 
     return launch(ctx, ctx->d_descs, (size_t)total, d_in, in_bytes, d_out, out_bytes, st);
 }
 
-// THE WALK IN STRETCHES, BESIDE ramp_convert_kernel (the default).  A stream's walk is a chain of dependent steps -- it
-// takes as long as the stream is long however many streams there are -- so the way to hide it is not to slice the batch
-// by streams but by TIME: every stream is walked a stretch of its length at a time (an eighth of it,
-// sched::stretch_stop_frame), the walks leave their state in HBM between stretches (sched::WalkState), and
+// THE WALK IN STRETCHES (OHP_STRETCHES=k; not the default).  A stream's walk is a chain of dependent steps -- it takes as
+// long as the stream is long however many streams there are -- so the way to hide it behind ramp_convert_kernel is not to
+// slice the batch by streams but by TIME: every stream is walked a stretch of its length at a time
+// (sched::stretch_stop_frame), the walks leave their state in HBM between stretches (sched::WalkState), and
 // ramp_convert_kernel runs on stretch k while stretch k + 1 is walked on the schedule stream.  Each stretch is count +
 // scan + emit (the exact two passes: descriptors compact, no padding), laid out behind the previous stretch's by a base
-// the scan carries forward on the device; the host only waits for each stretch's total to size the launch.  What is
-// left in front of ramp_convert_kernel is the walk of the first stretch.
+// the scan carries forward on the device; the host only waits for each stretch's total to size the launch.
+//
+// It works -- same bytes for any number of stretches (tests/test_gpu_schedule.py), and a caller that gets its audio a
+// window at a time can use the resumable walk for exactly that -- but it does NOT overlap, and so it is slower than the
+// one-walk path (configs[1]: 4.6 ms in 4 stretches, 4.8 in 8, against 4.1).  OHP_STRETCH_TRACE=1 prints the device
+// timeline that shows why (profiles/README.md, GPU calls 16-18): every CTA of a walk enqueued beside ramp_convert_kernel
+// starts within 27 us of the others, AFTER that kernel has ended.  The walk's CTAs find no room: an SM's register file is
+// four sub-partition files of 16 K registers, ramp_convert_kernel's two persistent CTAs put 18 warps of 2304 registers
+// on them (6 + 4 + 4 + 4 or 5 + 5 + 4 + 4), and a 168-register walk warp (5376) does not fit the fuller ones, so a
+// four-warp CTA can not be placed (the SM-wide sum, 41472 + 21504 of 65536, would fit).  Neither the shared-memory split,
+// nor stream priorities, nor a 96-register walk (spills; and 6 warps of 2304 leave 2560) changed that.  What would: eight
+// or twelve warps per ramp_convert CTA (an even load on the sub-partitions), at a cost on the hot path this repo has measured
+// before (0.92 against 0.99 on configs[1]); or a walk of 80 registers.
 static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                                         const ohp_ramp_event* d_events, size_t n_events,
                                         const uint8_t* d_in, uint64_t in_bytes, uint8_t* d_out, uint64_t out_bytes,
@@ -1102,13 +1132,34 @@ static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec*
         OHP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->sched_events.push_back(e);
     }
-    if (!ctx->sched_stream) OHP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sched_stream, cudaStreamNonBlocking));
+    if (!ctx->sched_stream) {
+        int least = 0, greatest = 0;
+        OHP_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        OHP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sched_stream, cudaStreamNonBlocking, least));
+    }
     // the schedule stream starts behind whatever the caller's stream holds so far (specs, events and PCM may just have arrived)
     OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * n_stretches], st));
     OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_events[2 * n_stretches], 0));
     const int team = schedule_team(n_streams);
     const unsigned grid = sched::schedule_grid(n_streams, team);
-    for (uint32_t j = 0; j < n_stretches; j++) {
+    // OHP_STRETCH_TRACE=1 (experiments): when each piece started and ended on the device, printed to stderr
+    static const bool trace = std::getenv("OHP_STRETCH_TRACE") != nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    auto mark = [&](const char* what, uint32_t j, cudaStream_t on) {
+        if (!trace) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        (void)cudaEventRecord(e, on);
+        marks.emplace_back(std::string(what) + " " + std::to_string(j), e);
+    };
+    mark("start", 0, st);
+    uint64_t* d_timeline = nullptr; // of stretch 1's count pass, the first walk that runs beside ramp_convert_kernel
+    if (trace && n_stretches > 1) {
+        if (cudaMalloc(reinterpret_cast<void**>(&d_timeline), (size_t)grid * 3 * sizeof(uint64_t)) != cudaSuccess) d_timeline = nullptr;
+        else (void)cudaMemset(d_timeline, 0, (size_t)grid * 3 * sizeof(uint64_t));
+    }
+    // count + scan + total to the host + emit of stretch j, on the schedule stream
+    auto enqueue_walk = [&](uint32_t j) -> int {
         sched::ScheduleParams p{};
         p.streams = d_streams; p.n_streams = n_streams; p.events = d_events; p.n_events = n_events;
         p.status = ctx->d_status + 2;
@@ -1116,21 +1167,32 @@ static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec*
         p.state_out = ctx->d_walk[(j + 1) & 1];
         p.stretch = j; p.n_stretches = n_stretches;
         p.chunk_count = ctx->d_begin; p.out_bytes = d_stream_out_bytes;
+        p.timeline = j == 1 ? d_timeline : nullptr;
+        mark("count begins", j, ctx->sched_stream);
         if (team == 32) sched::schedule_kernel<false, 32><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
         else sched::schedule_kernel<false, 1><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
         OHP_CUDA(ctx, cudaGetLastError());
+        mark("count ends", j, ctx->sched_stream);
         sched::scan_kernel<<<1, sched::kScanThreads, 0, ctx->sched_stream>>>(ctx->d_begin, n_streams, ctx->d_bases + j);
         OHP_CUDA(ctx, cudaGetLastError());
         OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_bases + j + 1, ctx->d_bases + j + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->sched_stream));
         OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * j], ctx->sched_stream));
-        p.chunk_count = nullptr; p.out_bytes = nullptr; p.state_out = nullptr;
+        mark("emit begins", j, ctx->sched_stream);
+        p.chunk_count = nullptr; p.out_bytes = nullptr; p.state_out = nullptr; p.timeline = nullptr;
         p.chunk_begin = ctx->d_begin; p.descs = ctx->d_descs; p.info = nullptr;
         p.descs_cap = ctx->d_descs_cap / sizeof(ohp_chunk_desc);
         if (team == 32) sched::schedule_kernel<true, 32><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
         else sched::schedule_kernel<true, 1><<<grid, sched::kScheduleBlock, 0, ctx->sched_stream>>>(p);
         OHP_CUDA(ctx, cudaGetLastError());
         OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[2 * j + 1], ctx->sched_stream));
+        mark("emit ends", j, ctx->sched_stream);
         ctx->launches += 3;
+        return OHP_OK;
+    };
+    // two stretches ahead of ramp_convert_kernel, no more: the host is not in the way of the first launch, and the GPU always
+    // has the next walk queued
+    for (uint32_t j = 0; j < n_stretches && j < 2; j++) {
+        if ((rc = enqueue_walk(j)) != OHP_OK) return rc;
     }
     ctx->h_bases[0] = 0;
     for (uint32_t j = 0; j < n_stretches; j++) {
@@ -1140,9 +1202,35 @@ static int run_streams_device_stretched(ohp_context* ctx, const ohp_stream_spec*
             *overflowed = true;
             break;
         }
-        if (hi == lo) continue;
-        OHP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sched_events[2 * j + 1], 0));
-        if ((rc = launch(ctx, ctx->d_descs + lo, (size_t)(hi - lo), d_in, in_bytes, d_out, out_bytes, st)) != OHP_OK) return rc;
+        if (hi != lo) {
+            OHP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->sched_events[2 * j + 1], 0));
+            mark("ramp_convert begins", j, st);
+            if ((rc = launch(ctx, ctx->d_descs + lo, (size_t)(hi - lo), d_in, in_bytes, d_out, out_bytes, st)) != OHP_OK) return rc;
+            mark("ramp_convert ends", j, st);
+        }
+        if (j + 2 < n_stretches && (rc = enqueue_walk(j + 2)) != OHP_OK) return rc;
+    }
+    if (trace) {
+        (void)cudaStreamSynchronize(st);
+        (void)cudaStreamSynchronize(ctx->sched_stream);
+        for (auto& m : marks) {
+            float ms = 0.f;
+            (void)cudaEventElapsedTime(&ms, marks[0].second, m.second);
+            std::fprintf(stderr, "[stretch trace] %8.3f ms  %s\n", ms, m.first.c_str());
+            if (&m != &marks[0]) (void)cudaEventDestroy(m.second);
+        }
+        (void)cudaEventDestroy(marks[0].second);
+        if (d_timeline) {
+            std::vector<uint64_t> tl((size_t)grid * 3);
+            (void)cudaMemcpy(tl.data(), d_timeline, tl.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+            (void)cudaFree(d_timeline);
+            uint64_t t0 = ~0ull;
+            for (unsigned b = 0; b < grid; b++) if (tl[3 * b] && tl[3 * b] < t0) t0 = tl[3 * b];
+            for (unsigned b = 0; b < grid; b += (grid > 64 ? grid / 64 : 1)) {
+                std::fprintf(stderr, "[stretch trace] count 1, CTA %4u on SM %3u: started %8.1f us after the first, ran %8.1f us\n", b,
+                             (unsigned)tl[3 * b + 2], (tl[3 * b] - t0) / 1e3, (tl[3 * b + 1] - tl[3 * b]) / 1e3);
+            }
+        }
     }
     // a stream the walk refused (spec, ASSERT, stack depth) fails the call
     const int src = schedule_status(ctx, ctx->sched_stream);
@@ -1174,7 +1262,7 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
         return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
                                            d_stream_out_bytes, total_chunks, st);
     }
-    uint32_t n_stretches = kDefaultStretches; // OHP_STRETCHES=k: k stretches; 0: the one-walk-into-regions path below
+    uint32_t n_stretches = kDefaultStretches; // OHP_STRETCHES=k: the walk in k stretches; 0 (default): the one-walk-into-regions path below
     if (const char* e = std::getenv("OHP_STRETCHES")) {
         const long v = std::atol(e);
         n_stretches = v < 0 ? 0u : (v > (long)kMaxStretches ? kMaxStretches : (uint32_t)v);
@@ -1219,7 +1307,11 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
             ctx->sched_events.push_back(e);
         }
     }
-    if (!ctx->sched_stream) OHP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sched_stream, cudaStreamNonBlocking));
+    if (!ctx->sched_stream) {
+        int least = 0, greatest = 0;
+        OHP_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        OHP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->sched_stream, cudaStreamNonBlocking, least));
+    }
     // the schedule stream starts behind whatever the caller's stream holds so far (specs, events and PCM may just have arrived)
     OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[n_slices], st));
     OHP_CUDA(ctx, cudaStreamWaitEvent(ctx->sched_stream, ctx->sched_events[n_slices], 0));

@@ -38,6 +38,7 @@ struct ScheduleParams
     WalkState* state_out;      // [n_streams], COUNT only
     uint32_t stretch, n_stretches;
     uint64_t descs_cap;        // EMIT: descriptors the buffer holds; a stream whose stretch would end beyond writes nothing
+    uint64_t* timeline;        // experiments (OHP_STRETCH_TRACE): [3 * CTAs] globaltimer at a CTA's start and end, its SM; else null
 };
 
 constexpr uint32_t kErrBound = 4u; // a stream has more playables than stream_chunk_bound allowed for: the caller takes two passes
@@ -56,7 +57,9 @@ __global__ void __launch_bounds__(128) bound_kernel(const ohp_stream_spec* __res
 // step written side by side) when streams are few enough for that to fill the GPU, TEAM = 1 (a thread per stream) when
 // there are so many streams that they alone do.  All lanes of a team hold the same state; see schedule_walk.h.
 #ifndef OHP_SCHED_MIN_BLOCKS
-#define OHP_SCHED_MIN_BLOCKS 1 /* experiments: 5 caps the walk at 96 registers so that 7 of its warps fit beside ramp_convert_kernel */
+#define OHP_SCHED_MIN_BLOCKS 3 /* <= 168 registers: a 128-thread CTA of the walk must fit into the 24064 registers that two of ramp_convert_kernel's
+                                  persistent CTAs leave on an SM, or the walks of ohp_run_streams_device wait for that kernel to end
+                                  (measured: at 200 registers they did).  5 (96 registers, 7 warps beside it) spills and loses. */
 #endif
 template <bool EMIT, int TEAM>
 __global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(const ScheduleParams p)
@@ -64,6 +67,12 @@ __global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(con
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t local = t / TEAM;
     const uint32_t lane = (uint32_t)(t % TEAM);
+    if (p.timeline != nullptr && threadIdx.x == 0) {
+        uint64_t now; uint32_t sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        p.timeline[3 * blockIdx.x] = now; p.timeline[3 * blockIdx.x + 2] = sm;
+    }
     if (local >= p.n_streams) return;
     const uint64_t s = p.first_stream + local;
     const ohp_stream_spec sp = p.streams[s];
@@ -88,6 +97,11 @@ __global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(con
         const uint64_t from = rc == kOk ? nChunks : 0;
         uint4* d4 = reinterpret_cast<uint4*>(descs);
         for (uint64_t i = 2 * from + lane; i < 2 * limit; i += TEAM) d4[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.timeline != nullptr && threadIdx.x == 0) { // warp 0's end stands for the CTA's (streams of a batch are of a length)
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        p.timeline[3 * blockIdx.x + 1] = now;
     }
     if (lane != 0) return;
     if (rc != kOk) {

@@ -831,9 +831,7 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
 }
 
 // Where stretch aIndex of aCount ends, as a frame of the source: stretches of equal length; the last one runs to the end
-// of the stream.  (Stretches that double in length -- start the consumer after 1/16 of the walk -- were measured first and
-// lose: beside ramp_convert_kernel only 4 of a stream-per-warp walk's warps fit on an SM, the two passes of stretch
-// k + 1 then take as long as the consumer needs for a stretch half its size, and the pipeline runs at the walk's pace.)
+// of the stream.
 OHP_HD uint64_t stretch_stop_frame(uint64_t aTotalFrames, uint32_t aIndex, uint32_t aCount)
 {
     if (aIndex + 1 >= aCount) return ~0ull;

@@ -270,20 +270,19 @@ def test_whole_stage_for_a_batch_resident_in_hbm(ctx, port, make):
             torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("mode", ["stretches_1", "stretches_3", "stretches_16", "one_walk", "one_walk_sliced", "two_pass"])
+@pytest.mark.parametrize("mode", ["stretches_1", "stretches_3", "stretches_8", "stretches_16", "one_walk_sliced", "two_pass"])
 def test_whole_stage_device_call_in_every_mode(ctx, port, mode, monkeypatch):
-    """ohp_run_streams_device's default walks every stream in five stretches beside ramp_convert_kernel
-    (test_whole_stage_for_a_batch_resident_in_hbm); here the other stretch counts, the one-walk-into-bounded-regions path
-    (whole and cut into slices of streams), and the round-1 count + scan + emit path: same bytes, same sizes, same count."""
+    """ohp_run_streams_device's default is one walk per stream into bounded regions
+    (test_whole_stage_for_a_batch_resident_in_hbm); here that path cut into slices of streams, the walk in stretches of
+    time (stopped and resumed from its saved state, descriptors stretch-major), and the round-1 count + scan + emit path:
+    same bytes, same sizes, same count."""
     import torch
     if mode.startswith("stretches_"):
         monkeypatch.setenv("OHP_STRETCHES", mode.split("_")[1])
     elif mode == "two_pass":
         monkeypatch.setenv("OHP_ONE_WALK", "0")
     else:
-        monkeypatch.setenv("OHP_STRETCHES", "0")
-        if mode == "one_walk_sliced":
-            monkeypatch.setenv("OHP_SLICE_CHUNKS", "700")
+        monkeypatch.setenv("OHP_SLICE_CHUNKS", "700")
     for w in (workloads.config4(n_streams=120, seconds=0.12, seed=3), workloads.elements(4, n_streams=60), workloads.config5(n_streams=90, seconds=0.1)):
         inp = port.fill_pcm(w.in_bytes, w.seed)
         rc, want, chunks, _ = port.run(w.streams, w.events, inp, w.out_bytes)
