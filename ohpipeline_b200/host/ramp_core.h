@@ -57,32 +57,38 @@ OHP_HD bool ramp_is_valid(const RampPod& r)
     }
 }
 
-// (a * b + add) / d in 64 bits, as the reference computes it.  The GPU has no 64-bit divider (a __udivdi3-style call
-// is a dependent chain of some hundreds of cycles, and the ramp recurrence -- one such division per message, each
-// needing the previous one's result -- is what a stream's schedule walk waits on).  On the device: where the caller has 1 / d at hand (aInv: bulk_step knows the divisors of a run before it knows
-// the numerators) and the numerator is below 2^53 (exact in a double), quotient = trunc(num * aInv) corrected by the
-// remainder: the product is off by less than 2^-20 (quotient < 2^32, two roundings of 2^-53 each), so the truncation
-// is at most one off either way and one multiply-subtract settles it -- exact, no rounding assumption left.  Otherwise a
-// 32-bit divide when the numerator fits, the 64-bit one when it does not.  (Computing
-// 1 / d in here instead was measured in code size: 85 inlined reciprocal sequences, +20 % SASS in a kernel that is
-// already larger than the instruction cache.)
-OHP_HD uint32_t mul_add_div(uint32_t a, uint32_t b, uint32_t add, uint32_t d, double aInv = 0.0)
+// (a * b + add) / d in 64 bits, as the reference computes it; 32-bit divide when the numerator fits (the GPU has no
+// 64-bit divider: __udivdi3-style code is ~10x the cost of a 32-bit divide, and most ramp steps fit).
+OHP_HD uint32_t mul_add_div(uint32_t a, uint32_t b, uint32_t add, uint32_t d)
 {
     const uint64_t num = a * (uint64_t)b + add;
-#if defined(__CUDA_ARCH__)
-    if (aInv != 0.0 && (num >> 53) == 0) {
-        uint64_t q = (uint64_t)__double2ll_rz((double)(int64_t)num * aInv);
-        int64_t r = (int64_t)num - (int64_t)(q * d);
-        if (r < 0) { q--; r += d; }
-        else if (r >= (int64_t)d) { q++; r -= d; }
-        if ((uint64_t)r < d) return (uint32_t)q; // always, unless aInv was not 1 / d: then the plain division below
-    }
-#else
-    (void)aInv;
-#endif
     if ((num >> 32) == 0) return (uint32_t)num / d;
     return (uint32_t)(num / d);
 }
+
+#if defined(__CUDA_ARCH__)
+// ceil(aDistance * aSize / aRemaining) = (aDistance * aSize + aRemaining - 1) / aRemaining -- Ramp::Set's step
+// (Msg.cpp:603-605) -- through the FP64 pipe, for the schedule walk's ramp recurrence: one such division per message,
+// each needing the previous one's result, is the chain a stream's walk waits on, and in 64-bit integer arithmetic that
+// chain is ~60 dependent instructions.  Here it is: convert, fma, multiply by the reciprocal the caller took ahead
+// (aInv = 1.0 / aRemaining; the divisors of a run are known before its numerators), truncate, fma, compare.
+// EXACT, given aSize < 2^21 (aSizeD = (double)aSize): the numerator is an integer below 2^31 * 2^21 + 2^32 < 2^53, so the
+// first fma is exact; the product with aInv is off by less than 2^-19 (quotient <= 2^31 + 1, two roundings of 2^-53),
+// so its truncation is the quotient or one beside it; the second fma gives the remainder for that candidate exactly
+// (an integer of magnitude below 2^33), and its sign / size says which.  (4 M random and 12 M adversarial numerators --
+// exact multiples of the divisor and their neighbours -- checked on the host against integer division.)
+__device__ __forceinline__ uint32_t ramp_step_fp(uint32_t aDistance, double aSizeD, uint32_t aRemaining, double aInv)
+{
+    const double dd = (double)aRemaining;
+    const double numd = fma((double)aDistance, aSizeD, dd - 1.0);
+    const double qd = trunc(numd * aInv);
+    const double r = fma(-qd, dd, numd);
+    uint32_t q = __double2uint_rz(qd);
+    if (r < 0.0) q--;
+    else if (r >= dd) q++;
+    return q;
+}
+#endif
 
 // two ramps over the same audio: the quieter one wins at both ends (Msg.cpp:721-734)
 OHP_HD void ramp_take_lower(RampPod& r, uint32_t aStart, uint32_t aEnd)

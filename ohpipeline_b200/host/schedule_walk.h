@@ -682,25 +682,33 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
         //     delta = ceil(distance * size / remaining);  end = current -+ delta;  remaining -= size
         // with distance = how far the ramp still has to go.  This chain -- message k + 1 starts where k ended -- is
         // what a stream's walk waits on (one warp per stream: nothing else to issue meanwhile), so nothing but the
-        // chain is left in the loop: the divisors are known up front (what is left of the ramp shrinks by one message
-        // each time), so on the device the warp takes their 32 reciprocals side by side first and a step is one
-        // multiply, one truncation and the exact remainder fix-up (core::mul_add_div).  Anything else -- a step of 0
-        // (the reference ASSERTs: Ramp::DoValidate), the ramp arriving (delta == distance: "finished early",
-        // Msg.cpp:2037-2043) or overshooting -- ends the run in front of that message; the general path decides it.
+        // chain is left in the loop, and on the device the chain runs through the FP64 pipe (core::ramp_step_fp): the
+        // divisors are known up front (what is left of the ramp shrinks by one message each time), so the warp takes
+        // their 32 reciprocals side by side first.  Anything else -- a step of 0 (the reference ASSERTs:
+        // Ramp::DoValidate), the ramp arriving (delta == distance: "finished early", Msg.cpp:2037-2043) or
+        // overshooting -- ends the run in front of that message; the general path decides it.
         const bool down = rMode == RampingDown;
         const uint32_t dir = down ? core::kDirDown : core::kDirUp;
-        double myInv = 0.0;
 #if defined(__CUDA_ARCH__)
-        if (STRIDE == kBulk && rRemaining > cx.lane * size) myInv = 1.0 / (double)(rRemaining - cx.lane * size);
+        const bool fp = size < (1u << 21);
+        const double sizeD = (double)size;
+        double myInv = 0.0;
+        if (STRIDE == kBulk && fp && rRemaining > cx.lane * size) myInv = 1.0 / (double)(rRemaining - cx.lane * size);
 #endif
         uint32_t done = 0;
-        for (uint32_t k = 0; k < n; k++) {
-            double inv = 0.0;
-#if defined(__CUDA_ARCH__)
-            if (STRIDE == kBulk) inv = __shfl_sync(0xffffffffu, myInv, (int)k);
+#if defined(__CUDA_ARCH__) && defined(OHP_LEAN_UNROLL)
+#pragma unroll OHP_LEAN_UNROLL
 #endif
+        for (uint32_t k = 0; k < n; k++) {
             const uint32_t distance = down ? rCurrent : core::kRampMax - rCurrent;
-            const uint32_t delta = core::mul_add_div(distance, size, rRemaining - 1, rRemaining, inv);
+#if defined(__CUDA_ARCH__)
+            // (a thread walking a stream alone takes the reciprocal as it goes: it does not depend on the chain either)
+            const uint32_t delta = fp ? core::ramp_step_fp(distance, sizeD, rRemaining,
+                                                           STRIDE == kBulk ? __shfl_sync(0xffffffffu, myInv, (int)k) : 1.0 / (double)rRemaining)
+                                      : core::mul_add_div(distance, size, rRemaining - 1, rRemaining);
+#else
+            const uint32_t delta = core::mul_add_div(distance, size, rRemaining - 1, rRemaining);
+#endif
             if (delta == 0 || delta >= distance) break;
             const uint32_t end = down ? rCurrent - delta : rCurrent + delta;
             if (k % STRIDE == cx.lane) {
