@@ -1276,12 +1276,75 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
         return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
                                            d_stream_out_bytes, total_chunks, st);
     }
-    // 1. regions: bound per stream, exclusive scan, their offsets to the host (the one synchronisation of the call)
+    // 1. regions: bound per stream, exclusive scan
     sched::bound_kernel<<<(unsigned)((n_streams + 127) / 128), 128, 0, st>>>(d_streams, n_streams, d_events, n_events, ctx->d_begin);
     OHP_CUDA(ctx, cudaGetLastError());
     sched::scan_kernel<<<1, sched::kScanThreads, 0, st>>>(ctx->d_begin, n_streams);
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
+    if (!std::getenv("OHP_SLICE_CHUNKS")) {
+        // THE DEFAULT: everything on the caller's stream, and the walk is launched BEFORE the host knows how many
+        // descriptors the regions add up to -- the total (8 bytes, pinned) comes back while the walk runs, so the host's
+        // round trip costs the GPU nothing.  The walk writes nothing for a stream whose region would end beyond the
+        // buffer; if the total says the buffer was too small (first call of a shape), it grows and the walk runs again.
+        if (!ctx->h_bases) OHP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_bases), (kMaxStretches + 2) * sizeof(uint64_t), cudaHostAllocDefault));
+        if (ctx->sched_events.empty()) {
+            cudaEvent_t e;
+            OHP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->sched_events.push_back(e);
+        }
+        OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_bases, ctx->d_begin + n_streams, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[0], st));
+        const int team = schedule_team(n_streams);
+        auto walk = [&]() -> int {
+            sched::ScheduleParams p{};
+            p.streams = d_streams; p.n_streams = n_streams; p.events = d_events; p.n_events = n_events;
+            p.chunk_begin = ctx->d_begin; p.descs = ctx->d_descs; p.info = nullptr;
+            p.descs_cap = ctx->d_descs_cap / sizeof(ohp_chunk_desc);
+            p.status = ctx->d_status + 2;
+            p.first_stream = 0; p.counts_out = ctx->d_counts; p.out_bytes = d_stream_out_bytes;
+            if (team == 32) sched::schedule_kernel<true, 32><<<sched::schedule_grid(n_streams, 32), sched::kScheduleBlock, 0, st>>>(p);
+            else sched::schedule_kernel<true, 1><<<sched::schedule_grid(n_streams, 1), sched::kScheduleBlock, 0, st>>>(p);
+            OHP_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+            return OHP_OK;
+        };
+        if (ctx->d_descs_cap >= sizeof(ohp_chunk_desc) && (rc = walk()) != OHP_OK) return rc; // (no buffer yet: after the total)
+        OHP_CUDA(ctx, cudaEventSynchronize(ctx->sched_events[0]));
+        const uint64_t regions = ctx->h_bases[0];
+        if (regions > ctx->d_descs_cap / sizeof(ohp_chunk_desc)) {
+            OHP_CUDA(ctx, cudaDeviceSynchronize()); // the buffer may still be read by a launch enqueued earlier on another stream
+            if ((rc = grow(ctx, ctx->d_descs, ctx->d_descs_cap, regions * sizeof(ohp_chunk_desc))) != OHP_OK) return rc;
+            if ((rc = walk()) != OHP_OK) return rc;
+        }
+        if (total_chunks) {
+            // the exact number of playables, and what the walk refused: in front of ramp_convert_kernel in the stream, so the
+            // host waits for the walk only
+            ctx->h_outb.resize(n_streams);
+            OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_outb.data(), ctx->d_counts, n_streams * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            OHP_CUDA(ctx, cudaEventRecord(ctx->sched_events[0], st));
+        }
+        if ((rc = launch(ctx, ctx->d_descs, (size_t)regions, d_in, in_bytes, d_out, out_bytes, st)) != OHP_OK) return rc;
+        if (total_chunks) {
+            OHP_CUDA(ctx, cudaEventSynchronize(ctx->sched_events[0]));
+            if (ctx->h_status[2] != 0) {
+                const int src = schedule_status(ctx, st); // waits for ramp_convert_kernel too: the call has failed anyway
+                if (src == OHP_E_NO_MEMORY && ctx->error.find("region") != std::string::npos) {
+                    // a stream outgrew its region: nothing wrong with the batch, take the exact two-pass path
+                    (void)read_status(ctx, st);
+                    return run_streams_device_two_pass(ctx, d_streams, n_streams, d_events, n_events, d_in, in_bytes, d_out, out_bytes,
+                                                       d_stream_out_bytes, total_chunks, st);
+                }
+                if (src != OHP_OK) return src;
+            }
+            uint64_t total = 0;
+            for (size_t s2 = 0; s2 < n_streams; s2++) total += ctx->h_outb[s2];
+            *total_chunks = total;
+        }
+        return OHP_OK;
+    }
+    // 1b. (OHP_SLICE_CHUNKS: slices of streams) the regions' offsets to the host
     ctx->h_begin.resize(n_streams + 1);
     OHP_CUDA(ctx, cudaMemcpyAsync(ctx->h_begin.data(), ctx->d_begin, (n_streams + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     OHP_CUDA(ctx, cudaStreamSynchronize(st));

@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(con
     ohp_chunk_desc* descs = EMIT ? p.descs + p.chunk_begin[s] - before : nullptr;
     ohp_chunk_info* info = (EMIT && p.info) ? p.info + p.chunk_begin[s] - before : nullptr;
     const bool regions = EMIT && p.counts_out != nullptr;
+    // (regions: launched before the host has sized the buffer -- a stream whose region would end beyond it is left for the
+    //  second launch that follows when that turns out to be the case)
+    if (regions && p.descs_cap != 0 && p.chunk_begin[s + 1] > p.descs_cap) return;
     uint64_t limit = regions ? p.chunk_begin[s + 1] - p.chunk_begin[s] : ~0ull;
     if (EMIT && stretched) { // a refused stream counted 0: it writes nothing
         limit = p.chunk_begin[s + 1] <= p.descs_cap ? before + (p.chunk_begin[s + 1] - p.chunk_begin[s]) : before;

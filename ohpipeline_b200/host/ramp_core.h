@@ -66,30 +66,6 @@ OHP_HD uint32_t mul_add_div(uint32_t a, uint32_t b, uint32_t add, uint32_t d)
     return (uint32_t)(num / d);
 }
 
-#if defined(__CUDA_ARCH__)
-// ceil(aDistance * aSize / aRemaining) = (aDistance * aSize + aRemaining - 1) / aRemaining -- Ramp::Set's step
-// (Msg.cpp:603-605) -- through the FP64 pipe, for the schedule walk's ramp recurrence: one such division per message,
-// each needing the previous one's result, is the chain a stream's walk waits on, and in 64-bit integer arithmetic that
-// chain is ~60 dependent instructions.  Here it is: convert, fma, multiply by the reciprocal the caller took ahead
-// (aInv = 1.0 / aRemaining; the divisors of a run are known before its numerators), truncate, fma, compare.
-// EXACT, given aSize < 2^21 (aSizeD = (double)aSize): the numerator is an integer below 2^31 * 2^21 + 2^32 < 2^53, so the
-// first fma is exact; the product with aInv is off by less than 2^-19 (quotient <= 2^31 + 1, two roundings of 2^-53),
-// so its truncation is the quotient or one beside it; the second fma gives the remainder for that candidate exactly
-// (an integer of magnitude below 2^33), and its sign / size says which.  (4 M random and 12 M adversarial numerators --
-// exact multiples of the divisor and their neighbours -- checked on the host against integer division.)
-__device__ __forceinline__ uint32_t ramp_step_fp(uint32_t aDistance, double aSizeD, uint32_t aRemaining, double aInv)
-{
-    const double dd = (double)aRemaining;
-    const double numd = fma((double)aDistance, aSizeD, dd - 1.0);
-    const double qd = trunc(numd * aInv);
-    const double r = fma(-qd, dd, numd);
-    uint32_t q = __double2uint_rz(qd);
-    if (r < 0.0) q--;
-    else if (r >= dd) q++;
-    return q;
-}
-#endif
-
 // two ramps over the same audio: the quieter one wins at both ends (Msg.cpp:721-734)
 OHP_HD void ramp_take_lower(RampPod& r, uint32_t aStart, uint32_t aEnd)
 {

@@ -679,45 +679,81 @@ OHP_HD uint32_t bulk_step(const ohp_stream_spec& sp, StreamCtx& cx, Stage (&st)[
     if (uniform && ramping) {
         // THE RAMP RECURRENCE, LEAN.  Every message of the run is fresh (no ramp of its own), whole, and lies inside
         // the ramp, so MsgAudio::SetRamp / Ramp::Set (msg_set_ramp / core::ramp_set) come down to
-        //     delta = ceil(distance * size / remaining);  end = current -+ delta;  remaining -= size
-        // with distance = how far the ramp still has to go.  This chain -- message k + 1 starts where k ended -- is
-        // what a stream's walk waits on (one warp per stream: nothing else to issue meanwhile), so nothing but the
-        // chain is left in the loop, and on the device the chain runs through the FP64 pipe (core::ramp_step_fp): the
-        // divisors are known up front (what is left of the ramp shrinks by one message each time), so the warp takes
-        // their 32 reciprocals side by side first.  Anything else -- a step of 0 (the reference ASSERTs:
-        // Ramp::DoValidate), the ramp arriving (delta == distance: "finished early", Msg.cpp:2037-2043) or
-        // overshooting -- ends the run in front of that message; the general path decides it.
+        //     delta = ceil(distance * size / remaining);  distance -= delta;  remaining -= size
+        // with distance = how far the ramp still has to go (current for a ramp down, kRampMax - current for a ramp up).
+        // This chain -- message k + 1 starts where k ended -- is what a stream's walk waits on (one warp per stream:
+        // nothing else to issue meanwhile, so EVERY instruction in the loop costs its latency, on the chain or not), so
+        // nothing but the chain is left in the loop.  Anything else -- a step of 0 (the reference ASSERTs:
+        // Ramp::DoValidate), the ramp arriving (delta == distance: "finished early", Msg.cpp:2037-2043) or overshooting
+        // -- ends the run in front of that message; the general path decides it.
         const bool down = rMode == RampingDown;
         const uint32_t dir = down ? core::kDirDown : core::kDirUp;
-#if defined(__CUDA_ARCH__)
-        const bool fp = size < (1u << 21);
-        const double sizeD = (double)size;
-        double myInv = 0.0;
-        if (STRIDE == kBulk && fp && rRemaining > cx.lane * size) myInv = 1.0 / (double)(rRemaining - cx.lane * size);
-#endif
         uint32_t done = 0;
-#if defined(__CUDA_ARCH__) && defined(OHP_LEAN_UNROLL)
-#pragma unroll OHP_LEAN_UNROLL
-#endif
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t distance = down ? rCurrent : core::kRampMax - rCurrent;
 #if defined(__CUDA_ARCH__)
-            // (a thread walking a stream alone takes the reciprocal as it goes: it does not depend on the chain either)
-            const uint32_t delta = fp ? core::ramp_step_fp(distance, sizeD, rRemaining,
-                                                           STRIDE == kBulk ? __shfl_sync(0xffffffffu, myInv, (int)k) : 1.0 / (double)rRemaining)
-                                      : core::mul_add_div(distance, size, rRemaining - 1, rRemaining);
-#else
-            const uint32_t delta = core::mul_add_div(distance, size, rRemaining - 1, rRemaining);
-#endif
-            if (delta == 0 || delta >= distance) break;
-            const uint32_t end = down ? rCurrent - delta : rCurrent + delta;
-            if (k % STRIDE == cx.lane) {
-                core::RampPod& r = mine[k / STRIDE];
-                r.start = rCurrent; r.end = end; r.direction = dir; r.enabled = 1;
+        if (STRIDE == kBulk && size < (1u << 21)) {
+            // A warp, on the device: the chain runs through the FP64 pipe, on doubles that hold integers.  The divisors
+            // are known up front (what is left of the ramp shrinks by one message each time), so the warp takes their 32
+            // reciprocals side by side first and a step is fma, multiply, truncate, fma, compare.  EXACT: the numerator
+            // distance * size + remaining - 1 is an integer below 2^31 * 2^21 + 2^32 < 2^53, so the first fma is exact;
+            // the product with the reciprocal is off by less than 2^-19 (quotient <= 2^31 + 1, two roundings of 2^-53
+            // each), so its truncation is the quotient or one beside it; the second fma gives that candidate's remainder
+            // exactly (an integer of magnitude below 2^33), and its sign / size says which.  (4 M random and 12 M
+            // adversarial numerators -- exact multiples of the divisor and their neighbours -- checked on the host
+            // against integer division; every GPU schedule test compares the result with the host's integer walk.)
+            // 38 instructions per message where the integer version had 57 (+ a call for the 64-bit division).
+            // Measured and dropped: settling message k one iteration later, beside message k + 1's chain (a chain of
+            // four operations, but 55 instructions: slower -- it is the instruction count that this loop pays for).
+            const double sizeD = (double)size;
+            double myInv = 0.0;
+            if (rRemaining > cx.lane * size) myInv = 1.0 / (double)(rRemaining - cx.lane * size);
+            double remD = (double)rRemaining;
+            double distD = (double)(down ? rCurrent : core::kRampMax - rCurrent);
+            double myFrom = 0.0; // distance in front of this lane's message (behind it: what the next lane has in front)
+            uint32_t lane = cx.lane;
+            asm volatile("" : "+r"(lane)); // held in a register: the compiler would otherwise recompute it from %tid in every iteration
+            uint32_t k = 0;
+            for (; k < n; k++) {
+                const double inv = __shfl_sync(0xffffffffu, myInv, (int)k);
+                const double numd = fma(distD, sizeD, remD - 1.0);
+                double qd = trunc(numd * inv);
+                const double r = fma(-qd, remD, numd);
+                if (r < 0.0) qd -= 1.0;
+                else if (r >= remD) qd += 1.0;
+                if (qd == 0.0 || qd >= distD) break;
+                if (k == lane) myFrom = distD;
+                distD -= qd;
+                remD -= sizeD;
             }
-            rCurrent = end;
-            rRemaining -= size;
-            done = k + 1;
+            done = k;
+            double myTo = __shfl_down_sync(0xffffffffu, myFrom, 1);
+            if (cx.lane + 1 >= done) myTo = distD;
+            const uint32_t dist = __double2uint_rz(distD);
+            rCurrent = down ? dist : core::kRampMax - dist;
+            rRemaining -= done * size;
+            if (cx.lane < done) {
+                const uint32_t from = __double2uint_rz(myFrom), to = __double2uint_rz(myTo);
+                core::RampPod& r = mine[0];
+                r.start = down ? from : core::kRampMax - from;
+                r.end = down ? to : core::kRampMax - to;
+                r.direction = dir; r.enabled = 1;
+            }
+        }
+        else
+#endif
+        {
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t distance = down ? rCurrent : core::kRampMax - rCurrent;
+                const uint32_t delta = core::mul_add_div(distance, size, rRemaining - 1, rRemaining);
+                if (delta == 0 || delta >= distance) break;
+                const uint32_t end = down ? rCurrent - delta : rCurrent + delta;
+                if (k % STRIDE == cx.lane) {
+                    core::RampPod& r = mine[k / STRIDE];
+                    r.start = rCurrent; r.end = end; r.direction = dir; r.enabled = 1;
+                }
+                rCurrent = end;
+                rRemaining -= size;
+                done = k + 1;
+            }
         }
         n = done;
         if (n == 0) return 0;

@@ -333,3 +333,30 @@ def test_whole_stage_device_call_reports_errors(ctx):
     assert e.value.status == abi.E_OUT_OF_RANGE
     assert ctx.run_streams_device(d_ok.data_ptr(), 4, d_e.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes, d_out.data_ptr(), w.out_bytes) > 0
     ctx.sync()
+
+
+def test_whole_stage_device_call_is_the_first_thing_a_context_does(port):
+    """A fresh context has no descriptor buffer: the walk that is normally launched before the host knows the regions'
+    total has nowhere to write yet, and must wait for it."""
+    import torch
+    ctx = capi.Context(0)
+    try:
+        w = workloads.config5(n_streams=40, seconds=0.05)
+        inp = port.fill_pcm(w.in_bytes, w.seed)
+        rc, want, chunks, _ = port.run(w.streams, w.events, inp, w.out_bytes)
+        assert rc == 0
+        d_streams = torch.from_numpy(w.streams.view(np.uint8).copy()).cuda()
+        d_events = torch.from_numpy(w.events.view(np.uint8).copy()).cuda()
+        d_in = torch.from_numpy(inp).cuda()
+        d_out = torch.zeros(w.out_bytes + 16, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        assert ctx.run_streams_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes,
+                                      d_out.data_ptr(), w.out_bytes, 0, None, want_total=False) is None
+        ctx.sync()
+        mask = covered_mask(chunks, w.out_bytes)
+        assert np.array_equal(d_out.cpu().numpy()[:w.out_bytes][mask], want[mask])
+        assert ctx.run_streams_device(d_streams.data_ptr(), len(w.streams), d_events.data_ptr(), len(w.events), d_in.data_ptr(), w.in_bytes,
+                                      d_out.data_ptr(), w.out_bytes) == len(chunks)
+        ctx.sync()
+    finally:
+        ctx.close()
