@@ -886,6 +886,25 @@ static int schedule_team(size_t n_streams)
     return n_streams <= kScheduleWarpTeamMaxStreams ? 32 : 1;
 }
 
+// Streams per warp when a thread walks a stream (see schedule_kernel): as many as it takes to have about one warp per warp
+// scheduler (4 per SM), no more.  Threads of a warp that walk different streams take turns wherever their paths differ, so
+// fewer streams per warp are faster per warp -- until there are more warps than schedulers: the walk is 690 KB of code,
+// and warps sharing a scheduler share an instruction cache they each drag a different part of it through.  Measured
+// (profiles/README.md, GPU call 32): 4096 streams (configs[2]) 32 per warp 1.09 ms, 8 per warp 0.79, 2 per warp 1.37;
+// 16384 streams (configs[3]) 32 per warp 1.95 ms, 16 per warp 2.15, 1 per warp 3.7.  OHP_SCHED_LANES=k pins it (experiments).
+static uint32_t schedule_lanes(const ohp_context* ctx, size_t n_streams)
+{
+    static const int pinned = [] {
+        const char* e = std::getenv("OHP_SCHED_LANES");
+        const int v = e ? std::atoi(e) : 0;
+        return (v >= 1 && v <= 32) ? v : 0;
+    }();
+    if (pinned) return (uint32_t)pinned;
+    const size_t schedulers = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 4u;
+    const size_t lanes = (n_streams + schedulers - 1) / schedulers;
+    return lanes < 1 ? 1u : (lanes > 32 ? 32u : (uint32_t)lanes);
+}
+
 int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
                               const ohp_ramp_event* d_events, size_t n_events, uint64_t* d_chunk_begin,
                               uint64_t* d_stream_out_bytes, uint64_t* total_chunks, void* stream)
@@ -904,7 +923,8 @@ int ohp_schedule_count_device(ohp_context* ctx, const ohp_stream_spec* d_streams
         if (schedule_team(n_streams) == 32) {
             sched::schedule_kernel<false, 32><<<sched::schedule_grid(n_streams, 32), sched::kScheduleBlock, 0, st>>>(p);
         } else {
-            sched::schedule_kernel<false, 1><<<sched::schedule_grid(n_streams, 1), sched::kScheduleBlock, 0, st>>>(p);
+            p.lanes_per_warp = schedule_lanes(ctx, n_streams);
+            sched::schedule_kernel<false, 1><<<sched::schedule_grid(n_streams, 1, p.lanes_per_warp), sched::kScheduleBlock, 0, st>>>(p);
         }
         OHP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
@@ -939,7 +959,8 @@ int ohp_schedule_emit_device(ohp_context* ctx, const ohp_stream_spec* d_streams,
     if (schedule_team(n_streams) == 32) {
         sched::schedule_kernel<true, 32><<<sched::schedule_grid(n_streams, 32), sched::kScheduleBlock, 0, st>>>(p);
     } else {
-        sched::schedule_kernel<true, 1><<<sched::schedule_grid(n_streams, 1), sched::kScheduleBlock, 0, st>>>(p);
+        p.lanes_per_warp = schedule_lanes(ctx, n_streams);
+        sched::schedule_kernel<true, 1><<<sched::schedule_grid(n_streams, 1, p.lanes_per_warp), sched::kScheduleBlock, 0, st>>>(p);
     }
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
@@ -1303,8 +1324,9 @@ int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, s
             p.descs_cap = ctx->d_descs_cap / sizeof(ohp_chunk_desc);
             p.status = ctx->d_status + 2;
             p.first_stream = 0; p.counts_out = ctx->d_counts; p.out_bytes = d_stream_out_bytes;
+            p.lanes_per_warp = schedule_lanes(ctx, n_streams);
             if (team == 32) sched::schedule_kernel<true, 32><<<sched::schedule_grid(n_streams, 32), sched::kScheduleBlock, 0, st>>>(p);
-            else sched::schedule_kernel<true, 1><<<sched::schedule_grid(n_streams, 1), sched::kScheduleBlock, 0, st>>>(p);
+            else sched::schedule_kernel<true, 1><<<sched::schedule_grid(n_streams, 1, p.lanes_per_warp), sched::kScheduleBlock, 0, st>>>(p);
             OHP_CUDA(ctx, cudaGetLastError());
             ctx->launches++;
             return OHP_OK;

@@ -39,6 +39,7 @@ struct ScheduleParams
     uint32_t stretch, n_stretches;
     uint64_t descs_cap;        // EMIT: descriptors the buffer holds; a stream whose stretch would end beyond writes nothing
     uint64_t* timeline;        // experiments (OHP_STRETCH_TRACE): [3 * CTAs] globaltimer at a CTA's start and end, its SM; else null
+    uint32_t lanes_per_warp;   // TEAM = 1: streams a warp walks (its first lanes, one each; the others idle); 0 = 32
 };
 
 constexpr uint32_t kErrBound = 4u; // a stream has more playables than stream_chunk_bound allowed for: the caller takes two passes
@@ -65,8 +66,14 @@ template <bool EMIT, int TEAM>
 __global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(const ScheduleParams p)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t local = t / TEAM;
+    uint64_t local = t / TEAM;
     const uint32_t lane = (uint32_t)(t % TEAM);
+    if (TEAM == 1 && p.lanes_per_warp != 0) {
+        // a thread per stream, but fewer streams than lanes in a warp: threads of a warp walk different streams and
+        // take turns wherever their paths differ, so a warp takes about as long as its streams take one after the other
+        if ((t & 31u) >= p.lanes_per_warp) return;
+        local = (t >> 5) * p.lanes_per_warp + (t & 31u);
+    }
     if (p.timeline != nullptr && threadIdx.x == 0) {
         uint64_t now; uint32_t sm;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -126,8 +133,12 @@ __global__ void __launch_bounds__(128, OHP_SCHED_MIN_BLOCKS) schedule_kernel(con
 
 // threads per block; grid for n streams
 constexpr unsigned kScheduleBlock = 128;
-inline unsigned schedule_grid(uint64_t n_streams, int team)
+inline unsigned schedule_grid(uint64_t n_streams, int team, uint32_t lanes_per_warp = 0)
 {
+    if (team == 1 && lanes_per_warp != 0) {
+        const uint64_t warps = (n_streams + lanes_per_warp - 1) / lanes_per_warp;
+        return (unsigned)((warps * 32u + kScheduleBlock - 1) / kScheduleBlock);
+    }
     return (unsigned)((n_streams * (uint64_t)team + kScheduleBlock - 1) / kScheduleBlock);
 }
 
