@@ -61,6 +61,13 @@ int ohp_container_parse(const uint8_t* bytes, uint64_t len, uint32_t max_bit_dep
  * the audio itself, chunk_frames = min(5 ms, 9216 B) as CodecController cuts it, codec_read_frames as the codec reads.
  * Audio present in [data_offset, len) beyond audio_bytes is ignored, audio missing (truncated file) shortens the stream.
  * Fails (OHP_CONTAINER_E_UNSUPPORTED) where output depth != stored depth: that is a re-quantising sink, not a stream.
+ *
+ * ASSUMPTION for WAV (and raw PCM): every message is a full chunk_frames (the last one excepted).  CodecWav::Process fills
+ * the 5 ms buffer from what is left of the current MsgAudioEncoded plus ONE more (Wav.cpp:140-185), so over a transport
+ * whose encoded messages are so small that two of them hold less than 5 ms of audio the reference's messages are shorter
+ * and follow the transport's boundaries -- and Ramp::Set rounds per message, so a ramp over such a stretch differs in its
+ * last bits.  Reads of a FIXED size can be expressed (codec_read_frames of the spec: the codec's read size in frames,
+ * what AIFF's 9216-byte reads use; 0 = messages of chunk_frames); arbitrary transport boundaries cannot.
  */
 int ohp_container_stream_spec(const ohp_container_info* info, uint64_t container_len, uint64_t arena_offset,
                               uint64_t dst_base, ohp_stream_spec* out);
