@@ -62,13 +62,19 @@ int ohp_run_streams_host(ohp_context* ctx, const ohp_stream_spec* h_streams, siz
 
 /*
  * The same stage for a batch that is already RESIDENT IN HBM: stream specs, ramp events and PCM in device memory in,
- * every stream's output bytes in device memory out -- both schedule passes and the ramp + convert kernel, enqueued on
- * `stream` (NULL = the context's own).  The descriptors live in a buffer the context owns and reuses.  The call
- * returns once everything is enqueued; it blocks the host only for the chunk total the count pass hands back (the
- * context's descriptor buffer has to be large enough before the second pass starts).  ohp_sync(ctx, stream) waits and
- * reports device-side errors.
+ * every stream's output bytes in device memory out -- the schedule walk and the ramp + convert kernel, enqueued on
+ * `stream` (NULL = the context's own).  The descriptors live in a buffer the context owns and reuses: one region per
+ * stream, sized by a closed-form bound on its playables (ohp_schedule_chunk_bounds), filled by ONE walk per stream,
+ * unused slots left empty.  The call returns once everything is enqueued; the host waits only for the regions' total
+ * (8 bytes, while the walk is already running).  ohp_sync(ctx, stream) waits and reports device-side errors.
  *   d_stream_out_bytes (n_streams, device, may be NULL): bytes each stream produced at d_out + dst_base.
- *   total_chunks (host, may be NULL): playables read.
+ *   total_chunks (host, may be NULL): playables read.  Asking for it makes the call wait for the walk (not for the
+ *     ramp + convert kernel), report a stream the walk refuses here instead of at the next ohp_sync, and -- should a
+ *     stream ever have more playables than its region holds (none of this repo's generators produces one; the bound is
+ *     held against exact counts in the tests) -- redo the batch through count + emit.  Without it that case is an
+ *     OHP_E_NO_MEMORY from the next ohp_sync.
+ * One call at a time per context.  Environment (experiments, tests): OHP_STRETCHES=k walks every stream in k stretches of
+ * time, resumable (the form for audio that arrives a window at a time); OHP_ONE_WALK=0 takes count + scan + emit.
  * Errors as ohp_run_streams_host.
  */
 int ohp_run_streams_device(ohp_context* ctx, const ohp_stream_spec* d_streams, size_t n_streams,
