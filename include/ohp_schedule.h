@@ -134,6 +134,61 @@ const char* ohp_schedule_last_error(void);
 void   ohp_schedule_free(ohp_schedule* s);
 
 /*
+ * What a stream's StarvationRamper stage was doing when its reservoir ran dry (OHP_EV_STARVATION): everything the flywheel
+ * ramp it then plays is made from.  ohp_schedule_build records one per starvation event it applies, streams in order
+ * (the class-free walk and the device builders do not: starvations are rare, their flywheel work is planned on the host).
+ * tests/test_elements_vs_reference.py holds the audio planned from these records against what the real StarvationRamper
+ * object plays when it is starved at the same position.
+ *
+ * The element keeps a clone of every MsgAudioPcm and MsgSilence it hands on (ProcessAudioOut, StarvationRamper.cpp:548-577);
+ * only a flywheel ramp and a new stream empty that store -- a MsgHalt does not.  StartFlywheelRamp (:491-536) cuts it to the
+ * last kTrainingJiffies (1 ms) and reads it through FlywheelInput with the messages' ramps cleared, attenuation kept.
+ */
+typedef struct ohp_starvation {
+    uint64_t stream;         /* index into the batch                                                                   */
+    uint64_t pcm_jiffies;    /* PCM of the stream that had passed the element, in jiffies: not always a whole number of
+                                samples (stages before it split messages wherever their events fall)                    */
+    uint32_t event;          /* index of the event in the batch's events array                                          */
+    uint32_t ramp;           /* iCurrentRampValue: Ramp::kMax when running, the value reached when ramping up           */
+    uint32_t plays;          /* 1: StartFlywheelRamp (running, or ramping up and audible, :640-650); 0: nothing to ramp
+                                down from (halted, muted, starting): no flywheel audio                                  */
+    uint32_t recent_jiffies; /* how much of the element's recent audio, counted back from its end, is PCM of one
+                                attenuation and nothing else (no MsgSilence between), saturated at 2^32 - 1.  Below
+                                OHP_FLYWHEEL_TRAINING_JIFFIES the training block holds silence (a MsgSilence that passed,
+                                or the padding of :509-518) or a change of attenuation: ohp_flywheel_plan refuses it    */
+    uint32_t attenuation;    /* MsgAudioPcm attenuation of that PCM (OHP_UNITY_ATTENUATION: none)                        */
+    uint32_t reserved;
+} ohp_starvation;
+size_t ohp_schedule_num_starvations(const ohp_schedule* s);
+const ohp_starvation* ohp_schedule_starvations(const ohp_schedule* s);
+
+/*
+ * The three launches of one starvation, as data:
+ *   FlywheelInput::Prepare over the last kTrainingJiffies of PCM -> prep[0..*n_prep): descriptors with sink
+ *     OHP_OUT_PLANAR32_BE, reading the stream's own bytes in the input arena, writing the training block at training_off;
+ *   FlywheelRamperManager::Ramp -> *job (training block at training_off, generated audio at generated_off of the next
+ *     launch's arenas);
+ *   RampGenerator::Start / EndBlock -> blocks[0..*n_blocks): one ramped descriptor per 1 ms, reading at generated_off,
+ *     writing what the driver reads at out_off.
+ * prep must have room for OHP_FLYWHEEL_MAX_PREP descriptors.  It is one descriptor where the training block is a whole
+ * number of frames T = Jiffies::ToSamples(1 ms).  At the 44.1 kHz family of rates 1 ms is T frames and k jiffies more
+ * (k = 128 from 11.025 kHz up), so the reference's cut leaves T + 1 frames whenever pcm_jiffies falls less than k jiffies
+ * after a sample boundary (always, when the messages are whole samples: MsgAudioPcm::CreatePlayable rounds both ends of
+ * a message down to a sample, Msg.cpp:2234-2262); FlywheelInput sized its planes for T, so every channel's last subsample lands on the
+ * first slot of the next channel's plane and the last channel's beyond the block (StarvationRamper.cpp:90-111, 158-186).
+ * The plan reproduces exactly that block: frames 1 .. T-1 as one descriptor, the first slot of each plane as one
+ * one-subsample descriptor each (mono: frames 0 .. T-1 in one descriptor).  No two descriptors write the same byte.
+ * Returns OHP_OK; OHP_E_INVALID_ARG for a starvation that plays nothing (plays == 0) or whose training block is not PCM of
+ * one attenuation throughout (see recent_jiffies), OHP_E_INVALID_DESC where the reference would ASSERT (rates / channel
+ * counts FlywheelRamper cannot take: ohp_flywheel_validate), OHP_E_NO_MEMORY when cap is too small.
+ */
+#define OHP_FLYWHEEL_MAX_PREP 9u /* 1 + OHP_FLYWHEEL_MAX_CHANNELS */
+int    ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* starvation,
+                         uint64_t training_off, uint64_t generated_off, uint64_t out_off,
+                         ohp_chunk_desc* prep, size_t* n_prep, ohp_flywheel_job* job,
+                         ohp_chunk_desc* blocks, size_t cap, size_t* n_blocks);
+
+/*
  * RampGenerator::Start + EndBlock (Media/Pipeline/StarvationRamper.cpp:235-247, 351-364): the generated flywheel audio
  * of `job` (ohp_flywheel.h), resident at [src_off, ...) of the ramp pass's input arena, leaves as one MsgAudioPcm per
  * 1 ms block, ramped down from current_ramp over the whole generated length (SetMuted once the ramp has reached

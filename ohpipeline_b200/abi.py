@@ -68,6 +68,14 @@ assert CONTAINER_INFO.itemsize == 64
 CONTAINER_WAV, CONTAINER_AIFF, CONTAINER_AIFC = 1, 2, 3
 CONTAINER_OK, CONTAINER_E_UNRECOGNISED, CONTAINER_E_ENDED, CONTAINER_E_CORRUPT, CONTAINER_E_UNSUPPORTED, CONTAINER_E_ARG = range(6)
 
+# include/ohp_schedule.h: ohp_starvation
+STARVATION = np.dtype([
+    ("stream", "<u8"), ("pcm_jiffies", "<u8"), ("event", "<u4"), ("ramp", "<u4"), ("plays", "<u4"), ("recent_jiffies", "<u4"),
+    ("attenuation", "<u4"), ("reserved", "<u4"),
+])
+assert STARVATION.itemsize == 40
+FLYWHEEL_MAX_PREP = 9
+
 # include/ohp_flywheel.h
 FLYWHEEL_JOB = np.dtype([
     ("src_off", "<u8"), ("dst_off", "<u8"), ("sample_rate", "<u4"), ("out_frames", "<u4"),

@@ -121,6 +121,13 @@ def host_lib():
         L.ohp_schedule_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
         L.ohp_schedule_build_walk.restype = C.c_int
         L.ohp_schedule_build_walk.argtypes = L.ohp_schedule_build.argtypes
+        L.ohp_schedule_num_starvations.restype = C.c_size_t
+        L.ohp_schedule_num_starvations.argtypes = [C.c_void_p]
+        L.ohp_schedule_starvations.restype = C.c_void_p
+        L.ohp_schedule_starvations.argtypes = [C.c_void_p]
+        L.ohp_flywheel_plan.restype = C.c_int
+        L.ohp_flywheel_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_size_t),
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ohp_schedule_build_walk_stretches.restype = C.c_int
         L.ohp_schedule_build_walk_stretches.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32,
                                                         C.POINTER(C.c_void_p)]
@@ -243,11 +250,12 @@ def schedule_chunk_bounds(streams, events):
 class Schedule:
     """Result of ohp_schedule_build: chunk descriptors for a batch of streams."""
 
-    def __init__(self, chunks, info, chunk_begin, out_bytes):
+    def __init__(self, chunks, info, chunk_begin, out_bytes, starvations=None):
         self.chunks = chunks
         self.info = info
         self.stream_chunk_begin = chunk_begin
         self.stream_out_bytes = out_bytes
+        self.starvations = starvations if starvations is not None else np.zeros(0, dtype=abi.STARVATION)  # ohp_schedule_build only
 
 
 def schedule_build(streams, events, threads=0, walk=False, stretches=None):
@@ -279,9 +287,31 @@ def schedule_build(streams, events, threads=0, walk=False, stretches=None):
         C.memmove(_ptr(begin), L.ohp_schedule_stream_chunk_begin(h), (ns + 1) * 8)
         if ns:
             C.memmove(_ptr(outb), L.ohp_schedule_stream_out_bytes(h), ns * 8)
+        nst = L.ohp_schedule_num_starvations(h)
+        starved = np.zeros(nst, dtype=abi.STARVATION)
+        if nst:
+            C.memmove(_ptr(starved), L.ohp_schedule_starvations(h), nst * abi.STARVATION.itemsize)
     finally:
         L.ohp_schedule_free(h)
-    return Schedule(chunks, info, begin, outb)
+    return Schedule(chunks, info, begin, outb, starved)
+
+
+def flywheel_plan(stream, starvation, training_off=0, generated_off=0, out_off=0):
+    """ohp_flywheel_plan: the three launches of one starvation as data -> (prep descriptors, job, block descriptors).
+    Raises OhpError where the starvation plays nothing, its training block is not PCM throughout, or the reference would ASSERT."""
+    stream = np.ascontiguousarray(stream, dtype=abi.STREAM_SPEC).reshape(1)
+    starvation = np.ascontiguousarray(starvation, dtype=abi.STARVATION).reshape(1)
+    prep = np.zeros(abi.FLYWHEEL_MAX_PREP, dtype=abi.CHUNK_DESC)
+    job = np.zeros(1, dtype=abi.FLYWHEEL_JOB)
+    blocks = np.zeros(64, dtype=abi.CHUNK_DESC)
+    n = C.c_size_t(0)
+    n_prep = C.c_size_t(0)
+    L = host_lib()
+    rc = L.ohp_flywheel_plan(_ptr(stream), _ptr(starvation), C.c_uint64(training_off), C.c_uint64(generated_off), C.c_uint64(out_off),
+                             _ptr(prep), C.byref(n_prep), _ptr(job), _ptr(blocks), len(blocks), C.byref(n))
+    if rc != 0:
+        raise OhpError(rc, L.ohp_schedule_last_error().decode())
+    return prep[:n_prep.value].copy(), job, blocks[:n.value].copy()
 
 
 # ---------------------------------------------------------------------------------------------------

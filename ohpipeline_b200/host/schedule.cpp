@@ -47,6 +47,7 @@ struct StreamRecord
     std::vector<ohp_chunk_desc> chunks;
     std::vector<ohp_chunk_info> info;
     uint64_t outBytes = 0;
+    std::vector<ohp_starvation> starvations;
 };
 
 class DescSink
@@ -75,6 +76,7 @@ struct ohp_schedule
     std::vector<ohp_chunk_info> info;
     std::vector<uint64_t> chunkBegin;
     std::vector<uint64_t> outBytes;
+    std::vector<ohp_starvation> starvations;
 };
 
 extern "C" {
@@ -112,7 +114,22 @@ int ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams, const o
             DescSink sink(streams[s], recs[s]);
             try {
                 StageChain<MirrorApi, DescSink> chain(factory, streams[s], events + streams[s].first_event, sink);
+                std::vector<StageChain<MirrorApi, DescSink>::Starvation> starved;
+                chain.SetStarvationLog(&starved);
                 const int rc = chain.Run();
+                const uint32_t jps = Jiffies::PerSampleOrZero(streams[s].sample_rate);
+                for (const auto& st : starved) {
+                    ohp_starvation o;
+                    o.stream = s;
+                    o.pcm_jiffies = st.pcmJiffies;
+                    o.event = streams[s].first_event + st.event;
+                    o.ramp = st.ramp;
+                    o.plays = st.plays;
+                    o.recent_jiffies = st.recentJiffies;
+                    o.attenuation = st.attenuation;
+                    o.reserved = 0;
+                    recs[s].starvations.push_back(o);
+                }
                 if (rc != 0) {
                     rcs[(size_t)t] = OHP_E_INVALID_ARG;
                     errs[(size_t)t] = "stream " + std::to_string(s) + ": spec not representable";
@@ -153,6 +170,7 @@ int ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams, const o
         sch->outBytes[s] = recs[s].outBytes;
         sch->chunks.insert(sch->chunks.end(), recs[s].chunks.begin(), recs[s].chunks.end());
         sch->info.insert(sch->info.end(), recs[s].info.begin(), recs[s].info.end());
+        sch->starvations.insert(sch->starvations.end(), recs[s].starvations.begin(), recs[s].starvations.end());
         std::vector<ohp_chunk_desc>().swap(recs[s].chunks);
         std::vector<ohp_chunk_info>().swap(recs[s].info);
     }
@@ -254,8 +272,95 @@ const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s) { return s ? s-
 const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s) { return s ? s->info.data() : nullptr; }
 const uint64_t* ohp_schedule_stream_chunk_begin(const ohp_schedule* s) { return s ? s->chunkBegin.data() : nullptr; }
 const uint64_t* ohp_schedule_stream_out_bytes(const ohp_schedule* s) { return s ? s->outBytes.data() : nullptr; }
+size_t ohp_schedule_num_starvations(const ohp_schedule* s) { return s ? s->starvations.size() : 0; }
+const ohp_starvation* ohp_schedule_starvations(const ohp_schedule* s) { return s ? s->starvations.data() : nullptr; }
 const char* ohp_schedule_last_error(void) { return g_error.c_str(); }
 void ohp_schedule_free(ohp_schedule* s) { delete s; }
+
+int ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* starvation,
+                      uint64_t training_off, uint64_t generated_off, uint64_t out_off,
+                      ohp_chunk_desc* prep, size_t* n_prep, ohp_flywheel_job* job, ohp_chunk_desc* blocks, size_t cap, size_t* n_blocks)
+{
+    if (!stream || !starvation || !prep || !n_prep || !job || (!blocks && cap) || !n_blocks) return OHP_E_INVALID_ARG;
+    *n_blocks = 0;
+    *n_prep = 0;
+    const uint32_t jps = Jiffies::PerSampleOrZero(stream->sample_rate);
+    const uint32_t B = stream->bit_depth / 8u;
+    const uint32_t C = stream->channels;
+    const uint32_t frameBytes = C * B;
+    if (jps == 0 || frameBytes == 0 || !(stream->bit_depth == 8 || stream->bit_depth == 16 || stream->bit_depth == 24 || stream->bit_depth == 32)) {
+        g_error = "flywheel plan: spec not representable";
+        return OHP_E_INVALID_ARG;
+    }
+    if (C > OHP_FLYWHEEL_MAX_CHANNELS) {
+        g_error = "flywheel plan: more channels than FlywheelRamperManager takes";
+        return OHP_E_INVALID_DESC;
+    }
+    if (!starvation->plays) {
+        g_error = "flywheel plan: this starvation plays nothing (the element was halted, muted or had not become audible)";
+        return OHP_E_INVALID_ARG;
+    }
+    if (starvation->recent_jiffies < OHP_FLYWHEEL_TRAINING_JIFFIES || starvation->pcm_jiffies < OHP_FLYWHEEL_TRAINING_JIFFIES) {
+        g_error = "flywheel plan: the last 1 ms the element played is not PCM of one attenuation throughout (silence or padding in the training block: not planned)";
+        return OHP_E_INVALID_ARG;
+    }
+    // StarvationRamper::StartFlywheelRamp (StarvationRamper.cpp:491-536) cuts the recent audio to its last kTrainingJiffies;
+    // MsgAudioPcm::CreatePlayable rounds both ends of every message down to a sample (Msg.cpp:2234-2243): the frames read are
+    const uint64_t lastFrame = starvation->pcm_jiffies / jps;                                     // one past the last
+    const uint64_t firstFrame = (starvation->pcm_jiffies - OHP_FLYWHEEL_TRAINING_JIFFIES) / jps;
+    const uint32_t got = (uint32_t)(lastFrame - firstFrame);
+    // ... and FlywheelInput::Prepare lays its planes out for Jiffies::ToSamples(kTrainingJiffies) of them (:90-98)
+    const uint32_t train = OHP_FLYWHEEL_TRAINING_JIFFIES / jps;
+    if (lastFrame > stream->total_frames || (got != train && got != train + 1) || train < 2) {
+        g_error = "flywheel plan: starvation record does not fit the stream";
+        return OHP_E_INVALID_ARG;
+    }
+    const uint8_t flags = (uint8_t)((stream->in_little_endian && B > 1) ? OHP_F_IN_LITTLE_ENDIAN : 0);
+    auto planar = [&](uint64_t aSrc, uint64_t aDstSlot, uint32_t aBytes, uint32_t aChannels) {
+        // FlywheelPlayableCreator clears the messages' ramps, not their attenuation (:61-74)
+        ohp_chunk_desc& d = prep[(*n_prep)++];
+        std::memset(&d, 0, sizeof d);
+        d.src_off = aSrc;
+        d.dst_off = training_off + aDstSlot * 4u;
+        d.bytes = aBytes;
+        d.ramp_start = (uint16_t)Ramp::kMax;
+        d.ramp_end = (uint16_t)Ramp::kMax;
+        d.attenuation = starvation->attenuation;
+        d.bit_depth = (uint8_t)stream->bit_depth;
+        d.channels = (uint8_t)aChannels;
+        d.flags = flags;
+        d.out_fmt = OHP_OUT_PLANAR32_BE;
+        d.aux = (uint16_t)train;
+    };
+    const uint64_t src = stream->src_base + firstFrame * frameBytes;
+    if (got == train || C == 1) {
+        // mono with a frame too many: the plane's last subsample falls beyond the block (DoProcessFragment, :158-186)
+        planar(src, 0, train * frameBytes, C);
+    }
+    else {
+        // train + 1 frames into planes of train slots: channel c's last subsample is written, last of all, where channel
+        // c + 1's first went; the last channel's falls beyond the block
+        planar(src + frameBytes, 1, (train - 1) * frameBytes, C);
+        planar(src, 0, B, 1);
+        for (uint32_t c = 1; c < C; c++) {
+            planar(src + (uint64_t)train * frameBytes + (c - 1) * B, (uint64_t)c * train, B, 1);
+        }
+    }
+    // FlywheelRamperManager::Ramp for this stream: 20 ms from the 1 ms block (StarvationRamper.cpp:374-375, 422)
+    std::memset(job, 0, sizeof *job);
+    job->src_off = training_off;
+    job->dst_off = generated_off;
+    job->sample_rate = stream->sample_rate;
+    job->out_frames = OHP_FLYWHEEL_RAMP_JIFFIES / jps;
+    job->train_frames = (uint16_t)train;
+    job->channels = (uint8_t)C;
+    job->bit_depth = (uint8_t)stream->bit_depth;
+    // RampGenerator plays it from the element's ramp value down (StarvationRamper.cpp:526-531)
+    const int n = ohp_flywheel_ramp_chunks(job, starvation->ramp, generated_off, out_off, blocks, cap, nullptr);
+    if (n < 0) return -n;
+    *n_blocks = (size_t)n;
+    return OHP_OK;
+}
 
 int ohp_flywheel_ramp_chunks(const ohp_flywheel_job* job, uint32_t current_ramp, uint64_t src_off, uint64_t dst_off,
                              ohp_chunk_desc* out, size_t cap, uint32_t* final_ramp)

@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <deque>
+#include <vector>
 
 #include "../../include/ohp_schedule.h"
 #include "codec_source.h"
@@ -57,9 +58,23 @@ class StageChain
         uint32_t nextEv = 0;
         Element elem = Generic;
         bool halted = true; // Muter::iHalted / StarvationRamper's Halted-or-Starting: no PCM has passed since the start or the last halt
+        uint64_t pcmJiffies = 0; // PCM that has passed the stage (pos counts MsgSilence too)
+        uint64_t pcmRun = 0;     // ... the latest unbroken run of it: nothing but PCM with one attenuation (pcmRunAtt) since the
+        uint32_t pcmRunAtt = OHP_UNITY_ATTENUATION; // stream began, a MsgSilence passed or a flywheel ramp used the recent audio up
+    };
+public:
+    // What a StarvationRamper stage was doing when its reservoir ran dry (OHP_EV_STARVATION): what the flywheel ramp it then
+    // plays is made from (ohp_schedule.h, ohp_starvation).  Stream-local: `event` indexes the stream's own events.
+    struct Starvation
+    {
+        uint32_t event;
+        uint32_t ramp;          // the element's ramp value: what RampGenerator starts from
+        uint32_t plays;         // running, or ramping up and audible: the flywheel ramp plays
+        uint32_t recentJiffies; // the unbroken run of PCM the element's recent audio ends with, saturated
+        uint32_t attenuation;   // ... and the attenuation its messages carry
+        uint64_t pcmJiffies;    // PCM that had passed the element
     };
 
-public:
     StageChain(typename Api::Factory& aFactory, const ohp_stream_spec& aSpec,
                const ohp_ramp_event* aEvents, Sink& aSink)
         : iFactory(aFactory), iSpec(aSpec), iEvents(aEvents), iNumEvents(aSpec.num_events), iSink(aSink)
@@ -77,6 +92,8 @@ public:
             }
         }
     }
+    // Where Run() leaves a record per OHP_EV_STARVATION it applies (null: nowhere).
+    void SetStarvationLog(std::vector<Starvation>* aLog) { iStarvationLog = aLog; }
     // Returns 0, or -2 for a spec the message model cannot represent.  The API's AssertionFailed propagates.
     int Run()
     {
@@ -240,6 +257,7 @@ private:
         MsgAudio* msg = aItem.msg;
         uint32_t ei;
         while (NextStageEvent(aStage, ei) && iEvents[ei].at_jiffies <= s.pos) {
+            NoteStarvation(s, ei);
             ApplyEvent(s, iEvents[ei]);
             s.nextEv = ei + 1;
         }
@@ -247,6 +265,7 @@ private:
             uint32_t at = (uint32_t)(iEvents[ei].at_jiffies - s.pos);
             if (aItem.silence) at -= at % iJps; // silence only splits on sample blocks
             if (at == 0) {
+                NoteStarvation(s, ei);
                 ApplyEvent(s, iEvents[ei]);
                 s.nextEv = ei + 1;
             }
@@ -265,6 +284,7 @@ private:
             if (aItem.silence) {
                 ElementSeesSilence(s);
                 s.pos += msg->Jiffies();
+                s.pcmRun = 0;
                 return;
             }
             s.halted = false; // Muter::ProcessAudio, Muter.cpp:212; StarvationRamper::ProcessMsgOut(MsgAudioPcm), StarvationRamper.cpp:797-799
@@ -290,6 +310,42 @@ private:
             msg->SetMuted();
         }
         s.pos += msg->Jiffies();
+        if (!aItem.silence) {
+            if (s.elem == ElemStarvation) {
+                // the attenuation the message carries: set by the last stage up to this one that has one (every stage whose
+                // attenuation is not unity calls SetAttenuation, above; a message is handed down the chain as soon as a stage
+                // lets go of it, so the stages before this one are still as they were when it passed them)
+                uint32_t att = OHP_UNITY_ATTENUATION;
+                for (unsigned i = aStage + 1; i-- > 0;) {
+                    if (iStages[i].attenuation != OHP_UNITY_ATTENUATION) { att = iStages[i].attenuation; break; }
+                }
+                if (att != s.pcmRunAtt) { s.pcmRun = 0; s.pcmRunAtt = att; }
+            }
+            s.pcmJiffies += msg->Jiffies();
+            s.pcmRun += msg->Jiffies();
+        }
+    }
+    // StarvationRamper keeps a clone of every MsgAudioPcm and MsgSilence it hands on, trimmed to about 1 ms
+    // (ProcessAudioOut, StarvationRamper.cpp:548-577); StartFlywheelRamp (:491-536) cuts that to the last kTrainingJiffies,
+    // reads it through FlywheelInput and leaves it empty.  Only that and a new stream (NewStream, :539-546) empty it: a
+    // MsgHalt does not.  pcmRun is how much of its tail is PCM and nothing else.
+    void NoteStarvation(Stage& s, uint32_t aEvent)
+    {
+        const ohp_ramp_event& e = iEvents[aEvent];
+        if (s.elem != ElemStarvation) return;
+        if (e.op != OHP_EV_STARVATION) return;
+        const bool plays = (s.mode == Running && !s.halted) || (s.mode == RampingUp && s.current != Api::kRampMin); // as ApplyElementEvent
+        if (iStarvationLog != nullptr) {
+            Starvation st;
+            st.event = aEvent;
+            st.plays = plays ? 1u : 0u;
+            st.ramp = s.mode == RampingUp ? s.current : Api::kRampMax;
+            st.recentJiffies = s.pcmRun > 0xffffffffull ? 0xffffffffu : (uint32_t)s.pcmRun;
+            st.attenuation = s.pcmRunAtt;
+            st.pcmJiffies = s.pcmJiffies;
+            iStarvationLog->push_back(st);
+        }
+        if (plays) s.pcmRun = 0;
     }
     void Feed(unsigned aStage, Item aItem)
     {
@@ -347,6 +403,7 @@ private:
     uint32_t iFrameBytes;
     uint32_t iBlockFill;
     int iErr = 0;
+    std::vector<Starvation>* iStarvationLog = nullptr;
     Stage iStages[OHP_MAX_STAGES];
 };
 

@@ -332,6 +332,24 @@ class Ref(_Lib):
         chunks, info, begin, outb = self._collect(res, len(streams), self._free_result)
         return 0, out, chunks, info, begin, outb, gen[:len(streams)].copy()
 
+    def elements_generated_audio(self, stream, events, inp, cap=1 << 22):
+        """ONE stream through the reference's element objects; returns (rc, the bytes a driver reads from the flywheel messages
+        its StarvationRamper plays when it starves -- every starvation, one after the other --, the element's ramp value at each)."""
+        stream = np.ascontiguousarray(stream, dtype=abi.STREAM_SPEC)
+        events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+        inp = np.ascontiguousarray(inp, dtype=np.uint8)
+        audio = np.zeros(cap, dtype=np.uint8)
+        ramps = np.zeros(64, dtype=np.uint32)
+        n = C.c_uint32(0)
+        f = self.lib.ref_elements_generated_audio
+        f.restype = C.c_long
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        got = f(_ptr(stream), _ptr(events), _ptr(inp), _ptr(audio), cap, _ptr(ramps), len(ramps), C.byref(n))
+        if got < 0:
+            return int(got), None, None
+        assert got <= cap
+        return 0, audio[:got].copy(), ramps[:n.value].copy()
+
     def volume_ramper(self, enabled, ramps, kinds):
         """The real VolumeRamper element on one message per ramp (kinds: 0 PCM, 1 silence).  Returns (multipliers handed to
         IVolumeRamper::ApplyVolumeMultiplier, the ramp each message leaves with)."""

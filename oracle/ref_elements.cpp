@@ -237,6 +237,7 @@ private:
     TUint iNextStreamId;
     bool iAtStarvation;
     uint32_t iStarvationArg;
+    uint32_t iAttenuation = OHP_UNITY_ATTENUATION;
     Semaphore iRelease;
 };
 
@@ -293,8 +294,12 @@ Msg* Gate::Fire(const ohp_ramp_event& e)
         iAtStarvationFlag.store(true);
         iRelease.Wait();
         return nullptr;
+    case OHP_EV_SET_ATTENUATION:
+        // what an Attenuator ahead of the element does to every MsgAudioPcm from here on (Attenuator.cpp:55-58)
+        iAttenuation = e.arg;
+        return nullptr;
     default:
-        return nullptr; // OHP_EV_SET_ATTENUATION, OHP_EV_MAX_MSG_JIFFIES and the bare ramp ops have no element to go to
+        return nullptr; // OHP_EV_MAX_MSG_JIFFIES and the bare ramp ops have no element to go to
     }
 }
 
@@ -330,6 +335,7 @@ Msg* Gate::Pull()
             iHeld = audio->Split(at);
         }
         iPos += audio->Jiffies();
+        if (!probe.silence && iAttenuation != OHP_UNITY_ATTENUATION) static_cast<MsgAudioPcm*>(audio)->SetAttenuation(iAttenuation);
         return msg;
     }
 }
@@ -343,8 +349,10 @@ Msg* Gate::Pull()
 class After : public IPipelineElementUpstream
 {
 public:
-    After(IPipelineElementUpstream& aElement, Gate& aGate, StarvationRamper* aStarvation, uint32_t& aGenerated, uint32_t& aHalts)
-        : iElement(aElement), iGate(aGate), iSr(aStarvation), iGenerated(aGenerated), iHalts(aHalts), iProbe(*this) {}
+    After(IPipelineElementUpstream& aElement, Gate& aGate, StarvationRamper* aStarvation, uint32_t& aGenerated, uint32_t& aHalts,
+          std::vector<uint8_t>& aGeneratedAudio, std::vector<uint32_t>& aStarvedAtRamp)
+        : iElement(aElement), iGate(aGate), iSr(aStarvation), iGenerated(aGenerated), iHalts(aHalts), iGeneratedAudio(aGeneratedAudio)
+        , iStarvedAtRamp(aStarvedAtRamp), iProbe(*this) {}
     Msg* Pull() override
     {
         for (;;) {
@@ -366,15 +374,28 @@ public:
                 }
             }
             if (generating) {
-                // the flywheel ramp, then the MsgHalt that ends it (StarvationRamper.cpp:640-650)
+                // the flywheel ramp, then the MsgHalt that ends it (StarvationRamper.cpp:640-650); what a driver would read from
+                // the generated messages is kept (PreDriver -> CreatePlayable -> Read, as for the stream's own audio)
+                iStarvedAtRamp.push_back(iSr->iCurrentRampValue);
                 for (;;) {
                     Msg* msg = iElement.Pull();
                     iProbe.Reset();
                     (void)msg->Process(iProbe);
                     const bool halt = iProbe.halt;
-                    if (iProbe.audio) iGenerated++;
                     if (halt) { iHalts++; static_cast<MsgHalt*>(msg)->ReportHalted(); }
-                    msg->RemoveRef();
+                    if (iProbe.audio && !iProbe.silence) {
+                        iGenerated++;
+                        MsgPlayable* playable = static_cast<MsgAudioPcm*>(iProbe.audio)->CreatePlayable(); // takes the message's reference
+                        ProcessorPcmBufTest proc;
+                        playable->Read(proc);
+                        const Brn bytes = proc.Buf();
+                        iGeneratedAudio.insert(iGeneratedAudio.end(), bytes.Ptr(), bytes.Ptr() + bytes.Bytes());
+                        playable->RemoveRef();
+                    }
+                    else {
+                        if (iProbe.audio) iGenerated++;
+                        msg->RemoveRef();
+                    }
                     if (halt) break;
                 }
                 iGate.ReleaseStarvation();
@@ -409,6 +430,8 @@ private:
     StarvationRamper* iSr;
     uint32_t& iGenerated;
     uint32_t& iHalts;
+    std::vector<uint8_t>& iGeneratedAudio;
+    std::vector<uint32_t>& iStarvedAtRamp;
     Probe iProbe;
 };
 
@@ -419,6 +442,8 @@ struct StreamOut
     uint64_t outBytes = 0;
     uint32_t generated = 0; // flywheel messages the StarvationRamper played (not part of the stream)
     uint32_t halts = 0;
+    std::vector<uint8_t> generatedAudio;   // ... what a driver reads from them (every starvation of the stream, one after the other)
+    std::vector<uint32_t> starvedAtRamp;   // ... the element's iCurrentRampValue when it starved, per starvation
 };
 
 // Pulls the last element until MsgQuit: PreDriver -> CreatePlayable, a driver that pulls fixed blocks (stage_chain.h Drive()).
@@ -544,10 +569,11 @@ int StageKind(const ohp_stream_spec& sp, const ohp_ramp_event* ev, uint32_t stag
         case OHP_EV_MUTER_MUTE: case OHP_EV_MUTER_UNMUTE: of = 2; break;
         case OHP_EV_STARVATION: of = 3; break;
         case OHP_EV_HALT: case OHP_EV_INSERT_SILENCE: break;
-        default: return -1; // the bare ramp ops, attenuation and message caps are the stage MODEL's; no element takes them
+        case OHP_EV_SET_ATTENUATION: if (kind == 0) kind = 4; break; // the stage's Gate alone (an Attenuator ahead of the element, if any)
+        default: return -1; // the bare ramp ops and message caps are the stage MODEL's; no element takes them
         }
         if (of != 0) {
-            if (kind != 0 && kind != of) return -1;
+            if (kind != 0 && kind != 4 && kind != of) return -1;
             kind = of;
             if (ev[i].arg != 0) {
                 if (arg != 0 && arg != ev[i].arg) return -1; // an element has ONE ramp duration
@@ -589,12 +615,16 @@ int RunStream(const ohp_stream_spec& sp, const ohp_ramp_event* events, const uin
             elems.muter[s]->SetAnimator(animator);
             up = elems.muter[s];
         }
+        else if (kind == 4) {
+            up = gate; // no element: the attenuation alone
+            continue;
+        }
         else {
             elems.starvation[s] = new StarvationRamper(*f->factory, *gate, observer, observer, 0x7fffffffu /* never full */, kPriorityNormal,
                                                        arg, 1000);
             up = elems.starvation[s];
         }
-        elems.after[s] = new After(*up, *gate, elems.starvation[s], rec.generated, rec.halts);
+        elems.after[s] = new After(*up, *gate, elems.starvation[s], rec.generated, rec.halts, rec.generatedAudio, rec.starvedAtRamp);
         up = elems.after[s];
     }
     if (rc == 0) {
@@ -741,6 +771,22 @@ int ref_elements_run(const ohp_stream_spec* streams, size_t n_streams, const ohp
     res->stream_chunk_begin[n_streams] = k;
     res->num_chunks = k;
     return 0;
+}
+
+// ONE stream through the element objects, for what its StarvationRamper plays when it starves: the bytes a driver reads from
+// the flywheel messages (every starvation, one after the other) and the ramp value the element had when each began.
+// Returns the number of bytes (copied up to cap), -1 / -2 as ref_elements_run.
+long ref_elements_generated_audio(const ohp_stream_spec* stream, const ohp_ramp_event* events, const uint8_t* in,
+                                  uint8_t* audio, size_t cap, uint32_t* ramps, size_t ramps_cap, uint32_t* n_starvations)
+{
+    StreamOut rec;
+    const int rc = RunStream(*stream, events, in, nullptr, rec);
+    if (rc != 0) return rc;
+    const size_t n = rec.generatedAudio.size() < cap ? rec.generatedAudio.size() : cap;
+    if (n) std::memcpy(audio, rec.generatedAudio.data(), n);
+    for (size_t i = 0; i < rec.starvedAtRamp.size() && i < ramps_cap; i++) ramps[i] = rec.starvedAtRamp[i];
+    if (n_starvations) *n_starvations = (uint32_t)rec.starvedAtRamp.size();
+    return (long)rec.generatedAudio.size();
 }
 
 } // extern "C"

@@ -11,12 +11,15 @@ handed in, the StarvationRamper's reservoir played dry -- each at the stream pos
 
 descriptor for descriptor, and the bytes read out of them must be the port's.  CPU only (tests/test_gpu_schedule.py holds
 the device walk against the golden file recorded here); skipped where oracle/_ref did not travel."""
+import os
+
 import numpy as np
 import pytest
 
 from ohpipeline_b200 import abi, capi, workloads
 
 MS = abi.JIFFIES_PER_MS
+STARVED_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "starvation_flywheel.npz")
 
 
 def one_stream(w, s):
@@ -177,3 +180,151 @@ def test_volume_ramper_hands_on_the_median_multiplier_and_clears_the_ramp(ref):
             assert tuple(int(x) for x in after[i]) == r
     mult, after = ref.volume_ramper(False, ramps, kinds)
     assert len(mult) == 0 and all(tuple(int(x) for x in after[i]) == ramps[i] for i in range(len(ramps)))
+
+
+def _flywheel_on_cpu(port, st, starvation, inp):
+    """ohp_flywheel_plan's three launches, run by the C port: FlywheelInput::Prepare, FlywheelRamperManager::Ramp,
+    RampGenerator's ramped 1 ms blocks -> the bytes a driver reads."""
+    prep, job, blocks = capi.flywheel_plan(st, starvation)
+    assert 1 <= len(prep) <= abi.FLYWHEEL_MAX_PREP
+    rc, training = port.process_chunks(prep, inp, int(job["train_frames"][0]) * 4 * int(st[0]["channels"]))
+    assert rc == 0
+    fb = int(st[0]["channels"]) * int(st[0]["bit_depth"]) // 8
+    rc, raw = port.flywheel(job, training, int(job["out_frames"][0]) * fb)
+    assert rc == 0
+    rc, played = port.process_chunks(blocks, raw, raw.size)
+    assert rc == 0
+    return played
+
+
+@pytest.mark.parametrize("rate,ch,bits,le", [(44100, 2, 16, True), (48000, 2, 24, False), (96000, 2, 24, False), (192000, 2, 24, True),
+                                             (96000, 6, 32, False), (176400, 1, 16, False), (88200, 8, 24, True), (384000, 2, 8, False),
+                                             (32000, 3, 16, True)])
+def test_planned_flywheel_audio_is_what_the_starved_element_plays(ref, port, rate, ch, bits, le):
+    """The real StarvationRamper object, starved at positions aligned to nothing (twice: the second time while it is still
+    ramping up from the first), against ohp_schedule_build's starvation records + ohp_flywheel_plan: the training block is the
+    last millisecond of PCM that passed the element, ramps cleared (FlywheelPlayableCreator, StarvationRamper.cpp:23-88), and
+    RampGenerator starts from the element's ramp value (:526-531)."""
+    jps = abi.jiffies_per_sample(rate)
+    total = rate * 3 // 10
+    spec = workloads._spec(rate, bits, ch, le, workloads.max_chunk_frames(rate, bits, ch), total)
+    first = 37 * MS + 12345
+    second = first + 17 * MS + 777          # 17 ms into the 50 ms ramp up
+    events = [(0, 0, abi.EV_RAMPER_STREAM, 40 * MS),        # a Ramper upstream: its ramp is on the messages the element keeps
+              (first, 1, abi.EV_STARVATION, 50 * MS), (second, 1, abi.EV_STARVATION, 50 * MS)]
+    w = workloads._finish("starved", [spec], [events], seed=77)
+    inp = port.fill_pcm(w.in_bytes, 1000 + rate + ch)
+    rc, audio, ramps = ref.elements_generated_audio(w.streams, w.events, inp)
+    assert rc == 0 and len(ramps) == 2
+    sched = capi.schedule_build(w.streams, w.events)
+    sv = sched.starvations
+    assert len(sv) == 2 and list(sv["plays"]) == [1, 1] and list(sv["event"]) == [1, 2]
+    assert [int(r) for r in sv["ramp"]] == [int(r) for r in ramps]
+    assert int(sv["ramp"][0]) == abi.RAMP_MAX and 0 < int(sv["ramp"][1]) < abi.RAMP_MAX
+    assert [int(f) for f in sv["pcm_jiffies"]] == [first, second]
+    fb = ch * bits // 8
+    per = abi.FLYWHEEL_RAMP_JIFFIES // jps * fb
+    assert audio.size == 2 * per
+    for k in range(2):
+        played = _flywheel_on_cpu(port, w.streams, sv[k:k + 1], inp)
+        assert np.array_equal(played, audio[k * per:(k + 1) * per]), (rate, ch, bits, le, k)
+
+
+def test_starvations_that_play_nothing_are_recorded_as_such(ref, port):
+    """Starved before any audio has passed (Starting / Halted) or again before the ramp up has moved: no flywheel ramp
+    (StarvationRamper.cpp:628-629, 640-650); ohp_flywheel_plan refuses those, and one with under 1 ms of PCM behind it."""
+    w = workloads.config5(n_streams=1, seconds=0.2)
+    st = w.streams.copy()
+    inp = port.fill_pcm(w.in_bytes, 3)
+    at = 12 * MS + MS // 2
+
+    def run(events):
+        ev = workloads._events(sorted(events))
+        st[0]["first_event"], st[0]["num_events"] = 0, len(ev)
+        rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+        assert rc == 0
+        return capi.schedule_build(st, ev).starvations, audio, ramps
+
+    sv, audio, ramps = run([(0, 1, abi.EV_STARVATION, 50 * MS)])
+    assert len(sv) == 1 and int(sv["plays"][0]) == 0 and audio.size == 0 and len(ramps) == 0
+    with pytest.raises(capi.OhpError) as e:
+        capi.flywheel_plan(st, sv[0:1])
+    assert e.value.status == abi.E_INVALID_ARG
+    sv, audio, ramps = run([(at, 1, abi.EV_STARVATION, 50 * MS), (at, 1, abi.EV_STARVATION, 50 * MS)])
+    assert [int(p) for p in sv["plays"]] == [1, 0] and len(ramps) == 1
+    assert np.array_equal(_flywheel_on_cpu(port, st, sv[0:1], inp), audio)
+    # half a millisecond after a MsgHalt: the halt did not empty the element's recent audio, the block reaches back across it
+    sv, audio, ramps = run([(at, 1, abi.EV_HALT, 0), (at + MS // 2, 1, abi.EV_STARVATION, 50 * MS)])
+    assert len(sv) == 1 and int(sv["plays"][0]) == 1 and int(sv["recent_jiffies"][0]) == at + MS // 2 and len(ramps) == 1
+    assert np.array_equal(_flywheel_on_cpu(port, st, sv[0:1], inp), audio)
+    # ... but starved before any audio has followed the halt, it plays nothing
+    sv, audio, ramps = run([(at, 1, abi.EV_HALT, 0), (at, 1, abi.EV_STARVATION, 50 * MS)])
+    assert len(sv) == 1 and int(sv["plays"][0]) == 0 and audio.size == 0
+    # half a millisecond after a MsgSilence: the reference's training block holds the silence; not planned
+    jps = abi.jiffies_per_sample(96000)
+    # (the MsgSilence enters ahead of the message that begins at 15 ms; event positions count it)
+    sv, audio, ramps = run([(15 * MS, 0, abi.EV_INSERT_SILENCE, 96 * jps), (16 * MS + MS // 2, 1, abi.EV_STARVATION, 50 * MS)])
+    assert len(sv) == 1 and int(sv["plays"][0]) == 1 and int(sv["recent_jiffies"][0]) < MS and len(ramps) == 1 and audio.size > 0
+    with pytest.raises(capi.OhpError) as e:
+        capi.flywheel_plan(st, sv[0:1])
+    assert e.value.status == abi.E_INVALID_ARG
+    # ... and 3 ms after it the block is PCM again
+    sv, audio, ramps = run([(15 * MS, 0, abi.EV_INSERT_SILENCE, 96 * jps), (19 * MS, 1, abi.EV_STARVATION, 50 * MS)])
+    assert int(sv["recent_jiffies"][0]) == 3 * MS and int(sv["pcm_jiffies"][0]) == 18 * MS
+    assert np.array_equal(_flywheel_on_cpu(port, st, sv[0:1], inp), audio)
+
+
+def test_planned_flywheel_audio_keeps_the_messages_attenuation(ref, port):
+    """FlywheelPlayableCreator clears a message's ramp, not its attenuation (StarvationRamper.cpp:61-74; MsgPlayablePcm::Read
+    applies it, Msg.cpp ApplyAttenuation): a 16-bit stream attenuated ahead of the element trains the flywheel on the
+    attenuated samples.  A change of attenuation inside the last millisecond is not planned."""
+    rate, ch, bits = 44100, 2, 16
+    total = rate * 2 // 10
+    spec = workloads._spec(rate, bits, ch, False, workloads.max_chunk_frames(rate, bits, ch), total)
+    at = 60 * MS + 4321
+    for att_stage in (0, 1):
+        events = [(10 * MS, att_stage, abi.EV_SET_ATTENUATION, 100), (at, 1, abi.EV_STARVATION, 50 * MS)]
+        w = workloads._finish("starved", [spec], [events], seed=78)
+        inp = port.fill_pcm(w.in_bytes, 555)
+        rc, audio, ramps = ref.elements_generated_audio(w.streams, w.events, inp)
+        assert rc == 0 and len(ramps) == 1
+        sv = capi.schedule_build(w.streams, w.events).starvations
+        assert int(sv["attenuation"][0]) == 100 and int(sv["recent_jiffies"][0]) == at - 10 * MS
+        played = _flywheel_on_cpu(port, w.streams, sv[0:1], inp)
+        assert np.array_equal(played, audio)
+        plain = sv.copy()
+        plain["attenuation"] = abi.UNITY_ATTENUATION
+        assert not np.array_equal(_flywheel_on_cpu(port, w.streams, plain[0:1], inp), audio)
+    events = [(at - MS // 3, 0, abi.EV_SET_ATTENUATION, 100), (at, 1, abi.EV_STARVATION, 50 * MS)]
+    w = workloads._finish("starved", [spec], [events], seed=78)
+    sv = capi.schedule_build(w.streams, w.events).starvations
+    assert int(sv["plays"][0]) == 1 and int(sv["recent_jiffies"][0]) == MS // 3
+    with pytest.raises(capi.OhpError) as e:
+        capi.flywheel_plan(w.streams, sv[0:1])
+    assert e.value.status == abi.E_INVALID_ARG
+
+
+def test_golden_starvation_audio_is_current(ref, port):
+    """tests/golden/starvation_flywheel.npz is what the element object plays today (tests/golden/make_golden_starvation.py)."""
+    from flywheel_util import starved_streams
+    g = np.load(STARVED_GOLDEN)
+    quirk = 0
+    for name, w, seed in starved_streams():
+        inp = port.fill_pcm(w.in_bytes, seed)
+        rc, audio, ramps = ref.elements_generated_audio(w.streams, w.events, inp)
+        assert rc == 0 and np.array_equal(audio, g["audio_" + name]) and np.array_equal(ramps, g["ramps_" + name]), name
+        for sv in capi.schedule_build(w.streams, w.events).starvations:
+            quirk += len(capi.flywheel_plan(w.streams, sv)[0]) > 1
+    assert quirk >= 3, "no stream left a frame too many in its training block"
+
+
+def test_planned_flywheel_audio_reproduces_the_golden_file(port):
+    """No reference needed: the records of ohp_schedule_build, ohp_flywheel_plan and the C port against the recorded audio."""
+    from flywheel_util import starved_streams
+    g = np.load(STARVED_GOLDEN)
+    for name, w, seed in starved_streams():
+        inp = port.fill_pcm(w.in_bytes, seed)
+        sv = capi.schedule_build(w.streams, w.events).starvations
+        assert [int(r) for r in sv["ramp"][sv["plays"] == 1]] == [int(r) for r in g["ramps_" + name]]
+        played = np.concatenate([_flywheel_on_cpu(port, w.streams, sv[k:k + 1], inp) for k in range(len(sv)) if sv["plays"][k]])
+        assert np.array_equal(played, g["audio_" + name]), name

@@ -152,3 +152,43 @@ def test_device_rejects_bad_flywheel_jobs_loudly(ctx):
     # and the context keeps working
     got = run_jobs(ctx, ok, inp, 5760)
     assert got.any()
+
+
+def test_planned_starvations_on_the_gpu_play_what_the_reference_element_plays(ctx, port):
+    """ohp_schedule_build's starvation records -> ohp_flywheel_plan -> the three launches on the device, against
+    tests/golden/starvation_flywheel.npz: what the reference's own StarvationRamper object played when it was starved at the
+    same positions (recorded by tests/golden/make_golden_starvation.py).  Some of these training blocks are a frame too long
+    in the reference (44.1 kHz family): one-subsample planar descriptors at odd offsets."""
+    import torch
+    from flywheel_util import starved_streams
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "starvation_flywheel.npz"))
+    many = 0
+    for name, w, seed in starved_streams():
+        inp = port.fill_pcm(w.in_bytes, seed)
+        d_in = torch.from_numpy(inp).cuda()
+        sv = capi.schedule_build(w.streams, w.events).starvations
+        played = []
+        for k in range(len(sv)):
+            if not sv["plays"][k]:
+                continue
+            prep, job, blocks = capi.flywheel_plan(w.streams, sv[k:k + 1])
+            many += len(prep) > 1
+            ch, B = int(job["channels"][0]), int(job["bit_depth"][0]) // 8
+            train_bytes = int(job["train_frames"][0]) * 4 * ch
+            gen_bytes = int(job["out_frames"][0]) * ch * B
+            d_train = torch.full((train_bytes,), 0xEE, dtype=torch.uint8, device="cuda")
+            d_gen = torch.zeros(gen_bytes, dtype=torch.uint8, device="cuda")
+            d_out = torch.zeros(gen_bytes, dtype=torch.uint8, device="cuda")
+            d_prep = torch.from_numpy(prep.view(np.uint8).copy()).cuda()
+            d_job = torch.from_numpy(job.view(np.uint8).copy()).cuda()
+            d_blocks = torch.from_numpy(blocks.view(np.uint8).copy()).cuda()
+            torch.cuda.synchronize()
+            ctx.process_device(d_prep.data_ptr(), len(prep), d_in.data_ptr(), inp.size, d_train.data_ptr(), train_bytes)
+            ctx.flywheel_device(d_job.data_ptr(), 1, d_train.data_ptr(), train_bytes, d_gen.data_ptr(), gen_bytes)
+            ctx.process_device(d_blocks.data_ptr(), len(blocks), d_gen.data_ptr(), gen_bytes, d_out.data_ptr(), gen_bytes)
+            ctx.sync()
+            rc, want_train = port.process_chunks(prep, inp, train_bytes)
+            assert rc == 0 and np.array_equal(d_train.cpu().numpy(), want_train), (name, k)
+            played.append(d_out.cpu().numpy())
+        assert np.array_equal(np.concatenate(played), g["audio_" + name]), name
+    assert many >= 3
