@@ -103,6 +103,26 @@ def cuda_lib():
             L.ohp_fill_streams_device.restype = C.c_int
             L.ohp_fill_streams_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64,
                                                   C.c_void_p]
+        # include/ohp_multi.h
+        L.ohp_multi_create.restype = C.c_int
+        L.ohp_multi_create.argtypes = [C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_void_p)]
+        L.ohp_multi_destroy.restype = C.c_int
+        L.ohp_multi_destroy.argtypes = [C.c_void_p]
+        L.ohp_multi_num_devices.restype = C.c_size_t
+        L.ohp_multi_num_devices.argtypes = [C.c_void_p]
+        L.ohp_multi_last_error.restype = C.c_char_p
+        L.ohp_multi_last_error.argtypes = [C.c_void_p]
+        L.ohp_multi_shard.restype = None
+        L.ohp_multi_shard.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.ohp_multi_run_streams_host.restype = C.c_int
+        L.ohp_multi_run_streams_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64,
+                                                 C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ohp_multi_host_alloc.restype = C.c_int
+        L.ohp_multi_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.ohp_multi_host_free.restype = C.c_int
+        L.ohp_multi_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.ohp_multi_context.restype = C.c_void_p
+        L.ohp_multi_context.argtypes = [C.c_void_p, C.c_size_t]
         L.ohp_set_timing.restype = C.c_int
         L.ohp_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.ohp_last_kernel_ms.restype = C.c_double
@@ -512,3 +532,66 @@ class Context:
 
     def last_kernel_ms(self):
         return float(self._L.ohp_last_kernel_ms(self._h))
+
+
+def multi_shard(n_streams, n_devices, index):
+    """ohp_multi_shard: (first, count) of the block of streams device `index` of n_devices takes."""
+    first, count = C.c_size_t(0), C.c_size_t(0)
+    cuda_lib().ohp_multi_shard(n_streams, n_devices, index, C.byref(first), C.byref(count))
+    return int(first.value), int(count.value)
+
+
+class MultiContext:
+    """One ohp_multi (include/ohp_multi.h): a context, a host thread and its own CUDA streams per device, streams dealt in
+    contiguous blocks, no collective."""
+
+    def __init__(self, devices):
+        self._L = cuda_lib()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._L.ohp_multi_create(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise OhpError(rc, self._L.ohp_last_error(None).decode())
+        self._h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if self._h:
+            self._L.ohp_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OhpError(rc, self._L.ohp_multi_last_error(self._h).decode())
+
+    def host_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._L.ohp_multi_host_alloc(self._h, nbytes, C.byref(p)))
+        return np.frombuffer((C.c_uint8 * nbytes).from_address(p.value), dtype=np.uint8), p.value
+
+    def host_free(self, ptr):
+        self._check(self._L.ohp_multi_host_free(self._h, C.c_void_p(ptr)))
+
+    def inflight_cap(self, index):
+        return int(self._L.ohp_inflight_cap(C.c_void_p(self._L.ohp_multi_context(self._h, index))))
+
+    def run_streams_host(self, streams, events, inp, out, checksums=True):
+        """ohp_multi_run_streams_host -> (per-stream output bytes, per-stream checksums or None, playables read)."""
+        streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+        events = np.ascontiguousarray(events, dtype=abi.RAMP_EVENT)
+        assert inp.dtype == np.uint8 and out.dtype == np.uint8 and inp.flags.c_contiguous and out.flags.c_contiguous
+        outb = np.zeros(len(streams), dtype=np.uint64)
+        sums = np.zeros(len(streams), dtype=np.uint64) if checksums else None
+        total = C.c_uint64(0)
+        self._check(self._L.ohp_multi_run_streams_host(self._h, _ptr(streams) if len(streams) else None, len(streams),
+                                                       _ptr(events) if len(events) else None, len(events),
+                                                       _ptr(inp) if inp.size else None, inp.size, _ptr(out) if out.size else None, out.size,
+                                                       _ptr(outb) if len(streams) else None,
+                                                       _ptr(sums) if checksums and len(streams) else None, C.byref(total)))
+        return outb, sums, int(total.value)

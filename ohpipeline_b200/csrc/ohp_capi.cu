@@ -809,7 +809,7 @@ int ohp_checksums_device(ohp_context* ctx, const uint8_t* d_out, const uint64_t*
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     uint64_t grid = (uint64_t)ctx->sm_count * 8u;
     if (grid > n_streams) grid = n_streams;
-    checksum_kernel<<<(unsigned)grid, 256, 0, st>>>(d_out, d_stream_off, n_streams, d_sums);
+    checksum_kernel<<<(unsigned)grid, 256, 0, st>>>(d_out, d_stream_off, n_streams, d_sums, 1u);
     OHP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return OHP_OK;
@@ -1536,3 +1536,5 @@ double ohp_last_kernel_ms(ohp_context* ctx)
 }
 
 } // extern "C"
+
+#include "ohp_multi.cuh"

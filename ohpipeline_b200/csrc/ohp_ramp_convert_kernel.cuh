@@ -505,13 +505,14 @@ __global__ void __launch_bounds__(kThreads) ramp_convert_kernel(const KernelPara
     }
 }
 
-// Per-stream checksum: sum_i (byte_i + 1) * (i + 1) mod 2^64 over [off[s], off[s+1]).  One CTA per stream.
+// Per-stream checksum: sum_i (byte_i + 1) * (i + 1) mod 2^64 over [off[s * stride], off[s * stride + 1]): stride 1 for
+// streams that tile the arena (n_streams + 1 offsets), 2 for a (begin, end) pair per stream.  One CTA per stream.
 __global__ void __launch_bounds__(256) checksum_kernel(const uint8_t* __restrict__ out, const uint64_t* __restrict__ off,
-                                                       uint64_t n_streams, uint64_t* __restrict__ sums)
+                                                       uint64_t n_streams, uint64_t* __restrict__ sums, uint32_t stride)
 {
     __shared__ uint64_t s_part[8];
     for (uint64_t s = blockIdx.x; s < n_streams; s += gridDim.x) {
-        const uint64_t lo = off[s], hi = off[s + 1];
+        const uint64_t lo = off[s * stride], hi = off[s * stride + 1];
         const uint8_t* base = out + lo;
         const uint64_t n = hi - lo;
         uint64_t acc = 0;

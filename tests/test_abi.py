@@ -42,6 +42,31 @@ def test_cuda_library_exports_the_flywheel_generator():
         assert hasattr(lib, n), n
 
 
+def test_cuda_library_exports_the_multi_device_driver_and_it_fails_loudly_without_a_gpu():
+    lib = capi.cuda_lib()
+    names = declared_functions("ohp_multi.h")
+    assert names == ["ohp_multi_context", "ohp_multi_create", "ohp_multi_destroy", "ohp_multi_host_alloc", "ohp_multi_host_free",
+                     "ohp_multi_last_error", "ohp_multi_num_devices", "ohp_multi_run_streams_host", "ohp_multi_shard"]
+    for n in names:
+        assert hasattr(lib, n), n
+    # the block rule is sharding.py's (one process per GPU) -- contiguous, sizes differing by at most one, any sizes
+    from ohpipeline_b200 import sharding
+    for n_streams in (0, 1, 7, 1000, 65536, 65537, 2**40 + 3):
+        for n_devices in (1, 2, 3, 8, 64):
+            at = 0
+            for g in range(n_devices):
+                first, count = capi.multi_shard(n_streams, n_devices, g)
+                assert (first, first + count) == sharding.shard_range(n_streams, n_devices, g) and first == at
+                at += count
+            assert at == n_streams
+    if capi.device_count() == 0:
+        with pytest.raises(capi.OhpError) as e:
+            capi.MultiContext([0, 0])
+        assert e.value.status in (abi.E_NO_DEVICE, abi.E_CUDA) and "device 0" in str(e.value)
+    with pytest.raises(capi.OhpError):
+        capi.MultiContext([])
+
+
 def test_host_library_exports_the_container_front_end():
     lib = capi.host_lib()
     names = declared_functions("ohp_container.h")
