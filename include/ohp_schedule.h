@@ -149,13 +149,19 @@ typedef struct ohp_starvation {
     uint64_t pcm_jiffies;    /* PCM of the stream that had passed the element, in jiffies: not always a whole number of
                                 samples (stages before it split messages wherever their events fall)                    */
     uint32_t event;          /* index of the event in the batch's events array                                          */
-    uint32_t ramp;           /* iCurrentRampValue: Ramp::kMax when running, the value reached when ramping up           */
+    uint32_t ramp;           /* iCurrentRampValue, what RampGenerator starts from: what the element's own SetRamp calls last
+                                returned (Ramp::kMax before its first ramp; after a completed ramp up Ramp::kMax too, unless
+                                the messages carried a lower ramp from a stage before it: then where that one stood)     */
     uint32_t plays;          /* 1: StartFlywheelRamp (running, or ramping up and audible, :640-650); 0: nothing to ramp
                                 down from (halted, muted, starting): no flywheel audio                                  */
     uint32_t recent_jiffies; /* how much of the element's recent audio, counted back from its end, is PCM of one
                                 attenuation and nothing else (no MsgSilence between), saturated at 2^32 - 1.  Below
                                 OHP_FLYWHEEL_TRAINING_JIFFIES the training block holds silence (a MsgSilence that passed,
-                                or the padding of :509-518) or a change of attenuation: ohp_flywheel_plan refuses it    */
+                                or the padding of :509-518) or a change of attenuation: ohp_flywheel_plan refuses it.
+                                (With a MsgSilence there the reference itself may never return: its cut, :495-507, splits
+                                the silence at a jiffy count that need not be a whole sample, MsgSilence::SplitCompleted
+                                rounds the front part down, Msg.cpp:2530-2535, and the loop goes on splitting off messages
+                                of zero jiffies -- at 44.1 kHz x 2^n whenever the silence lies under the cut.)             */
     uint32_t attenuation;    /* MsgAudioPcm attenuation of that PCM (OHP_UNITY_ATTENUATION: none)                        */
     uint32_t reserved;
 } ohp_starvation;

@@ -61,6 +61,9 @@ class StageChain
         uint64_t pcmJiffies = 0; // PCM that has passed the stage (pos counts MsgSilence too)
         uint64_t pcmRun = 0;     // ... the latest unbroken run of it: nothing but PCM with one attenuation (pcmRunAtt) since the
         uint32_t pcmRunAtt = OHP_UNITY_ATTENUATION; // stream began, a MsgSilence passed or a flywheel ramp used the recent audio up
+        uint32_t elemRamp = Api::kRampMax; // StarvationRamper::iCurrentRampValue as the element itself keeps it: what SetRamp last
+                                           // returned -- NOT reset to kMax when its ramp up completes, so where the messages carried
+                                           // a lower ramp from upstream it stays at where THAT ramp stood (StarvationRamper.cpp:812-817)
     };
 public:
     // What a StarvationRamper stage was doing when its reservoir ran dry (OHP_EV_STARVATION): what the flywheel ramp it then
@@ -297,6 +300,7 @@ private:
                 }
                 MsgAudio* split = nullptr;
                 s.current = msg->SetRamp(s.current, s.remaining, s.mode == RampingDown ? Api::kDirDown : Api::kDirUp, split);
+                s.elemRamp = s.current;
                 if (split != nullptr) {
                     s.queue.push_front(Item{split, aItem.silence});
                 }
@@ -339,13 +343,13 @@ private:
             Starvation st;
             st.event = aEvent;
             st.plays = plays ? 1u : 0u;
-            st.ramp = s.mode == RampingUp ? s.current : Api::kRampMax;
+            st.ramp = s.elemRamp;
             st.recentJiffies = s.pcmRun > 0xffffffffull ? 0xffffffffu : (uint32_t)s.pcmRun;
             st.attenuation = s.pcmRunAtt;
             st.pcmJiffies = s.pcmJiffies;
             iStarvationLog->push_back(st);
         }
-        if (plays) s.pcmRun = 0;
+        if (plays) { s.pcmRun = 0; s.elemRamp = Api::kRampMin; } // Pull(): FlywheelRamping -> RampingUp from kMin (:651-656)
     }
     void Feed(unsigned aStage, Item aItem)
     {

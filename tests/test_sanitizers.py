@@ -67,10 +67,14 @@ def test_schedule_model_and_walk_under_sanitizers(tmp_path):
             dump(workloads.mixed(n_streams=80, seed=seed, max_frames=5000))
             dump(workloads.steady_edges(seed, n_streams=80))
             dump(workloads.config4(n_streams=40, seconds=0.15, seed=seed))
+            dump(workloads.elements(seed, n_streams=40))   # element state machines; starvations -> ohp_flywheel_plan
         dump(workloads.all_rates(seconds=0.15))
         dump(workloads.config3(n_streams=30, seconds=1.0))
     exe = build(tmp_path, "schedule_fuzz", [os.path.join(HOST, "schedule.cpp"), os.path.join(HOST, "msg_model.cpp")])
-    assert "chunks" in run(exe, path)
+    out = run(exe, path)
+    assert "chunks" in out
+    planned = int(out.split(" starvations planned")[0].split()[-1])
+    assert planned >= 50, out
 
 
 def test_bulk_step_covers_the_steady_stretches(tmp_path):
