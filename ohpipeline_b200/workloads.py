@@ -374,15 +374,18 @@ def mixed(n_streams=64, seed=4, max_frames=6000, with_silence=True, p2=True):
     return _finish("mixed: %d streams, seed %d" % (n_streams, seed), specs, evs, seed=(4 << 32) + seed, slack=slack)
 
 
-def elements(seed, n_streams=24, seconds=0.6, illegal=False):
+def elements(seed, n_streams=24, seconds=0.6, illegal=False, attenuation=False):
     """Streams whose stages ARE the reference's elements (include/ohp_schedule.h, ops 8-12): stage 0 a Ramper (a stream that
     starts with its 50 ms ramp up, sometimes a second MsgDecodedStream mid-stream, MsgHalt), stage 1 a StarvationRamper
     (the reservoir runs dry at positions aligned to nothing: ramp up from silence over 50 ms afterwards, messages held to
     5 ms), stage 2 a Muter (Mute / Unmute in turn, 30 ms ramps, some calls landing inside the ramp the previous one
     started, MsgHalt while ramping down and while muted), MsgSilence entering at the top now and then (every element reacts
     to it differently), a driver pulling fixed blocks on some streams.  tests/test_elements_vs_reference.py runs them
-    through the element objects themselves.  illegal: Mute() twice in a row on some streams -- the reference ASSERTS."""
+    through the element objects themselves.  illegal: Mute() twice in a row on some streams -- the reference ASSERTS.
+    attenuation: on the 16-bit streams an Attenuator ahead of one of the stages changes its mind a few times
+    (OHP_EV_SET_ATTENUATION; drawn from a generator of their own, so the streams are otherwise those of the same seed)."""
     rng = np.random.default_rng(seed)
+    rng_att = np.random.default_rng((seed << 8) | 0xA7)
     specs, evs, slack = [], [], []
     for i in range(n_streams):
         rate = int(rng.choice((44100, 48000, 96000, 192000)))
@@ -429,6 +432,10 @@ def elements(seed, n_streams=24, seconds=0.6, illegal=False):
                 t += at(1, 25 * MS) if rng.random() < 0.4 else 30 * MS + at(0, 60 * MS)
             if rng.random() < 0.4:
                 lst.append((at(0, total_j), 2, abi.EV_HALT, 0))
+        if attenuation and bits == 16:
+            stage = int(rng_att.integers(0, 3))
+            for _ in range(int(rng_att.integers(1, 4))):
+                lst.append((int(rng_att.integers(0, total_j)) // q * q, stage, abi.EV_SET_ATTENUATION, int(rng_att.choice((1, 64, 100, 255, 256)))))
         if use_silence:
             for _ in range(int(rng.integers(1, 4))):
                 sj = int(rng.integers(1, 12 * (rate // 1000) + 1)) * jps

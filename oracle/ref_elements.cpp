@@ -364,6 +364,12 @@ public:
                     iSr->iLock.Signal();
                     if (!empty) break;
                     if (iGate.iAtStarvationFlag.load()) {
+                        // the upstream thread is parked now and enqueues nothing more -- but it may have enqueued its last
+                        // message between the look at the reservoir above and the look at the flag: look again
+                        iSr->iLock.Wait();
+                        const bool stillEmpty = iSr->IsEmpty();
+                        iSr->iLock.Signal();
+                        if (!stillEmpty) break;
                         const bool reacts = iSr->iState == StarvationRamper::State::Running
                                          || (iSr->iState == StarvationRamper::State::RampingUp && iSr->iCurrentRampValue != Ramp::kMin);
                         if (!reacts) { iGate.ReleaseStarvation(); continue; }

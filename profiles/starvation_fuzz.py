@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""What a starved StarvationRamper plays: ohp_schedule_build's starvation records + ohp_flywheel_plan + the C port's three
+steps (FlywheelInput sink, flywheel generator, ramped blocks) against the REFERENCE'S OWN element object
+(oracle/_ref: StarvationRamper.cpp, FlywheelRamper.cpp, Msg.cpp linked unmodified; oracle/ref_elements.cpp stages the
+starvations), on random element schedules (workloads.elements: Ramper / StarvationRamper / Muter stages, halts, inserted
+silence, starvations wherever the PRNG put them).  CPU only; needs oracle/_ref (the build container).
+
+    python profiles/starvation_fuzz.py FIRST_SEED LAST_SEED [SECONDS] > profiles/r02_starvation_fuzz.json
+
+Streams with a MsgSilence inside the last millisecond before a starvation that plays are left out: the reference's own cut
+loop does not terminate on them (include/ohp_schedule.h, ohp_starvation.recent_jiffies)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build()
+from ohpipeline_b200 import abi, capi, workloads  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+
+
+def played_by_plan(port, st, starvation, inp):
+    prep, job, blocks = capi.flywheel_plan(st, starvation)
+    rc, training = port.process_chunks(prep, inp, int(job["train_frames"][0]) * 4 * int(st[0]["channels"]))
+    assert rc == 0
+    fb = int(st[0]["channels"]) * int(st[0]["bit_depth"]) // 8
+    rc, raw = port.flywheel(job, training, int(job["out_frames"][0]) * fb)
+    assert rc == 0
+    rc, out = port.process_chunks(blocks, raw, raw.size)
+    assert rc == 0
+    return out, len(prep) > 1
+
+
+def main():
+    first, last = int(sys.argv[1]), int(sys.argv[2])
+    budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
+    port, ref = pyoracle.Port(), pyoracle.Ref()
+    t0 = time.time()
+    tot = {"seeds": 0, "streams": 0, "starvations_compared": 0, "bytes_compared": 0, "frame_too_many": 0, "ramp_below_max": 0,
+           "played_nothing": 0, "streams_left_out_silence_under_the_cut": 0, "streams_refused_by_model_and_reference": 0,
+           "not_planned_shape": 0, "differences": []}
+    for seed in range(first, last):
+        if time.time() - t0 > budget:
+            break
+        w = workloads.elements(seed, n_streams=24)
+        inp = port.fill_pcm(w.in_bytes, w.seed)
+        tot["seeds"] += 1
+        for s in range(len(w.streams)):
+            st = w.streams[s:s + 1].copy()
+            ev = w.events[int(st[0]["first_event"]):int(st[0]["first_event"]) + int(st[0]["num_events"])].copy()
+            st[0]["first_event"] = 0
+            if not (ev["op"] == abi.EV_STARVATION).any():
+                continue
+            try:
+                sv = capi.schedule_build(st, ev).starvations
+            except capi.OhpError:
+                sv = None
+            if sv is not None and (sv["recent_jiffies"][sv["plays"] == 1] < abi.FLYWHEEL_TRAINING_JIFFIES).any():
+                tot["streams_left_out_silence_under_the_cut"] += 1
+                continue
+            rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+            if (rc != 0) != (sv is None):
+                tot["differences"].append({"seed": seed, "stream": s, "what": "status", "reference": rc})
+                continue
+            if sv is None:
+                tot["streams_refused_by_model_and_reference"] += 1
+                continue
+            tot["streams"] += 1
+            playing = sv[sv["plays"] == 1]
+            tot["played_nothing"] += int((sv["plays"] == 0).sum())
+            jps = abi.jiffies_per_sample(int(st[0]["sample_rate"]))
+            per = abi.FLYWHEEL_RAMP_JIFFIES // jps * int(st[0]["channels"]) * int(st[0]["bit_depth"]) // 8
+            if [int(r) for r in playing["ramp"]] != [int(r) for r in ramps] or audio.size != per * len(playing):
+                tot["differences"].append({"seed": seed, "stream": s, "what": "starvations or ramp values"})
+                continue
+            for k in range(len(playing)):
+                try:
+                    out, many = played_by_plan(port, st, playing[k:k + 1], inp)
+                except capi.OhpError:
+                    tot["not_planned_shape"] += 1
+                    continue
+                if not np.array_equal(out, audio[k * per:(k + 1) * per]):
+                    tot["differences"].append({"seed": seed, "stream": s, "starvation": k, "what": "audio"})
+                tot["starvations_compared"] += 1
+                tot["bytes_compared"] += per
+                tot["frame_too_many"] += int(many)
+                tot["ramp_below_max"] += int(int(playing["ramp"][k]) != abi.RAMP_MAX)
+    tot["first_seed"], tot["seconds"] = first, round(time.time() - t0, 1)
+    print(json.dumps(tot))
+    return 1 if tot["differences"] else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -54,6 +54,44 @@ def test_stage_model_is_the_element_objects(ref, port, seed):
     assert np.array_equal(chunks3, chunks) and np.array_equal(info3, info) and np.array_equal(out3, out)
 
 
+def without_endless_cuts(w):
+    """The streams of w the real StarvationRamper can be put through: not those with a MsgSilence inside the last millisecond
+    before a starvation that plays, where its cut to kTrainingJiffies does not terminate (ohp_schedule.h, recent_jiffies)."""
+    specs, evs = [], []
+    for s in range(len(w.streams)):
+        st, ev = one_stream(w, s)
+        try:
+            sv = capi.schedule_build(st, ev).starvations
+        except capi.OhpError:
+            sv = np.zeros(0, dtype=abi.STARVATION)
+        if (sv["recent_jiffies"][sv["plays"] == 1] < abi.FLYWHEEL_TRAINING_JIFFIES).any():
+            continue
+        specs.append(st[0])
+        evs.append([tuple(int(x) for x in e)[:4] for e in ev])
+    streams = np.array(specs, dtype=abi.STREAM_SPEC)
+    first = 0
+    for i, lst in enumerate(evs):
+        streams[i]["first_event"] = first
+        first += len(lst)
+    return workloads.Workload(w.name, streams, workloads._events([e for lst in evs for e in lst]), w.in_bytes, w.out_bytes, w.seed)
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_attenuated_streams_through_the_element_objects(ref, port, seed):
+    """The same with an Attenuator's SetAttenuation calls (Attenuator.cpp:55-58) landing between the elements of the 16-bit
+    streams: the playables carry the attenuation the messages were given, the bytes are attenuated after the ramp."""
+    w = without_endless_cuts(workloads.elements(seed, n_streams=60, attenuation=True))
+    assert len(w.streams) >= 50 and (w.events["op"] == abi.EV_SET_ATTENUATION).sum() >= 10
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    rc, out, chunks, info, begin, outb, generated = ref.elements_run(w.streams, w.events, inp, w.out_bytes)
+    assert rc == 0
+    assert (chunks["attenuation"] != abi.UNITY_ATTENUATION).sum() >= 50
+    for sched in (capi.schedule_build(w.streams, w.events), capi.schedule_build(w.streams, w.events, walk=True)):
+        assert np.array_equal(sched.chunks, chunks) and np.array_equal(sched.info, info)
+    rc3, out3, chunks3, info3 = port.run(w.streams, w.events, inp, w.out_bytes)
+    assert rc3 == 0 and np.array_equal(chunks3, chunks) and np.array_equal(out3, out)
+
+
 def test_every_stage_on_its_own(ref, port):
     """One element per stream, so that a difference names its element."""
     w = workloads.elements(9, n_streams=30)
