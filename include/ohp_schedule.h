@@ -195,6 +195,35 @@ int    ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* st
                          ohp_chunk_desc* blocks, size_t cap, size_t* n_blocks);
 
 /*
+ * ohp_flywheel_plan for every starvation of a batch at once: the arrays the three launches take.  Starvations that play
+ * nothing, whose training block is not PCM throughout, or whose shape FlywheelRamper does not take are left out (which of
+ * them were planned: ohp_flywheel_batch_planned).  The k-th planned starvation's training block, generated audio and
+ * output lie back to back with the others', each 16-byte aligned, from training_base / generated_base / out_base of the
+ * respective arenas; ohp_flywheel_batch_out_off()[k] .. [k] + ohp_flywheel_batch_out_len()[k] is where the driver
+ * reads what that starving element plays.  On the device:
+ *     ohp_process_device(ctx, prep,   n_prep,   d_pcm,       pcm_bytes,       d_training,  training_bytes,  s);
+ *     ohp_flywheel_device(ctx, jobs,  n_jobs,   d_training,  training_bytes,  d_generated, generated_bytes, s);
+ *     ohp_process_device(ctx, blocks, n_blocks, d_generated, generated_bytes, d_out,       out_bytes,       s);
+ * OHP_E_INVALID_ARG for a record whose stream index is outside the batch.
+ */
+typedef struct ohp_flywheel_batch ohp_flywheel_batch;
+int    ohp_flywheel_plan_batch(const ohp_stream_spec* streams, size_t n_streams,
+                               const ohp_starvation* starvations, size_t n_starvations,
+                               uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out);
+size_t ohp_flywheel_batch_num_planned(const ohp_flywheel_batch* b);
+const uint32_t* ohp_flywheel_batch_planned(const ohp_flywheel_batch* b);   /* indices into `starvations`, ascending      */
+const uint64_t* ohp_flywheel_batch_out_off(const ohp_flywheel_batch* b);   /* per planned starvation                     */
+const uint64_t* ohp_flywheel_batch_out_len(const ohp_flywheel_batch* b);
+size_t ohp_flywheel_batch_num_prep(const ohp_flywheel_batch* b);
+const ohp_chunk_desc* ohp_flywheel_batch_prep(const ohp_flywheel_batch* b);
+const ohp_flywheel_job* ohp_flywheel_batch_jobs(const ohp_flywheel_batch* b); /* one per planned starvation              */
+size_t ohp_flywheel_batch_num_blocks(const ohp_flywheel_batch* b);
+const ohp_chunk_desc* ohp_flywheel_batch_blocks(const ohp_flywheel_batch* b);
+/* how far the three arenas are used: sizes[0] training, [1] generated, [2] out (each including its base) */
+void   ohp_flywheel_batch_arena_bytes(const ohp_flywheel_batch* b, uint64_t sizes[3]);
+void   ohp_flywheel_batch_free(ohp_flywheel_batch* b);
+
+/*
  * RampGenerator::Start + EndBlock (Media/Pipeline/StarvationRamper.cpp:235-247, 351-364): the generated flywheel audio
  * of `job` (ohp_flywheel.h), resident at [src_off, ...) of the ramp pass's input arena, leaves as one MsgAudioPcm per
  * 1 ms block, ramped down from current_ramp over the whole generated length (SetMuted once the ramp has reached

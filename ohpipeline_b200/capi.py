@@ -148,6 +148,17 @@ def host_lib():
         L.ohp_flywheel_plan.restype = C.c_int
         L.ohp_flywheel_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_size_t),
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ohp_flywheel_plan_batch.restype = C.c_int
+        L.ohp_flywheel_plan_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
+                                              C.POINTER(C.c_void_p)]
+        for name in ("num_planned", "num_prep", "num_blocks"):
+            f = getattr(L, "ohp_flywheel_batch_" + name); f.restype = C.c_size_t; f.argtypes = [C.c_void_p]
+        for name in ("planned", "out_off", "out_len", "prep", "jobs", "blocks"):
+            f = getattr(L, "ohp_flywheel_batch_" + name); f.restype = C.c_void_p; f.argtypes = [C.c_void_p]
+        L.ohp_flywheel_batch_arena_bytes.restype = None
+        L.ohp_flywheel_batch_arena_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ohp_flywheel_batch_free.restype = None
+        L.ohp_flywheel_batch_free.argtypes = [C.c_void_p]
         L.ohp_schedule_build_walk_stretches.restype = C.c_int
         L.ohp_schedule_build_walk_stretches.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32,
                                                         C.POINTER(C.c_void_p)]
@@ -178,6 +189,41 @@ def host_lib():
         L.ohp_ramp_split.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _host = L
     return _host
+
+
+class FlywheelBatch:
+    """ohp_flywheel_plan_batch: the arrays of the three launches for every starvation of a batch that plays and is planned."""
+
+    def __init__(self, planned, out_off, out_len, prep, jobs, blocks, arena_bytes):
+        self.planned, self.out_off, self.out_len = planned, out_off, out_len
+        self.prep, self.jobs, self.blocks = prep, jobs, blocks
+        self.training_bytes, self.generated_bytes, self.out_bytes = arena_bytes
+
+
+def flywheel_plan_batch(streams, starvations, training_base=0, generated_base=0, out_base=0):
+    streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
+    starvations = np.ascontiguousarray(starvations, dtype=abi.STARVATION)
+    L = host_lib()
+    h = C.c_void_p()
+    rc = L.ohp_flywheel_plan_batch(_ptr(streams) if len(streams) else None, len(streams),
+                                   _ptr(starvations) if len(starvations) else None, len(starvations),
+                                   C.c_uint64(training_base), C.c_uint64(generated_base), C.c_uint64(out_base), C.byref(h))
+    if rc != 0:
+        raise OhpError(rc, L.ohp_schedule_last_error().decode())
+    try:
+        def take(name, n, dtype):
+            a = np.zeros(n, dtype=dtype)
+            if n:
+                C.memmove(_ptr(a), getattr(L, "ohp_flywheel_batch_" + name)(h), a.nbytes)
+            return a
+        n = L.ohp_flywheel_batch_num_planned(h)
+        sizes = (C.c_uint64 * 3)()
+        L.ohp_flywheel_batch_arena_bytes(h, sizes)
+        return FlywheelBatch(take("planned", n, np.uint32), take("out_off", n, np.uint64), take("out_len", n, np.uint64),
+                             take("prep", L.ohp_flywheel_batch_num_prep(h), abi.CHUNK_DESC), take("jobs", n, abi.FLYWHEEL_JOB),
+                             take("blocks", L.ohp_flywheel_batch_num_blocks(h), abi.CHUNK_DESC), tuple(int(x) for x in sizes))
+    finally:
+        L.ohp_flywheel_batch_free(h)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -9,6 +9,8 @@
 
 #include <string>
 #include <thread>
+#include <memory>
+#include <new>
 #include <vector>
 
 using namespace ohp;
@@ -77,6 +79,15 @@ struct ohp_schedule
     std::vector<uint64_t> chunkBegin;
     std::vector<uint64_t> outBytes;
     std::vector<ohp_starvation> starvations;
+};
+
+struct ohp_flywheel_batch
+{
+    std::vector<uint32_t> planned;
+    std::vector<uint64_t> outOff, outLen;
+    std::vector<ohp_chunk_desc> prep, blocks;
+    std::vector<ohp_flywheel_job> jobs;
+    uint64_t arena[3] = {0, 0, 0};
 };
 
 extern "C" {
@@ -361,6 +372,63 @@ int ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* starv
     *n_blocks = (size_t)n;
     return OHP_OK;
 }
+
+int ohp_flywheel_plan_batch(const ohp_stream_spec* streams, size_t n_streams, const ohp_starvation* starvations, size_t n_starvations,
+                            uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out)
+{
+    if (!out) return OHP_E_INVALID_ARG;
+    *out = nullptr;
+    if ((!streams && n_streams) || (!starvations && n_starvations) || n_starvations > 0xffffffffull) return OHP_E_INVALID_ARG;
+    std::unique_ptr<ohp_flywheel_batch> b(new (std::nothrow) ohp_flywheel_batch());
+    if (!b) return OHP_E_NO_MEMORY;
+    auto align16 = [](uint64_t x) { return (x + 15u) & ~(uint64_t)15u; };
+    uint64_t training = align16(training_base), generated = align16(generated_base), played = align16(out_base);
+    for (size_t k = 0; k < n_starvations; k++) {
+        const ohp_starvation& sv = starvations[k];
+        if (sv.stream >= n_streams) {
+            g_error = "flywheel plan: starvation " + std::to_string(k) + " names a stream outside the batch";
+            return OHP_E_INVALID_ARG;
+        }
+        const ohp_stream_spec& sp = streams[sv.stream];
+        ohp_chunk_desc prep[OHP_FLYWHEEL_MAX_PREP];
+        ohp_chunk_desc blocks[OHP_FLYWHEEL_RAMP_JIFFIES / OHP_FLYWHEEL_BLOCK_JIFFIES + 1];
+        ohp_flywheel_job job;
+        size_t n_prep = 0, n_blocks = 0;
+        const int rc = ohp_flywheel_plan(&sp, &sv, training, generated, played, prep, &n_prep, &job, blocks,
+                                         sizeof blocks / sizeof blocks[0], &n_blocks);
+        if (rc == OHP_E_INVALID_ARG || rc == OHP_E_INVALID_DESC) continue; // plays nothing / not planned / the reference ASSERTs
+        if (rc != OHP_OK) return rc;
+        const uint64_t frame_bytes = (uint64_t)sp.channels * (sp.bit_depth / 8u);
+        const uint64_t out_len = (uint64_t)job.out_frames * frame_bytes;
+        b->planned.push_back((uint32_t)k);
+        b->outOff.push_back(played);
+        b->outLen.push_back(out_len);
+        b->prep.insert(b->prep.end(), prep, prep + n_prep);
+        b->jobs.push_back(job);
+        b->blocks.insert(b->blocks.end(), blocks, blocks + n_blocks);
+        training = align16(training + (uint64_t)job.train_frames * 4u * sp.channels);
+        generated = align16(generated + out_len);
+        played = align16(played + out_len);
+    }
+    b->arena[0] = training; b->arena[1] = generated; b->arena[2] = played;
+    *out = b.release();
+    return OHP_OK;
+}
+
+size_t ohp_flywheel_batch_num_planned(const ohp_flywheel_batch* b) { return b ? b->planned.size() : 0; }
+const uint32_t* ohp_flywheel_batch_planned(const ohp_flywheel_batch* b) { return b ? b->planned.data() : nullptr; }
+const uint64_t* ohp_flywheel_batch_out_off(const ohp_flywheel_batch* b) { return b ? b->outOff.data() : nullptr; }
+const uint64_t* ohp_flywheel_batch_out_len(const ohp_flywheel_batch* b) { return b ? b->outLen.data() : nullptr; }
+size_t ohp_flywheel_batch_num_prep(const ohp_flywheel_batch* b) { return b ? b->prep.size() : 0; }
+const ohp_chunk_desc* ohp_flywheel_batch_prep(const ohp_flywheel_batch* b) { return b ? b->prep.data() : nullptr; }
+const ohp_flywheel_job* ohp_flywheel_batch_jobs(const ohp_flywheel_batch* b) { return b ? b->jobs.data() : nullptr; }
+size_t ohp_flywheel_batch_num_blocks(const ohp_flywheel_batch* b) { return b ? b->blocks.size() : 0; }
+const ohp_chunk_desc* ohp_flywheel_batch_blocks(const ohp_flywheel_batch* b) { return b ? b->blocks.data() : nullptr; }
+void ohp_flywheel_batch_arena_bytes(const ohp_flywheel_batch* b, uint64_t sizes[3])
+{
+    for (int i = 0; i < 3; i++) sizes[i] = b ? b->arena[i] : 0;
+}
+void ohp_flywheel_batch_free(ohp_flywheel_batch* b) { delete b; }
 
 int ohp_flywheel_ramp_chunks(const ohp_flywheel_job* job, uint32_t current_ramp, uint64_t src_off, uint64_t dst_off,
                              ohp_chunk_desc* out, size_t cap, uint32_t* final_ramp)

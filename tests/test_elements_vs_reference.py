@@ -405,3 +405,54 @@ def test_planned_flywheel_audio_on_random_element_schedules(ref, port, seed):
             assert np.array_equal(played, audio[k * per:(k + 1) * per]), (seed, s, k, playing[k])
             compared += 1
     assert compared >= 8, (compared, refused)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_a_batch_of_starvations_in_three_launches(ref, port, seed):
+    """ohp_flywheel_plan_batch: every starvation of a batch of random element schedules that plays, laid out in three arenas and
+    run as THREE calls over the whole batch (the C port standing in for ohp_process_device / ohp_flywheel_device /
+    ohp_process_device); what lands at out_off[k] is what the k-th starving element of the reference played."""
+    w = without_endless_cuts(workloads.elements(seed, n_streams=40))
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    sched = capi.schedule_build(w.streams, w.events)
+    sv = sched.starvations
+    b = capi.flywheel_plan_batch(w.streams, sv, training_base=5, generated_base=40, out_base=100)
+    playing = np.nonzero(sv["plays"] == 1)[0]
+    assert len(b.planned) >= 10 and set(int(k) for k in b.planned) <= set(int(k) for k in playing)
+    assert len(b.jobs) == len(b.planned) and (b.out_off % 16 == 0).all() and int(b.out_off[0]) == 112
+    # what the device calls check before they launch (ohp_validate / ohp_flywheel_validate: host functions of the CUDA library)
+    assert capi.validate(b.prep, w.in_bytes, b.training_bytes) == (abi.OK, 0)
+    assert capi.flywheel_validate(b.jobs, b.training_bytes, b.generated_bytes) == (abi.OK, 0)
+    assert capi.validate(b.blocks, b.generated_bytes, b.out_bytes) == (abi.OK, 0)
+    rc, training = port.process_chunks(b.prep, inp, b.training_bytes)
+    assert rc == 0
+    rc, generated = port.flywheel(b.jobs, training, b.generated_bytes)
+    assert rc == 0
+    rc, out = port.process_chunks(b.blocks, generated, b.out_bytes)
+    assert rc == 0
+    # the reference, stream by stream: its starvations that play, in order
+    at = {int(k): i for i, k in enumerate(b.planned)}
+    compared = 0
+    for s in range(len(w.streams)):
+        mine = [int(k) for k in playing if int(sv["stream"][k]) == s]
+        if not mine:
+            continue
+        st, ev = one_stream(w, s)
+        rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+        assert rc == 0 and len(ramps) == len(mine)
+        per = audio.size // len(mine)
+        for j, k in enumerate(mine):
+            if k not in at:
+                continue
+            i = at[k]
+            assert int(b.out_len[i]) == per
+            assert np.array_equal(out[int(b.out_off[i]):int(b.out_off[i]) + per], audio[j * per:(j + 1) * per]), (s, k)
+            compared += 1
+    assert compared == len(b.planned)
+    # a record that names no stream of the batch
+    bad = sv[:1].copy()
+    bad["stream"] = len(w.streams)
+    with pytest.raises(capi.OhpError) as e:
+        capi.flywheel_plan_batch(w.streams, bad)
+    assert e.value.status == abi.E_INVALID_ARG
+    assert len(capi.flywheel_plan_batch(w.streams, sv[:0]).planned) == 0
