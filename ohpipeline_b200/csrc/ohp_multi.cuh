@@ -196,7 +196,14 @@ static void multi_worker_main(ohp_multi* m, MultiWorker* w)
             seen = m->generation;
             job = m->job;
         }
-        if (w->ctx) (void)multi_run_block(*w, job, m->workers.size());
+        if (w->ctx) {
+            try {
+                (void)multi_run_block(*w, job, m->workers.size());
+            }
+            catch (const std::exception& e) { // the block's re-based specs and staging vectors: out of host memory
+                (void)multi_fail(*w, OHP_E_NO_MEMORY, e.what());
+            }
+        }
         std::lock_guard<std::mutex> g(m->lock);
         if (--m->pending == 0) m->done.notify_all();
     }
