@@ -143,6 +143,10 @@ void   ohp_schedule_free(ohp_schedule* s);
  * The element keeps a clone of every MsgAudioPcm and MsgSilence it hands on (ProcessAudioOut, StarvationRamper.cpp:548-577);
  * only a flywheel ramp and a new stream empty that store -- a MsgHalt does not.  StartFlywheelRamp (:491-536) cuts it to the
  * last kTrainingJiffies (1 ms) and reads it through FlywheelInput with the messages' ramps cleared, attenuation kept.
+ * (Attenuation is applied ONCE here, as everywhere in this library.  The reference attenuates a cell in place whenever a
+ * playable of it is read, Msg.cpp:2736-2756, and the element's clones share their cells with the messages it handed on:
+ * had the driver already read a cell when the element starves, the flywheel would see it attenuated twice -- a matter of
+ * thread timing there, not reproduced; the comparison with the real element is made before anything downstream reads.)
  */
 typedef struct ohp_starvation {
     uint64_t stream;         /* index into the batch                                                                   */
