@@ -100,6 +100,8 @@ class Bwx : public Brx
 public:
     inline TUint MaxBytes() const { return iMaxBytes; }
     inline TUint BytesRemaining() const { return iMaxBytes - iBytes; }
+    using Brx::At;
+    inline TByte& At(TUint aByteIndex) { ASSERT(aByteIndex < iBytes); return const_cast<TByte*>(Ptr())[aByteIndex]; } // (the reference's own tests write through it)
     void SetBytes(TUint aBytes) { ASSERT(aBytes <= iMaxBytes); iBytes = aBytes; }
     void Replace(const Brx& aBuf)
     {

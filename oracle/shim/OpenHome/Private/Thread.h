@@ -104,7 +104,7 @@ class Thread : private INonCopyable
 public:
     static const TUint kDefaultStackBytes = 32 * 1024;
     static const TChar* CurrentThreadName() { return "oracle"; }
-    static void Sleep(TUint /*aMilliSecs*/) {}
+    static void Sleep(TUint aMilliSecs) { std::this_thread::sleep_for(std::chrono::milliseconds(aMilliSecs)); } // (only the reference's tests sleep)
     virtual ~Thread() { Kill(); Join(); }
     void Start() { iThread = std::thread([this] { try { Run(); } catch (ThreadKill&) {} }); }
     void Wait()
