@@ -326,6 +326,19 @@ int ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* starv
         g_error = "flywheel plan: starvation record does not fit the stream";
         return OHP_E_INVALID_ARG;
     }
+    {
+        // what ohp_flywheel_validate / the flywheel kernel refuse (csrc/ohp_flywheel_kernels.cuh, check_job): the reference's
+        // fixed buffers -- FlywheelInput's 7680 bytes (StarvationRamper.cpp:76-83), RampGenerator's 6144 (:215-219) -- and
+        // Burg's method wanting more samples than its degree (FlywheelRamper.cpp:180-195)
+        const uint32_t decimation = (stream->sample_rate == 192000u || stream->sample_rate == 176400u) ? 4u
+                                  : (stream->sample_rate == 88200u || stream->sample_rate == 96000u) ? 2u : 1u; // FlywheelRamper.cpp:330-345
+        const uint32_t blockFrames = OHP_FLYWHEEL_BLOCK_JIFFIES / jps;
+        if (train / decimation < OHP_FLYWHEEL_DEGREE + 1u || train * 4u * C > OHP_FLYWHEEL_MAX_INPUT_BYTES
+            || blockFrames * frameBytes > OHP_FLYWHEEL_MAX_BLOCK_BYTES) {
+            g_error = "flywheel plan: a rate / channel count / depth the reference's flywheel buffers do not hold";
+            return OHP_E_INVALID_DESC;
+        }
+    }
     const uint8_t flags = (uint8_t)((stream->in_little_endian && B > 1) ? OHP_F_IN_LITTLE_ENDIAN : 0);
     auto planar = [&](uint64_t aSrc, uint64_t aDstSlot, uint32_t aBytes, uint32_t aChannels) {
         // FlywheelPlayableCreator clears the messages' ramps, not their attenuation (:61-74)

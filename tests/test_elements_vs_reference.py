@@ -456,3 +456,24 @@ def test_a_batch_of_starvations_in_three_launches(ref, port, seed):
         capi.flywheel_plan_batch(w.streams, bad)
     assert e.value.status == abi.E_INVALID_ARG
     assert len(capi.flywheel_plan_batch(w.streams, sv[:0]).planned) == 0
+
+
+def test_plan_refuses_what_the_flywheel_kernel_refuses():
+    """Shapes the reference's fixed flywheel buffers do not hold (ohp_flywheel_validate): the plan says so, as the launch would."""
+    for rate, ch, bits, ok in [(384000, 8, 32, False), (384000, 6, 8, False), (352800, 5, 24, True), (8000, 2, 16, True),
+                               (7350, 2, 16, True), (192000, 8, 32, True)]:
+        total = rate // 5
+        spec = workloads._spec(rate, bits, ch, False, workloads.max_chunk_frames(rate, bits, ch), total)
+        w = workloads._finish("starved", [spec], [[(30 * MS + 999, 1, abi.EV_STARVATION, 50 * MS)]], seed=80)
+        sv = capi.schedule_build(w.streams, w.events).starvations
+        assert len(sv) == 1 and int(sv["plays"][0]) == 1
+        job = capi.flywheel_job(rate, ch, bits)
+        assert (capi.flywheel_validate(job, 1 << 20, 1 << 24)[0] == abi.OK) == ok, (rate, ch, bits)
+        if ok:
+            prep, planned_job, blocks = capi.flywheel_plan(w.streams, sv[0:1])
+            assert capi.flywheel_validate(planned_job, 1 << 20, 1 << 24) == (abi.OK, 0)
+        else:
+            with pytest.raises(capi.OhpError) as e:
+                capi.flywheel_plan(w.streams, sv[0:1])
+            assert e.value.status == abi.E_INVALID_DESC
+            assert len(capi.flywheel_plan_batch(w.streams, sv).planned) == 0
