@@ -574,7 +574,9 @@ def main():
                 keep_for_e2e.free()
                 keep_for_e2e = None
             r = DeviceRun(ctx, torch, wc_rank, fid, stream)
-            ms = r.timed(r.step, max(5, args.steps // 2), args.warmup, barrier, dist)
+            # configs[4] is the ">= 1 M stream-seconds" case of SURVEY 8d: >= 16 launches of 65536 one-second streams
+            launches_c = max(16 if name == "config5" else 5, args.steps // 2)
+            ms = r.timed(r.step, launches_c, args.warmup, barrier, dist)
             cap = ctx.inflight_cap()
             s_c, ok_c, n_c, kind_c = (r.checksums(), None, 0, "skipped") if args.no_check else r.check_against_reference(args.check_streams, check_threads)
             gathered = sharding.gather_checksums(s_c, total_over_ranks(len(s_c)), world, rank, dist)
@@ -582,6 +584,9 @@ def main():
             ach = r.algo_bytes / (ms * 1e-3) / 1e9
             configs.append({"workload": wc.name, "baseline_config": BASELINE_INDEX[name], "streams_per_gpu": int(r.ns),
                             "chunks_per_launch": int(r.n_chunks), "ms_per_launch": ms, "frac": ach / peak, "gbs_per_gpu": ach,
+                            "launches_timed": launches_c,
+                            "stream_seconds_timed": launches_c * float(total_over_ranks(
+                                int((wc_rank.streams["total_frames"] / wc_rank.streams["sample_rate"]).sum() + 0.5))),
                             "frames_per_s": total_over_ranks(wc_rank.total_frames) / (ms * 1e-3),
                             "bit_exact": None if args.no_check else all_ranks(ok_c), "streams_checked": total_over_ranks(n_c),
                             "checked_against": kind_c, "scaling": scaling, "inflight_chunks_per_cta": cap,
