@@ -175,3 +175,26 @@ def test_headers_are_plain_c99_and_cxx11(tmp_path):
             r = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c", str(src),
                                       "-o", str(tmp_path / "one.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             assert r.returncode == 0, (hdr, cmd, r.stdout[-2000:])
+
+
+def test_a_plain_c99_program_links_and_drives_the_boundary(tmp_path):
+    """tests/c/abi_client.c: nothing but include/*.h and the two shared libraries, strict C99 -- what a cgo / JNI stub binds.
+    The host control plane of one starved stream works from C, the descriptors it produces pass the device calls' own
+    validation, and without a GPU every way into the compute path refuses (no fallback)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    capi.cuda_lib(), capi.host_lib()  # built
+    pkg = os.path.join(ROOT, "ohpipeline_b200")
+    exe = str(tmp_path / "abi_client")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                        os.path.join(ROOT, "tests", "c", "abi_client.c"), "-L" + pkg, "-lohp_b200", "-lohp_host", "-Wl,-rpath," + pkg],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-3000:]
+    out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines() if " " in line)
+    assert int(out["chunks"]) == 22 and int(out["starved_at_ramp"]) == abi.RAMP_MAX
+    if capi.device_count() == 0:
+        assert int(out["devices"]) == 0 and "no CPU fallback" in out["refused"]
