@@ -346,6 +346,28 @@ Msg* Gate::Pull()
 // StarvationRamper this is also where its starvations are staged: its puller thread parks in the Gate at the event's
 // position, the reservoir is played dry, and only then is the element pulled on an empty reservoir
 // (StarvationRamper::Pull, StarvationRamper.cpp:622-673) -- never before, whatever the two threads' timing.
+// StartFlywheelRamp cuts the element's recent audio to its last kTrainingJiffies by splitting the message under the cut
+// (StarvationRamper.cpp:495-507).  A MsgSilence split at a jiffy count that is not a whole sample keeps the whole samples in
+// front (MsgSilence::SplitCompleted, Msg.cpp:2530-2535): less is taken off than asked for, the loop comes round with under a
+// sample of excess, splits off a message of ZERO jiffies, subtracts nothing, and never ends.  The harness looks before it
+// lets the element in: such a starvation ends the stream with -3 instead of hanging the caller.
+struct ReferenceWouldNotReturn {};
+
+static bool CutNeverEnds(StarvationRamper& aSr)
+{
+    if (aSr.iRecentAudioJiffies <= StarvationRamper::kTrainingJiffies) return false;
+    TUint excess = aSr.iRecentAudioJiffies - StarvationRamper::kTrainingJiffies;
+    const TUint jps = Jiffies::PerSample(aSr.iSampleRate);
+    for (Msg* m = aSr.iRecentAudio.iHead; m != nullptr && excess > 0; m = m->iNextMsg) {
+        IsAudio probe;
+        (void)m->Process(probe);
+        const TUint jiffies = probe.audio->Jiffies();
+        if (jiffies > excess) return probe.silence && excess % jps != 0; // the message that is split
+        excess -= jiffies;
+    }
+    return false;
+}
+
 class After : public IPipelineElementUpstream
 {
 public:
@@ -382,6 +404,8 @@ public:
             if (generating) {
                 // the flywheel ramp, then the MsgHalt that ends it (StarvationRamper.cpp:640-650); what a driver would read from
                 // the generated messages is kept (PreDriver -> CreatePlayable -> Read, as for the stream's own audio)
+                // (OHP_REF_LET_IT_RUN=1 lets the element in regardless: how tests show, under a timeout, that it does not come back)
+                if (CutNeverEnds(*iSr) && std::getenv("OHP_REF_LET_IT_RUN") == nullptr) throw ReferenceWouldNotReturn();
                 iStarvedAtRamp.push_back(iSr->iCurrentRampValue);
                 for (;;) {
                     Msg* msg = iElement.Pull();
@@ -591,7 +615,8 @@ int StageKind(const ohp_stream_spec& sp, const ohp_ramp_event* ev, uint32_t stag
 }
 
 // One stream through the real elements.  Returns 0, -1 where the reference ASSERTs (or this harness would have to make a
-// call the reference ASSERTS on), -2 for a schedule this harness cannot stage.
+// call the reference ASSERTS on), -2 for a schedule this harness cannot stage, -3 where the reference would never return
+// (CutNeverEnds above).
 int RunStream(const ohp_stream_spec& sp, const ohp_ramp_event* events, const uint8_t* in, uint8_t* out, StreamOut& rec)
 {
     ElemFactory* f = new ElemFactory(); // leaked when an ASSERT unwinds with messages in flight (see ref_harness.cpp)
@@ -646,6 +671,9 @@ int RunStream(const ohp_stream_spec& sp, const ohp_ramp_event* events, const uin
         catch (Exception& e) {
             if (std::getenv("OHP_REF_TRACE") != nullptr) std::fprintf(stderr, "ref elements: %s at %s:%u\n", e.Message(), e.File(), e.Line());
             rc = -1;
+        }
+        catch (ReferenceWouldNotReturn&) {
+            rc = -3;
         }
     }
     // callers of Mute() still waiting for their mute to complete (it never will: the stream is over)

@@ -55,8 +55,9 @@ def test_stage_model_is_the_element_objects(ref, port, seed):
 
 
 def without_endless_cuts(w):
-    """The streams of w the real StarvationRamper can be put through: not those with a MsgSilence inside the last millisecond
-    before a starvation that plays, where its cut to kTrainingJiffies does not terminate (ohp_schedule.h, recent_jiffies)."""
+    """The streams of w without a MsgSilence inside the last millisecond before a starvation that plays: there the real
+    StarvationRamper's cut to kTrainingJiffies may not terminate (ohp_schedule.h, recent_jiffies; the harness answers -3 for
+    such a stream, and a whole-batch call would stop at it)."""
     specs, evs = [], []
     for s in range(len(w.streams)):
         st, ev = one_stream(w, s)
@@ -477,3 +478,45 @@ def test_plan_refuses_what_the_flywheel_kernel_refuses():
                 capi.flywheel_plan(w.streams, sv[0:1])
             assert e.value.status == abi.E_INVALID_DESC
             assert len(capi.flywheel_plan_batch(w.streams, sv).planned) == 0
+
+
+def test_the_cut_that_never_ends_is_recognised_not_run(ref, port):
+    """44.1 kHz: 1 ms is 44 samples and 128 jiffies.  A MsgSilence, half a millisecond of audio, then the reservoir runs dry:
+    the reference's cut to kTrainingJiffies (StarvationRamper.cpp:495-507) falls inside the silence at a jiffy count that is
+    not a whole sample, MsgSilence::SplitCompleted rounds the front part down (Msg.cpp:2530-2535) and the loop goes on
+    splitting off messages of zero jiffies for ever.  The harness sees it coming (-3, oracle/ref_elements.cpp CutNeverEnds)
+    instead of hanging; the model records the starvation as playing with less than 1 ms of PCM behind it, and the plan
+    refuses it.  The same silence at 48 kHz (1 ms = 48 samples exactly) cuts cleanly and plays."""
+    for rate, never_ends in ((44100, True), (48000, False)):
+        jps = abi.jiffies_per_sample(rate)
+        spec = workloads._spec(rate, 16, 2, False, rate // 200, rate // 5)
+        msg = (rate // 200) * jps                                 # one 5 ms message
+        silence = (rate // 250) * jps                             # 4 ms, enters ahead of the fourth message
+        starve = 3 * msg + silence + (rate // 2000) * jps         # half a millisecond of that message has passed
+        events = [(3 * msg, 0, abi.EV_INSERT_SILENCE, silence), (starve, 1, abi.EV_STARVATION, 50 * MS)]
+        w = workloads._finish("cut", [spec], [events], seed=81)
+        inp = port.fill_pcm(w.in_bytes, 7)
+        sv = capi.schedule_build(w.streams, w.events).starvations
+        assert len(sv) == 1 and int(sv["plays"][0]) == 1 and int(sv["recent_jiffies"][0]) == (rate // 2000) * jps
+        with pytest.raises(capi.OhpError) as e:
+            capi.flywheel_plan(w.streams, sv[0:1])
+        assert e.value.status == abi.E_INVALID_ARG
+        rc, audio, ramps = ref.elements_generated_audio(w.streams, w.events, inp)
+        if never_ends:
+            assert rc == -3
+            assert ref.elements_run(w.streams, w.events, inp, w.out_bytes + (1 << 16), want_audio=False)[0] == -3
+            # ... and it is the reference that does not come back, not the harness being cautious: let in (in a process of
+            # its own), the element is still cutting after five seconds; the 48 kHz stream takes milliseconds
+            import subprocess
+            import sys
+            code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import pyoracle; from ohpipeline_b200 import abi;"
+                    "st = np.frombuffer(bytes.fromhex(%r), dtype=abi.STREAM_SPEC); ev = np.frombuffer(bytes.fromhex(%r), dtype=abi.RAMP_EVENT);"
+                    "print(pyoracle.Ref().elements_generated_audio(st, ev, np.zeros(%d, dtype=np.uint8))[0])"
+                    % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), w.streams.tobytes().hex(), w.events.tobytes().hex(), w.in_bytes))
+            with pytest.raises(subprocess.TimeoutExpired):
+                subprocess.run([sys.executable, "-c", code], env=dict(os.environ, OHP_REF_LET_IT_RUN="1"), timeout=5,
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            done = subprocess.run([sys.executable, "-c", code], timeout=60, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            assert done.returncode == 0 and done.stdout.strip() == "-3", done.stderr[-2000:]
+        else:
+            assert rc == 0 and len(ramps) == 1 and audio.size == abi.FLYWHEEL_RAMP_JIFFIES // jps * 4
