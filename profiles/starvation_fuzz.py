@@ -40,21 +40,25 @@ def played_by_plan(port, st, starvation, inp):
     return out, len(prep) > 1
 
 
-def main():
-    first, last = int(sys.argv[1]), int(sys.argv[2])
-    budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
+KEYS = ("seeds", "streams", "starvations_compared", "bytes_compared", "frame_too_many", "ramp_below_max", "played_nothing",
+        "streams_the_reference_would_not_return_from", "streams_refused_by_model_and_reference", "not_planned")
+
+
+def worker(first, last, only_stream=None):
+    """Seeds [first, last) in THIS process (one stream of one seed when only_stream is given) -> totals."""
+    budget = 1e9
     port, ref = pyoracle.Port(), pyoracle.Ref()
     t0 = time.time()
     tot = {"seeds": 0, "streams": 0, "starvations_compared": 0, "bytes_compared": 0, "frame_too_many": 0, "ramp_below_max": 0,
            "played_nothing": 0, "streams_the_reference_would_not_return_from": 0, "streams_refused_by_model_and_reference": 0,
            "not_planned": 0, "differences": []}
     for seed in range(first, last):
-        if time.time() - t0 > budget:
-            break
         w = workloads.elements(seed, n_streams=24)
         inp = port.fill_pcm(w.in_bytes, w.seed)
         tot["seeds"] += 1
         for s in range(len(w.streams)):
+            if only_stream is not None and s != only_stream:
+                continue
             st = w.streams[s:s + 1].copy()
             ev = w.events[int(st[0]["first_event"]):int(st[0]["first_event"]) + int(st[0]["num_events"])].copy()
             st[0]["first_event"] = 0
@@ -98,6 +102,61 @@ def main():
                 tot["bytes_compared"] += per
                 tot["frame_too_many"] += int(many)
                 tot["ramp_below_max"] += int(int(playing["ramp"][k]) != abi.RAMP_MAX)
+    return tot
+
+
+def run_isolated(args):
+    """A worker in a process of its own: (totals or None, return code)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker"] + [str(a) for a in args],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if r.returncode != 0:
+        return None, r.returncode
+    return json.loads(r.stdout.strip().splitlines()[-1]), 0
+
+
+def main():
+    if sys.argv[1] == "--worker":
+        only = int(sys.argv[4]) if len(sys.argv) > 4 else None
+        print(json.dumps(worker(int(sys.argv[2]), int(sys.argv[3]), only)))
+        return 0
+    first, last = int(sys.argv[1]), int(sys.argv[2])
+    budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
+    t0 = time.time()
+    tot = {k: 0 for k in KEYS}
+    tot["differences"] = []
+    # The reference itself can die: FlywheelRamper::BurgsMethod divides by a 32-bit sum of squares that is left to wrap
+    # (FlywheelRamper.cpp:252-282); wrapped to exactly zero under a numerator that is not, it is an integer division by zero
+    # (SIGFPE) -- with 8-bit audio, whose squares are multiples of 2^16, about once in 2^16 sums.  Seeds run in processes of
+    # their own, 40 at a time; where one dies the seeds, then the streams, are run one by one and the stream is counted.
+    tot["streams_the_reference_died_on"] = []
+
+    def add(t):
+        for k in KEYS:
+            tot[k] += t[k]
+        tot["differences"] += t["differences"]
+
+    seed = first
+    while seed < last and time.time() - t0 < budget:
+        hi = min(seed + 40, last)
+        t, rc = run_isolated([seed, hi])
+        if t is not None:
+            add(t)
+        else:
+            for one in range(seed, hi):
+                t, rc = run_isolated([one, one + 1])
+                if t is not None:
+                    add(t)
+                    continue
+                for stream in range(24):
+                    t, rc = run_isolated([one, one + 1, stream])
+                    if t is not None:
+                        t["seeds"] = 0
+                        add(t)
+                    else:
+                        tot["streams_the_reference_died_on"].append({"seed": one, "stream": stream, "signal": -rc})
+                tot["seeds"] += 1
+        seed = hi
     tot["first_seed"], tot["seconds"] = first, round(time.time() - t0, 1)
     print(json.dumps(tot))
     return 1 if tot["differences"] else 0

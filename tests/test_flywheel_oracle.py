@@ -164,3 +164,43 @@ def test_planar_sink_matches_the_real_flywheel_input(port, ref):
                 rc, got = port.process_chunks(descs, wire, want.size)
                 assert rc == 0
                 assert np.array_equal(got, want), (rate, ch, bits, le, with_silence)
+
+
+def test_burg_denominator_that_wraps_to_zero(port, ref, tmp_path):
+    """FlywheelRamper::BurgsMethod divides by a 32-bit sum of squares that is left to wrap (FlywheelRamper.cpp:252-282).
+    Wrapped to exactly zero under a numerator that is not, the reference takes an integer division by zero and dies (SIGFPE);
+    with 8-bit audio, whose squares are multiples of 2^16, that is about one sum in 2^16 -- a random schedule found one
+    (profiles/starvation_fuzz.py, seed 100226, stream 21, its second starvation).  The port, and the kernel after it, leave
+    that coefficient at 0 (oracle/ohp_oracle.c, csrc/ohp_flywheel_kernels.cuh): a documented deviation, since there is no
+    output of the reference to be equal to.  Here: the reference dies on that training block in a process of its own, the
+    port generates audio, and the same stream's first starvation plays the same in both."""
+    import subprocess
+    import sys
+    from ohpipeline_b200 import workloads
+    w = workloads.elements(100226, n_streams=24)
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    st = w.streams[21:22].copy()
+    ev = w.events[int(st[0]["first_event"]):int(st[0]["first_event"]) + int(st[0]["num_events"])].copy()
+    st[0]["first_event"] = 0
+    assert (int(st[0]["sample_rate"]), int(st[0]["bit_depth"]), int(st[0]["channels"])) == (48000, 8, 2)
+    sv = capi.schedule_build(st, ev).starvations
+    assert len(sv) == 2 and list(sv["plays"]) == [1, 1]
+    blocks = []
+    for k in range(2):
+        prep, job, _ = capi.flywheel_plan(st, sv[k:k + 1])
+        rc, training = port.process_chunks(prep, inp, int(job["train_frames"][0]) * 4 * 2)
+        assert rc == 0
+        rc, out = port.flywheel(job, training, int(job["out_frames"][0]) * 2)
+        assert rc == 0 and out.any()
+        blocks.append((training, out, int(sv["ramp"][k])))
+    # the first starvation: reference and port agree
+    rc, raw, *_ = ref.flywheel(48000, 2, 8, blocks[0][2], blocks[0][0])
+    assert rc == 0 and np.array_equal(raw, blocks[0][1])
+    # the second: the reference does not survive its own arithmetic
+    path = tmp_path / "training.npy"
+    np.save(path, blocks[1][0])
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import pyoracle;"
+            "print(pyoracle.Ref().flywheel(48000, 2, 8, %d, np.load(%r))[0])"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), blocks[1][2], str(path)))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == -8, (r.returncode, r.stdout, r.stderr[-500:])   # SIGFPE
