@@ -199,6 +199,34 @@ int    ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* st
                          ohp_chunk_desc* blocks, size_t cap, size_t* n_blocks);
 
 /*
+ * The same with silence in the last millisecond.  ohp_schedule_build also keeps, per starvation record, the element's recent
+ * audio piece by piece -- every MsgSilence as it passed, PCM in runs of one attenuation -- oldest first, as far back as the
+ * last millisecond needs: record k's pieces are [ohp_schedule_recent_begin(s)[k], ...[k + 1]) of ohp_schedule_recent_audio(s).
+ * ohp_flywheel_plan_recent restates StartFlywheelRamp's cut and FlywheelInput::Prepare on those pieces: silence becomes
+ * silent planar descriptors, every run of PCM its own descriptor with its own attenuation, a frame too many is laid out as
+ * FlywheelInput lays it out.  Refused (OHP_E_INVALID_ARG): a starvation that plays nothing; less than 1 ms in all since
+ * the recent audio was last emptied (the reference pads with silence and hands FlywheelRamper a block of another length);
+ * pieces that give FlywheelInput fewer frames than its planes have (the rest of the plane is whatever the previous
+ * starvation left there); more descriptors than prep_cap.  OHP_E_INVALID_DESC: shapes the flywheel does not take, and THE
+ * CUT THAT NEVER ENDS -- a MsgSilence under the cut at a jiffy count that is not a whole sample: the reference does not
+ * return from that one (recent_jiffies above).
+ */
+typedef struct ohp_recent_audio {
+    uint64_t pcm_jiffies;   /* PCM: where in the stream's PCM the piece begins (jiffies); silence: 0        */
+    uint32_t jiffies;
+    uint32_t silence;       /* 1: a MsgSilence                                                              */
+    uint32_t attenuation;   /* PCM: MsgAudioPcm attenuation of the piece                                    */
+    uint32_t reserved;
+} ohp_recent_audio;
+const ohp_recent_audio* ohp_schedule_recent_audio(const ohp_schedule* s);
+const uint64_t* ohp_schedule_recent_begin(const ohp_schedule* s); /* ohp_schedule_num_starvations(s) + 1 entries */
+int    ohp_flywheel_plan_recent(const ohp_stream_spec* stream, const ohp_starvation* starvation,
+                                const ohp_recent_audio* recent, size_t n_recent,
+                                uint64_t training_off, uint64_t generated_off, uint64_t out_off,
+                                ohp_chunk_desc* prep, size_t prep_cap, size_t* n_prep, ohp_flywheel_job* job,
+                                ohp_chunk_desc* blocks, size_t cap, size_t* n_blocks);
+
+/*
  * ohp_flywheel_plan for every starvation of a batch at once: the arrays the three launches take.  Starvations that play
  * nothing, whose training block is not PCM throughout, or whose shape FlywheelRamper does not take are left out (which of
  * them were planned: ohp_flywheel_batch_planned).  The k-th planned starvation's training block, generated audio and

@@ -75,6 +75,9 @@ STARVATION = np.dtype([
 ])
 assert STARVATION.itemsize == 40
 FLYWHEEL_MAX_PREP = 9
+# include/ohp_schedule.h: ohp_recent_audio
+RECENT_AUDIO = np.dtype([("pcm_jiffies", "<u8"), ("jiffies", "<u4"), ("silence", "<u4"), ("attenuation", "<u4"), ("reserved", "<u4")])
+assert RECENT_AUDIO.itemsize == 24
 
 # include/ohp_flywheel.h
 FLYWHEEL_JOB = np.dtype([

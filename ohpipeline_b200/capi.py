@@ -148,6 +148,14 @@ def host_lib():
         L.ohp_flywheel_plan.restype = C.c_int
         L.ohp_flywheel_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_size_t),
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ohp_schedule_recent_audio.restype = C.c_void_p
+        L.ohp_schedule_recent_audio.argtypes = [C.c_void_p]
+        L.ohp_schedule_recent_begin.restype = C.c_void_p
+        L.ohp_schedule_recent_begin.argtypes = [C.c_void_p]
+        L.ohp_flywheel_plan_recent.restype = C.c_int
+        L.ohp_flywheel_plan_recent.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
+                                               C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_size_t,
+                                               C.POINTER(C.c_size_t)]
         L.ohp_flywheel_plan_batch.restype = C.c_int
         L.ohp_flywheel_plan_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.POINTER(C.c_void_p)]
@@ -189,6 +197,24 @@ def host_lib():
         L.ohp_ramp_split.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _host = L
     return _host
+
+
+def flywheel_plan_recent(stream, starvation, recent, training_off=0, generated_off=0, out_off=0, prep_cap=64):
+    """ohp_flywheel_plan_recent: as flywheel_plan, from the element's recent audio piece by piece (silence included)."""
+    stream = np.ascontiguousarray(stream, dtype=abi.STREAM_SPEC).reshape(1)
+    starvation = np.ascontiguousarray(starvation, dtype=abi.STARVATION).reshape(1)
+    recent = np.ascontiguousarray(recent, dtype=abi.RECENT_AUDIO)
+    prep = np.zeros(max(prep_cap, 1), dtype=abi.CHUNK_DESC)
+    job = np.zeros(1, dtype=abi.FLYWHEEL_JOB)
+    blocks = np.zeros(64, dtype=abi.CHUNK_DESC)
+    n, n_prep = C.c_size_t(0), C.c_size_t(0)
+    L = host_lib()
+    rc = L.ohp_flywheel_plan_recent(_ptr(stream), _ptr(starvation), _ptr(recent) if len(recent) else None, len(recent),
+                                    C.c_uint64(training_off), C.c_uint64(generated_off), C.c_uint64(out_off),
+                                    _ptr(prep), prep_cap, C.byref(n_prep), _ptr(job), _ptr(blocks), len(blocks), C.byref(n))
+    if rc != 0:
+        raise OhpError(rc, L.ohp_schedule_last_error().decode())
+    return prep[:n_prep.value].copy(), job, blocks[:n.value].copy()
 
 
 class FlywheelBatch:
@@ -322,6 +348,11 @@ class Schedule:
         self.stream_chunk_begin = chunk_begin
         self.stream_out_bytes = out_bytes
         self.starvations = starvations if starvations is not None else np.zeros(0, dtype=abi.STARVATION)  # ohp_schedule_build only
+        self.recent = np.zeros(0, dtype=abi.RECENT_AUDIO)       # ... the elements' recent audio, piece by piece
+        self.recent_begin = np.zeros(len(self.starvations) + 1, dtype=np.uint64)  # ... record k's pieces: [begin[k], begin[k + 1])
+
+    def recent_of(self, k):
+        return self.recent[int(self.recent_begin[k]):int(self.recent_begin[k + 1])]
 
 
 def schedule_build(streams, events, threads=0, walk=False, stretches=None):
@@ -357,9 +388,17 @@ def schedule_build(streams, events, threads=0, walk=False, stretches=None):
         starved = np.zeros(nst, dtype=abi.STARVATION)
         if nst:
             C.memmove(_ptr(starved), L.ohp_schedule_starvations(h), nst * abi.STARVATION.itemsize)
+        rbegin = np.zeros(nst + 1, dtype=np.uint64)
+        if not walk:
+            C.memmove(_ptr(rbegin), L.ohp_schedule_recent_begin(h), rbegin.nbytes)
+        recent = np.zeros(int(rbegin[-1]), dtype=abi.RECENT_AUDIO)
+        if len(recent):
+            C.memmove(_ptr(recent), L.ohp_schedule_recent_audio(h), recent.nbytes)
     finally:
         L.ohp_schedule_free(h)
-    return Schedule(chunks, info, begin, outb, starved)
+    sched = Schedule(chunks, info, begin, outb, starved)
+    sched.recent, sched.recent_begin = recent, rbegin
+    return sched
 
 
 def flywheel_plan(stream, starvation, training_off=0, generated_off=0, out_off=0):

@@ -50,6 +50,8 @@ struct StreamRecord
     std::vector<ohp_chunk_info> info;
     uint64_t outBytes = 0;
     std::vector<ohp_starvation> starvations;
+    std::vector<ohp_recent_audio> recent;   // ... their recent audio, piece by piece
+    std::vector<uint64_t> recentCount;      // ... pieces per starvation
 };
 
 class DescSink
@@ -79,6 +81,8 @@ struct ohp_schedule
     std::vector<uint64_t> chunkBegin;
     std::vector<uint64_t> outBytes;
     std::vector<ohp_starvation> starvations;
+    std::vector<ohp_recent_audio> recent;
+    std::vector<uint64_t> recentBegin = std::vector<uint64_t>(1, 0); // starvations.size() + 1
 };
 
 struct ohp_flywheel_batch
@@ -140,6 +144,16 @@ int ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams, const o
                     o.attenuation = st.attenuation;
                     o.reserved = 0;
                     recs[s].starvations.push_back(o);
+                    for (const auto& piece : st.recent) {
+                        ohp_recent_audio a;
+                        a.pcm_jiffies = piece.pcmJiffies;
+                        a.jiffies = piece.jiffies;
+                        a.silence = piece.silence;
+                        a.attenuation = piece.attenuation;
+                        a.reserved = 0;
+                        recs[s].recent.push_back(a);
+                    }
+                    recs[s].recentCount.push_back(st.recent.size());
                 }
                 if (rc != 0) {
                     rcs[(size_t)t] = OHP_E_INVALID_ARG;
@@ -182,6 +196,8 @@ int ohp_schedule_build(const ohp_stream_spec* streams, size_t n_streams, const o
         sch->chunks.insert(sch->chunks.end(), recs[s].chunks.begin(), recs[s].chunks.end());
         sch->info.insert(sch->info.end(), recs[s].info.begin(), recs[s].info.end());
         sch->starvations.insert(sch->starvations.end(), recs[s].starvations.begin(), recs[s].starvations.end());
+        for (const uint64_t n : recs[s].recentCount) sch->recentBegin.push_back(sch->recentBegin.back() + n);
+        sch->recent.insert(sch->recent.end(), recs[s].recent.begin(), recs[s].recent.end());
         std::vector<ohp_chunk_desc>().swap(recs[s].chunks);
         std::vector<ohp_chunk_info>().swap(recs[s].info);
     }
@@ -283,6 +299,8 @@ const ohp_chunk_desc* ohp_schedule_chunks(const ohp_schedule* s) { return s ? s-
 const ohp_chunk_info* ohp_schedule_chunk_info(const ohp_schedule* s) { return s ? s->info.data() : nullptr; }
 const uint64_t* ohp_schedule_stream_chunk_begin(const ohp_schedule* s) { return s ? s->chunkBegin.data() : nullptr; }
 const uint64_t* ohp_schedule_stream_out_bytes(const ohp_schedule* s) { return s ? s->outBytes.data() : nullptr; }
+const ohp_recent_audio* ohp_schedule_recent_audio(const ohp_schedule* s) { return s ? s->recent.data() : nullptr; }
+const uint64_t* ohp_schedule_recent_begin(const ohp_schedule* s) { return s ? s->recentBegin.data() : nullptr; }
 size_t ohp_schedule_num_starvations(const ohp_schedule* s) { return s ? s->starvations.size() : 0; }
 const ohp_starvation* ohp_schedule_starvations(const ohp_schedule* s) { return s ? s->starvations.data() : nullptr; }
 const char* ohp_schedule_last_error(void) { return g_error.c_str(); }
@@ -380,6 +398,160 @@ int ohp_flywheel_plan(const ohp_stream_spec* stream, const ohp_starvation* starv
     job->channels = (uint8_t)C;
     job->bit_depth = (uint8_t)stream->bit_depth;
     // RampGenerator plays it from the element's ramp value down (StarvationRamper.cpp:526-531)
+    const int n = ohp_flywheel_ramp_chunks(job, starvation->ramp, generated_off, out_off, blocks, cap, nullptr);
+    if (n < 0) return -n;
+    *n_blocks = (size_t)n;
+    return OHP_OK;
+}
+
+int ohp_flywheel_plan_recent(const ohp_stream_spec* stream, const ohp_starvation* starvation,
+                             const ohp_recent_audio* recent, size_t n_recent,
+                             uint64_t training_off, uint64_t generated_off, uint64_t out_off,
+                             ohp_chunk_desc* prep, size_t prep_cap, size_t* n_prep, ohp_flywheel_job* job,
+                             ohp_chunk_desc* blocks, size_t cap, size_t* n_blocks)
+{
+    if (!stream || !starvation || (!recent && n_recent) || !prep || !n_prep || !job || (!blocks && cap) || !n_blocks) return OHP_E_INVALID_ARG;
+    *n_blocks = 0;
+    *n_prep = 0;
+    const uint32_t jps = Jiffies::PerSampleOrZero(stream->sample_rate);
+    const uint32_t B = stream->bit_depth / 8u;
+    const uint32_t C = stream->channels;
+    const uint32_t frameBytes = C * B;
+    if (jps == 0 || frameBytes == 0 || !(stream->bit_depth == 8 || stream->bit_depth == 16 || stream->bit_depth == 24 || stream->bit_depth == 32)) {
+        g_error = "flywheel plan: spec not representable";
+        return OHP_E_INVALID_ARG;
+    }
+    if (C > OHP_FLYWHEEL_MAX_CHANNELS) {
+        g_error = "flywheel plan: more channels than FlywheelRamperManager takes";
+        return OHP_E_INVALID_DESC;
+    }
+    if (!starvation->plays) {
+        g_error = "flywheel plan: this starvation plays nothing (the element was halted, muted or had not become audible)";
+        return OHP_E_INVALID_ARG;
+    }
+    const uint32_t train = OHP_FLYWHEEL_TRAINING_JIFFIES / jps;
+    {
+        const uint32_t decimation = (stream->sample_rate == 192000u || stream->sample_rate == 176400u) ? 4u
+                                  : (stream->sample_rate == 88200u || stream->sample_rate == 96000u) ? 2u : 1u;
+        const uint32_t blockFrames = OHP_FLYWHEEL_BLOCK_JIFFIES / jps;
+        if (train < 2 || train / decimation < OHP_FLYWHEEL_DEGREE + 1u || train * 4u * C > OHP_FLYWHEEL_MAX_INPUT_BYTES
+            || blockFrames * frameBytes > OHP_FLYWHEEL_MAX_BLOCK_BYTES) {
+            g_error = "flywheel plan: a rate / channel count / depth the reference's flywheel buffers do not hold";
+            return OHP_E_INVALID_DESC;
+        }
+    }
+    // StartFlywheelRamp's cut (StarvationRamper.cpp:495-507): whole pieces go from the front while more than kTrainingJiffies
+    // is left, the piece under the cut is split
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_recent; i++) total += recent[i].jiffies;
+    if (total < OHP_FLYWHEEL_TRAINING_JIFFIES) {
+        g_error = "flywheel plan: less than 1 ms since the element's recent audio was emptied (the reference pads with silence: not planned)";
+        return OHP_E_INVALID_ARG;
+    }
+    uint64_t excess = total - OHP_FLYWHEEL_TRAINING_JIFFIES;
+    size_t first = 0;
+    ohp_recent_audio head = {0, 0, 0, 0, 0};
+    while (first < n_recent) {
+        head = recent[first];
+        if (excess == 0) break;
+        if (head.jiffies > excess) {
+            if (head.silence && excess % jps != 0) {
+                // MsgSilence::SplitCompleted keeps the whole samples in front (Msg.cpp:2530-2535): less goes than was asked
+                // for, the loop comes round with under a sample of excess and splits off messages of zero jiffies for ever
+                g_error = "flywheel plan: a MsgSilence under the cut at a jiffy count that is not a whole sample: the reference does not return from this starvation";
+                return OHP_E_INVALID_DESC;
+            }
+            head.jiffies -= (uint32_t)excess;
+            if (!head.silence) head.pcm_jiffies += excess;
+            excess = 0;
+            break;
+        }
+        excess -= head.jiffies;
+        first++;
+    }
+    // FlywheelInput::Prepare (:90-111): every piece through CreatePlayable -- both ends of a MsgAudioPcm rounded down to a
+    // sample (Msg.cpp:2234-2243), a MsgSilence whole samples by construction -- frames in the order they are read
+    struct Run { bool silence; uint64_t firstFrame; uint32_t frames; uint32_t attenuation; };
+    std::vector<Run> runs;
+    uint64_t got = 0;
+    for (size_t i = first; i < n_recent; i++) {
+        const ohp_recent_audio& p = (i == first) ? head : recent[i];
+        Run r;
+        r.silence = p.silence != 0;
+        r.attenuation = p.silence ? OHP_UNITY_ATTENUATION : p.attenuation;
+        if (p.silence) {
+            r.firstFrame = 0;
+            r.frames = p.jiffies / jps;
+        }
+        else {
+            r.firstFrame = p.pcm_jiffies / jps;
+            r.frames = (uint32_t)((p.pcm_jiffies + p.jiffies) / jps - r.firstFrame);
+            if ((p.pcm_jiffies + p.jiffies) / jps > stream->total_frames) {
+                g_error = "flywheel plan: a piece of recent audio outside the stream";
+                return OHP_E_INVALID_ARG;
+            }
+        }
+        if (r.frames == 0) continue;
+        got += r.frames;
+        runs.push_back(r);
+    }
+    if (got < train) {
+        g_error = "flywheel plan: the pieces give FlywheelInput fewer frames than its planes have (the rest would be what an earlier starvation left there)";
+        return OHP_E_INVALID_ARG;
+    }
+    if (got > (uint64_t)train + 1u) {
+        g_error = "flywheel plan: recent audio does not fit a starvation record";
+        return OHP_E_INVALID_ARG;
+    }
+    const uint8_t le = (uint8_t)((stream->in_little_endian && B > 1) ? OHP_F_IN_LITTLE_ENDIAN : 0);
+    bool full = false;
+    // frames [aFrom, aFrom + aCount) of run r, channels [aCh, aCh + aChannels), to slot aSlot of plane aCh and on
+    auto emit = [&](const Run& r, uint32_t aFrom, uint32_t aCount, uint32_t aCh, uint32_t aChannels, uint64_t aSlot) {
+        if (*n_prep == prep_cap) { full = true; return; }
+        ohp_chunk_desc& d = prep[(*n_prep)++];
+        std::memset(&d, 0, sizeof d);
+        d.src_off = r.silence ? 0 : stream->src_base + (r.firstFrame + aFrom) * frameBytes + (uint64_t)aCh * B;
+        d.dst_off = training_off + aSlot * 4u;
+        d.bytes = aCount * aChannels * B;
+        d.ramp_start = (uint16_t)Ramp::kMax;
+        d.ramp_end = (uint16_t)Ramp::kMax;
+        d.attenuation = (uint16_t)r.attenuation;
+        d.bit_depth = (uint8_t)stream->bit_depth;
+        d.channels = (uint8_t)aChannels;
+        d.flags = (uint8_t)(r.silence ? OHP_F_SILENCE : le);
+        d.out_fmt = OHP_OUT_PLANAR32_BE;
+        d.aux = (uint16_t)train;
+    };
+    // which frames go out whole: all of them; or, with a frame too many and more than one channel, frames 1 .. train - 1
+    // (every plane's first slot is written last by another frame: DoProcessFragment, :158-186); mono: frames 0 .. train - 1
+    const bool over = got == (uint64_t)train + 1u;
+    const uint64_t lo = (over && C > 1) ? 1 : 0, hi = train; // [lo, hi) in frames read
+    uint64_t at = 0;
+    const Run* firstRun = nullptr;
+    const Run* lastRun = nullptr;
+    for (const Run& r : runs) {
+        if (firstRun == nullptr) firstRun = &r;
+        lastRun = &r;
+        const uint64_t a = at > lo ? at : lo, b = (at + r.frames) < hi ? (at + r.frames) : hi;
+        if (b > a) emit(r, (uint32_t)(a - at), (uint32_t)(b - a), 0, C, a);
+        at += r.frames;
+    }
+    if (over && C > 1) {
+        emit(*firstRun, 0, 1, 0, 1, 0); // plane 0 keeps frame 0's subsample
+        for (uint32_t c = 1; c < C; c++) emit(*lastRun, lastRun->frames - 1, 1, c - 1, 1, (uint64_t)c * train); // the last frame's, one plane on
+    }
+    if (full) {
+        g_error = "flywheel plan: more descriptors than prep_cap";
+        return OHP_E_INVALID_ARG;
+    }
+    std::memset(job, 0, sizeof *job);
+    job->src_off = training_off;
+    job->dst_off = generated_off;
+    job->sample_rate = stream->sample_rate;
+    job->out_frames = OHP_FLYWHEEL_RAMP_JIFFIES / jps;
+    job->train_frames = (uint16_t)train;
+    job->channels = (uint8_t)C;
+    job->bit_depth = (uint8_t)stream->bit_depth;
     const int n = ohp_flywheel_ramp_chunks(job, starvation->ramp, generated_off, out_off, blocks, cap, nullptr);
     if (n < 0) return -n;
     *n_blocks = (size_t)n;

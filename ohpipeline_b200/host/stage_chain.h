@@ -43,6 +43,18 @@ class StageChain
         MsgAudio* msg;
         bool silence;
     };
+public:
+    // A piece of a StarvationRamper stage's recent audio: a MsgSilence as it passed, or PCM (adjacent messages of one
+    // attenuation run together: MsgAudioPcm can be cut anywhere, a MsgSilence only between samples -- Msg.cpp:2522-2545 --
+    // which is why silence stays message by message)
+    struct Recent
+    {
+        uint64_t pcmJiffies; // PCM: where in the stream's PCM it begins
+        uint32_t jiffies;
+        uint32_t silence;
+        uint32_t attenuation;
+    };
+private:
     enum Mode { Running = 0, RampingDown = 1, RampingUp = 2, Muted = 3 };
     // which of the reference's elements a stage is (decided by the ops of its events, see StageElement below)
     enum Element { Generic = 0, ElemRamper = 1, ElemMuter = 2, ElemStarvation = 3, ElemBad = 4 };
@@ -61,6 +73,8 @@ class StageChain
         uint64_t pcmJiffies = 0; // PCM that has passed the stage (pos counts MsgSilence too)
         uint64_t pcmRun = 0;     // ... the latest unbroken run of it: nothing but PCM with one attenuation (pcmRunAtt) since the
         uint32_t pcmRunAtt = OHP_UNITY_ATTENUATION; // stream began, a MsgSilence passed or a flywheel ramp used the recent audio up
+        std::deque<Recent> recent;         // StarvationRamper::iRecentAudio: what the element has handed on, oldest first, cut back
+        uint64_t recentJiffies = 0;        // (whole pieces only) to what still covers the last millisecond
         uint32_t elemRamp = Api::kRampMax; // StarvationRamper::iCurrentRampValue as the element itself keeps it: what SetRamp last
                                            // returned -- NOT reset to kMax when its ramp up completes, so where the messages carried
                                            // a lower ramp from upstream it stays at where THAT ramp stood (StarvationRamper.cpp:812-817)
@@ -76,6 +90,7 @@ public:
         uint32_t recentJiffies; // the unbroken run of PCM the element's recent audio ends with, saturated
         uint32_t attenuation;   // ... and the attenuation its messages carry
         uint64_t pcmJiffies;    // PCM that had passed the element
+        std::vector<Recent> recent; // the element's recent audio, oldest first (covers the last millisecond where that much has passed)
     };
 
     StageChain(typename Api::Factory& aFactory, const ohp_stream_spec& aSpec,
@@ -288,6 +303,7 @@ private:
                 ElementSeesSilence(s);
                 s.pos += msg->Jiffies();
                 s.pcmRun = 0;
+                if (s.elem == ElemStarvation) NoteRecent(s, Recent{0, msg->Jiffies(), 1u, OHP_UNITY_ATTENUATION});
                 return;
             }
             s.halted = false; // Muter::ProcessAudio, Muter.cpp:212; StarvationRamper::ProcessMsgOut(MsgAudioPcm), StarvationRamper.cpp:797-799
@@ -324,6 +340,7 @@ private:
                     if (iStages[i].attenuation != OHP_UNITY_ATTENUATION) { att = iStages[i].attenuation; break; }
                 }
                 if (att != s.pcmRunAtt) { s.pcmRun = 0; s.pcmRunAtt = att; }
+                NoteRecent(s, Recent{s.pcmJiffies, msg->Jiffies(), 0u, att});
             }
             s.pcmJiffies += msg->Jiffies();
             s.pcmRun += msg->Jiffies();
@@ -333,6 +350,39 @@ private:
     // (ProcessAudioOut, StarvationRamper.cpp:548-577); StartFlywheelRamp (:491-536) cuts that to the last kTrainingJiffies,
     // reads it through FlywheelInput and leaves it empty.  Only that and a new stream (NewStream, :539-546) empty it: a
     // MsgHalt does not.  pcmRun is how much of its tail is PCM and nothing else.
+    // ProcessAudioOut (StarvationRamper.cpp:548-577): the clone joins the queue; pieces the last millisecond no longer needs go
+    void NoteRecent(Stage& s, const Recent& aPiece)
+    {
+        if (aPiece.jiffies == 0) return;
+        if (!aPiece.silence && !s.recent.empty()) {
+            Recent& last = s.recent.back();
+            if (!last.silence && last.attenuation == aPiece.attenuation && last.pcmJiffies + last.jiffies == aPiece.pcmJiffies
+                && (uint64_t)last.jiffies + aPiece.jiffies <= 0x7fffffffu) {
+                last.jiffies += aPiece.jiffies;
+                s.recentJiffies += aPiece.jiffies;
+                TrimRecent(s);
+                return;
+            }
+        }
+        s.recent.push_back(aPiece);
+        s.recentJiffies += aPiece.jiffies;
+        TrimRecent(s);
+    }
+    static void TrimRecent(Stage& s)
+    {
+        while (s.recent.size() > 1 && s.recentJiffies - s.recent.front().jiffies >= OHP_FLYWHEEL_TRAINING_JIFFIES) {
+            s.recentJiffies -= s.recent.front().jiffies;
+            s.recent.pop_front();
+        }
+        // a long run of PCM: only its tail matters (kept generously: a MsgAudioPcm can be cut anywhere)
+        Recent& front = s.recent.front();
+        if (!front.silence && s.recent.size() == 1 && front.jiffies > 4u * OHP_FLYWHEEL_TRAINING_JIFFIES) {
+            const uint32_t drop = front.jiffies - 2u * OHP_FLYWHEEL_TRAINING_JIFFIES;
+            front.pcmJiffies += drop;
+            front.jiffies -= drop;
+            s.recentJiffies -= drop;
+        }
+    }
     void NoteStarvation(Stage& s, uint32_t aEvent)
     {
         const ohp_ramp_event& e = iEvents[aEvent];
@@ -347,9 +397,10 @@ private:
             st.recentJiffies = s.pcmRun > 0xffffffffull ? 0xffffffffu : (uint32_t)s.pcmRun;
             st.attenuation = s.pcmRunAtt;
             st.pcmJiffies = s.pcmJiffies;
+            st.recent.assign(s.recent.begin(), s.recent.end());
             iStarvationLog->push_back(st);
         }
-        if (plays) { s.pcmRun = 0; s.elemRamp = Api::kRampMin; } // Pull(): FlywheelRamping -> RampingUp from kMin (:651-656)
+        if (plays) { s.pcmRun = 0; s.elemRamp = Api::kRampMin; s.recent.clear(); s.recentJiffies = 0; } // Pull(): FlywheelRamping -> RampingUp from kMin (:651-656)
     }
     void Feed(unsigned aStage, Item aItem)
     {

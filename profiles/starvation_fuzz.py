@@ -28,8 +28,8 @@ from ohpipeline_b200 import abi, capi, workloads  # noqa: E402
 from oracle import pyoracle  # noqa: E402
 
 
-def played_by_plan(port, st, starvation, inp):
-    prep, job, blocks = capi.flywheel_plan(st, starvation)
+def played_by_plan(port, st, starvation, recent, inp):
+    prep, job, blocks = capi.flywheel_plan_recent(st, starvation, recent)
     rc, training = port.process_chunks(prep, inp, int(job["train_frames"][0]) * 4 * int(st[0]["channels"]))
     assert rc == 0
     fb = int(st[0]["channels"]) * int(st[0]["bit_depth"]) // 8
@@ -41,7 +41,8 @@ def played_by_plan(port, st, starvation, inp):
 
 
 KEYS = ("seeds", "streams", "starvations_compared", "bytes_compared", "frame_too_many", "ramp_below_max", "played_nothing",
-        "streams_the_reference_would_not_return_from", "streams_refused_by_model_and_reference", "not_planned")
+        "streams_the_reference_would_not_return_from", "streams_refused_by_model_and_reference", "not_planned",
+        "with_silence_in_the_block")
 
 
 def worker(first, last, only_stream=None):
@@ -51,7 +52,7 @@ def worker(first, last, only_stream=None):
     t0 = time.time()
     tot = {"seeds": 0, "streams": 0, "starvations_compared": 0, "bytes_compared": 0, "frame_too_many": 0, "ramp_below_max": 0,
            "played_nothing": 0, "streams_the_reference_would_not_return_from": 0, "streams_refused_by_model_and_reference": 0,
-           "not_planned": 0, "differences": []}
+           "not_planned": 0, "with_silence_in_the_block": 0, "differences": []}
     for seed in range(first, last):
         w = workloads.elements(seed, n_streams=24)
         inp = port.fill_pcm(w.in_bytes, w.seed)
@@ -65,15 +66,23 @@ def worker(first, last, only_stream=None):
             if not (ev["op"] == abi.EV_STARVATION).any():
                 continue
             try:
-                sv = capi.schedule_build(st, ev).starvations
+                sched = capi.schedule_build(st, ev)
+                sv = sched.starvations
             except capi.OhpError:
-                sv = None
+                sched = sv = None
             rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
             if rc == -3:
                 # the reference's own cut loop would not terminate (oracle/ref_elements.cpp, CutNeverEnds): the model must have
                 # seen silence under the cut too
-                if sv is None or not (sv["recent_jiffies"][sv["plays"] == 1] < abi.FLYWHEEL_TRAINING_JIFFIES).any():
-                    tot["differences"].append({"seed": seed, "stream": s, "what": "reference would not return, model saw nothing"})
+                seen = False
+                if sv is not None:
+                    for k in np.nonzero(sv["plays"] == 1)[0]:
+                        try:
+                            capi.flywheel_plan_recent(st, sv[k:k + 1], sched.recent_of(int(k)))
+                        except capi.OhpError as e:
+                            seen = seen or (e.status == abi.E_INVALID_DESC and "does not return" in str(e))
+                if not seen:
+                    tot["differences"].append({"seed": seed, "stream": s, "what": "reference would not return, the plan does not say so"})
                 tot["streams_the_reference_would_not_return_from"] += 1
                 continue
             if (rc != 0) != (sv is None):
@@ -83,7 +92,8 @@ def worker(first, last, only_stream=None):
                 tot["streams_refused_by_model_and_reference"] += 1
                 continue
             tot["streams"] += 1
-            playing = sv[sv["plays"] == 1]
+            playing_at = np.nonzero(sv["plays"] == 1)[0]
+            playing = sv[playing_at]
             tot["played_nothing"] += int((sv["plays"] == 0).sum())
             jps = abi.jiffies_per_sample(int(st[0]["sample_rate"]))
             per = abi.FLYWHEEL_RAMP_JIFFIES // jps * int(st[0]["channels"]) * int(st[0]["bit_depth"]) // 8
@@ -92,9 +102,13 @@ def worker(first, last, only_stream=None):
                 continue
             for k in range(len(playing)):
                 try:
-                    out, many = played_by_plan(port, st, playing[k:k + 1], inp)
-                except capi.OhpError:
-                    tot["not_planned"] += 1  # silence (or a change of attenuation) inside the last millisecond, or a shape the flywheel does not take
+                    pieces = sched.recent_of(int(playing_at[k]))
+                    out, many = played_by_plan(port, st, playing[k:k + 1], pieces, inp)
+                    tot["with_silence_in_the_block"] += int((pieces["silence"] != 0).any() and int(playing["recent_jiffies"][k]) < abi.FLYWHEEL_TRAINING_JIFFIES)
+                except capi.OhpError as e:
+                    if "does not return" in str(e):
+                        tot["differences"].append({"seed": seed, "stream": s, "starvation": k, "what": "the plan says the reference does not return; it did"})
+                    tot["not_planned"] += 1  # under 1 ms since the recent audio was emptied, too few frames for the planes, a shape the flywheel does not take
                     continue
                 if not np.array_equal(out, audio[k * per:(k + 1) * per]):
                     tot["differences"].append({"seed": seed, "stream": s, "starvation": k, "what": "audio"})

@@ -11,11 +11,23 @@ static int plan_starvations(const ohp_stream_spec& one, const ohp_schedule* a, u
     const ohp_starvation* sv = ohp_schedule_starvations(a);
     const uint64_t fb = (uint64_t)one.channels * (one.bit_depth / 8u);
     for (size_t k = 0; k < ohp_schedule_num_starvations(a); k++) {
-        ohp_chunk_desc* prep = (ohp_chunk_desc*)malloc(sizeof(ohp_chunk_desc) * OHP_FLYWHEEL_MAX_PREP);
+      // twice: the PCM-only plan, then the plan from the recent audio piece by piece (exact-size copy of the pieces)
+      for (int from_recent = 0; from_recent < 2; from_recent++) {
+        const size_t prep_cap = from_recent ? 48 : OHP_FLYWHEEL_MAX_PREP;
+        ohp_chunk_desc* prep = (ohp_chunk_desc*)malloc(sizeof(ohp_chunk_desc) * prep_cap);
         ohp_chunk_desc* blocks = (ohp_chunk_desc*)malloc(sizeof(ohp_chunk_desc) * 24);
         ohp_flywheel_job job;
         size_t np = 0, nb = 0;
-        const int rc = ohp_flywheel_plan(&one, &sv[k], 0, 0, 0, prep, &np, &job, blocks, 24, &nb);
+        int rc;
+        if (from_recent) {
+            const uint64_t* rb = ohp_schedule_recent_begin(a);
+            const size_t nr = (size_t)(rb[k + 1] - rb[k]);
+            ohp_recent_audio* pieces = (ohp_recent_audio*)malloc(sizeof(ohp_recent_audio) * (nr ? nr : 1));
+            if (nr) memcpy(pieces, ohp_schedule_recent_audio(a) + rb[k], nr * sizeof(ohp_recent_audio));
+            rc = ohp_flywheel_plan_recent(&one, &sv[k], pieces, nr, 0, 0, 0, prep, prep_cap, &np, &job, blocks, 24, &nb);
+            free(pieces);
+        }
+        else rc = ohp_flywheel_plan(&one, &sv[k], 0, 0, 0, prep, &np, &job, blocks, 24, &nb);
         if (rc == OHP_OK) {
             planned++;
             const uint64_t slots = (uint64_t)job.train_frames * one.channels;
@@ -23,7 +35,8 @@ static int plan_starvations(const ohp_stream_spec& one, const ohp_schedule* a, u
             for (size_t i = 0; i < np; i++) {
                 const ohp_chunk_desc& d = prep[i];
                 const uint64_t dfb = (uint64_t)d.channels * (d.bit_depth / 8u);
-                if (d.src_off < one.src_base || d.src_off + d.bytes > one.src_base + one.total_frames * fb || d.bytes % dfb || d.dst_off % 4) { printf("plan reads outside the stream\n"); return 1; }
+                const bool silent = (d.flags & OHP_F_SILENCE) != 0;
+                if ((!silent && (d.src_off < one.src_base || d.src_off + d.bytes > one.src_base + one.total_frames * fb)) || d.bytes % dfb || d.dst_off % 4) { printf("plan reads outside the stream\n"); return 1; }
                 const uint64_t frames = d.bytes / dfb;
                 for (uint32_t c = 0; c < d.channels; c++) {
                     for (uint64_t i2 = 0; i2 < frames; i2++) {
@@ -41,6 +54,7 @@ static int plan_starvations(const ohp_stream_spec& one, const ohp_schedule* a, u
         else if (rc == OHP_E_INVALID_ARG || rc == OHP_E_INVALID_DESC) unplanned++;
         else { printf("plan status %d\n", rc); return 1; }
         free(prep); free(blocks);
+      }
     }
     return 0;
 }

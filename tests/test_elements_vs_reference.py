@@ -520,3 +520,89 @@ def test_the_cut_that_never_ends_is_recognised_not_run(ref, port):
             assert done.returncode == 0 and done.stdout.strip() == "-3", done.stderr[-2000:]
         else:
             assert rc == 0 and len(ramps) == 1 and audio.size == abi.FLYWHEEL_RAMP_JIFFIES // jps * 4
+
+
+def _flywheel_from_recent_on_cpu(port, st, starvation, recent, inp):
+    prep, job, blocks = capi.flywheel_plan_recent(st, starvation, recent)
+    assert capi.validate(prep, len(inp), int(job["train_frames"][0]) * 4 * int(st[0]["channels"])) == (abi.OK, 0)
+    rc, training = port.process_chunks(prep, inp, int(job["train_frames"][0]) * 4 * int(st[0]["channels"]))
+    assert rc == 0
+    rc, raw = port.flywheel(job, training, int(job["out_frames"][0]) * int(st[0]["channels"]) * int(st[0]["bit_depth"]) // 8)
+    assert rc == 0
+    rc, played = port.process_chunks(blocks, raw, raw.size)
+    assert rc == 0
+    return played, prep
+
+
+def test_silence_inside_the_last_millisecond_is_planned_from_the_recent_audio(ref, port):
+    """ohp_flywheel_plan_recent: the element's recent audio piece by piece.  96 kHz stereo 24-bit, a 1 ms MsgSilence ahead of
+    the message at 15 ms, the reservoir dry half a millisecond later: the training block is half silence, half audio, and
+    what the plan plays is what the real element plays.  The PCM-only plan refuses that starvation; where there is no
+    silence in the block both plans give the same descriptors."""
+    w = workloads.config5(n_streams=1, seconds=0.2)
+    st = w.streams.copy()
+    inp = port.fill_pcm(w.in_bytes, 3)
+    jps = abi.jiffies_per_sample(96000)
+    for at, with_silence in ((16 * MS + MS // 2, True), (16 * MS + MS // 4 + 3 * jps, True), (19 * MS, False)):
+        ev = workloads._events(sorted([(15 * MS, 0, abi.EV_INSERT_SILENCE, 96 * jps), (at, 1, abi.EV_STARVATION, 50 * MS)]))
+        st[0]["first_event"], st[0]["num_events"] = 0, len(ev)
+        sched = capi.schedule_build(st, ev)
+        sv = sched.starvations
+        assert len(sv) == 1 and int(sv["plays"][0]) == 1
+        pieces = sched.recent_of(0)
+        assert bool((pieces["silence"] != 0).any()) == with_silence or not with_silence
+        rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+        assert rc == 0 and len(ramps) == 1
+        played, prep = _flywheel_from_recent_on_cpu(port, st, sv[0:1], pieces, inp)
+        assert np.array_equal(played, audio), at
+        if with_silence:
+            assert ((prep["flags"] & abi.F_SILENCE) != 0).any() and ((prep["flags"] & abi.F_SILENCE) == 0).any()
+            with pytest.raises(capi.OhpError):
+                capi.flywheel_plan(st, sv[0:1])
+        else:
+            assert np.array_equal(prep, capi.flywheel_plan(st, sv[0:1])[0])
+
+
+@pytest.mark.parametrize("seed", [41, 42, 43, 44])
+def test_recent_audio_plans_on_random_element_schedules(ref, port, seed):
+    """Random element schedules again, planned from the recent audio: everything the PCM-only plan gives comes out the same,
+    starvations with silence in their last millisecond are played as the real element plays them, and the plan says "the
+    reference does not return" exactly where the harness finds the cut that never ends (-3)."""
+    w = workloads.elements(seed, n_streams=30)
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    compared = with_silence = never = 0
+    for s in range(len(w.streams)):
+        st, ev = one_stream(w, s)
+        if not (ev["op"] == abi.EV_STARVATION).any():
+            continue
+        sched = capi.schedule_build(st, ev)
+        sv = sched.starvations
+        playing_at = np.nonzero(sv["plays"] == 1)[0]
+        verdicts = []
+        for k in playing_at:
+            try:
+                verdicts.append(_flywheel_from_recent_on_cpu(port, st, sv[k:k + 1], sched.recent_of(int(k)), inp))
+            except capi.OhpError as e:
+                verdicts.append(e)
+        says_never = any(isinstance(v, capi.OhpError) and v.status == abi.E_INVALID_DESC and "does not return" in str(v) for v in verdicts)
+        rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+        assert (rc == -3) == says_never, (seed, s, rc)
+        if rc == -3:
+            never += 1
+            continue
+        assert rc == 0 and len(ramps) == len(playing_at)
+        per = audio.size // max(1, len(playing_at))
+        for j, (k, v) in enumerate(zip(playing_at, verdicts)):
+            if isinstance(v, capi.OhpError):
+                continue
+            played, prep = v
+            assert np.array_equal(played, audio[j * per:(j + 1) * per]), (seed, s, int(k))
+            compared += 1
+            if ((prep["flags"] & abi.F_SILENCE) != 0).any():
+                with_silence += 1
+            else:
+                try:
+                    assert np.array_equal(prep, capi.flywheel_plan(st, sv[k:k + 1])[0])
+                except capi.OhpError:
+                    pass  # (a change of attenuation inside the block: the PCM-only plan declines)
+    assert compared >= 20
