@@ -242,6 +242,11 @@ typedef struct ohp_flywheel_batch ohp_flywheel_batch;
 int    ohp_flywheel_plan_batch(const ohp_stream_spec* streams, size_t n_streams,
                                const ohp_starvation* starvations, size_t n_starvations,
                                uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out);
+/* ... planned from the recent audio (ohp_flywheel_plan_recent): recent / recent_begin as ohp_schedule_build left them */
+int    ohp_flywheel_plan_batch_recent(const ohp_stream_spec* streams, size_t n_streams,
+                                      const ohp_starvation* starvations, size_t n_starvations,
+                                      const ohp_recent_audio* recent, const uint64_t* recent_begin,
+                                      uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out);
 size_t ohp_flywheel_batch_num_planned(const ohp_flywheel_batch* b);
 const uint32_t* ohp_flywheel_batch_planned(const ohp_flywheel_batch* b);   /* indices into `starvations`, ascending      */
 const uint64_t* ohp_flywheel_batch_out_off(const ohp_flywheel_batch* b);   /* per planned starvation                     */

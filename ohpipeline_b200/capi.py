@@ -159,6 +159,9 @@ def host_lib():
         L.ohp_flywheel_plan_batch.restype = C.c_int
         L.ohp_flywheel_plan_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.POINTER(C.c_void_p)]
+        L.ohp_flywheel_plan_batch_recent.restype = C.c_int
+        L.ohp_flywheel_plan_batch_recent.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                     C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
         for name in ("num_planned", "num_prep", "num_blocks"):
             f = getattr(L, "ohp_flywheel_batch_" + name); f.restype = C.c_size_t; f.argtypes = [C.c_void_p]
         for name in ("planned", "out_off", "out_len", "prep", "jobs", "blocks"):
@@ -226,14 +229,24 @@ class FlywheelBatch:
         self.training_bytes, self.generated_bytes, self.out_bytes = arena_bytes
 
 
-def flywheel_plan_batch(streams, starvations, training_base=0, generated_base=0, out_base=0):
+def flywheel_plan_batch(streams, starvations, training_base=0, generated_base=0, out_base=0, recent=None, recent_begin=None):
+    """ohp_flywheel_plan_batch; with recent / recent_begin (Schedule.recent, .recent_begin) ohp_flywheel_plan_batch_recent."""
     streams = np.ascontiguousarray(streams, dtype=abi.STREAM_SPEC)
     starvations = np.ascontiguousarray(starvations, dtype=abi.STARVATION)
     L = host_lib()
     h = C.c_void_p()
-    rc = L.ohp_flywheel_plan_batch(_ptr(streams) if len(streams) else None, len(streams),
-                                   _ptr(starvations) if len(starvations) else None, len(starvations),
-                                   C.c_uint64(training_base), C.c_uint64(generated_base), C.c_uint64(out_base), C.byref(h))
+    if recent_begin is not None:
+        recent = np.ascontiguousarray(recent, dtype=abi.RECENT_AUDIO)
+        recent_begin = np.ascontiguousarray(recent_begin, dtype=np.uint64)
+        assert len(recent_begin) == len(starvations) + 1 and int(recent_begin[-1]) <= len(recent)
+        rc = L.ohp_flywheel_plan_batch_recent(_ptr(streams) if len(streams) else None, len(streams),
+                                              _ptr(starvations) if len(starvations) else None, len(starvations),
+                                              _ptr(recent) if len(recent) else None, _ptr(recent_begin),
+                                              C.c_uint64(training_base), C.c_uint64(generated_base), C.c_uint64(out_base), C.byref(h))
+    else:
+        rc = L.ohp_flywheel_plan_batch(_ptr(streams) if len(streams) else None, len(streams),
+                                       _ptr(starvations) if len(starvations) else None, len(starvations),
+                                       C.c_uint64(training_base), C.c_uint64(generated_base), C.c_uint64(out_base), C.byref(h))
     if rc != 0:
         raise OhpError(rc, L.ohp_schedule_last_error().decode())
     try:

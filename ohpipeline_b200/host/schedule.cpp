@@ -558,8 +558,27 @@ int ohp_flywheel_plan_recent(const ohp_stream_spec* stream, const ohp_starvation
     return OHP_OK;
 }
 
+static int plan_batch(const ohp_stream_spec* streams, size_t n_streams, const ohp_starvation* starvations, size_t n_starvations,
+                      const ohp_recent_audio* recent, const uint64_t* recent_begin,
+                      uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out);
+
 int ohp_flywheel_plan_batch(const ohp_stream_spec* streams, size_t n_streams, const ohp_starvation* starvations, size_t n_starvations,
                             uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out)
+{
+    return plan_batch(streams, n_streams, starvations, n_starvations, nullptr, nullptr, training_base, generated_base, out_base, out);
+}
+
+int ohp_flywheel_plan_batch_recent(const ohp_stream_spec* streams, size_t n_streams, const ohp_starvation* starvations, size_t n_starvations,
+                                   const ohp_recent_audio* recent, const uint64_t* recent_begin,
+                                   uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out)
+{
+    if (!recent_begin || (!recent && n_starvations && recent_begin[n_starvations] != 0)) return OHP_E_INVALID_ARG;
+    return plan_batch(streams, n_streams, starvations, n_starvations, recent, recent_begin, training_base, generated_base, out_base, out);
+}
+
+static int plan_batch(const ohp_stream_spec* streams, size_t n_streams, const ohp_starvation* starvations, size_t n_starvations,
+                      const ohp_recent_audio* recent, const uint64_t* recent_begin,
+                      uint64_t training_base, uint64_t generated_base, uint64_t out_base, ohp_flywheel_batch** out)
 {
     if (!out) return OHP_E_INVALID_ARG;
     *out = nullptr;
@@ -575,12 +594,15 @@ int ohp_flywheel_plan_batch(const ohp_stream_spec* streams, size_t n_streams, co
             return OHP_E_INVALID_ARG;
         }
         const ohp_stream_spec& sp = streams[sv.stream];
-        ohp_chunk_desc prep[OHP_FLYWHEEL_MAX_PREP];
+        ohp_chunk_desc prep[64];
         ohp_chunk_desc blocks[OHP_FLYWHEEL_RAMP_JIFFIES / OHP_FLYWHEEL_BLOCK_JIFFIES + 1];
         ohp_flywheel_job job;
         size_t n_prep = 0, n_blocks = 0;
-        const int rc = ohp_flywheel_plan(&sp, &sv, training, generated, played, prep, &n_prep, &job, blocks,
-                                         sizeof blocks / sizeof blocks[0], &n_blocks);
+        const int rc = recent_begin
+            ? ohp_flywheel_plan_recent(&sp, &sv, recent + recent_begin[k], (size_t)(recent_begin[k + 1] - recent_begin[k]), training, generated,
+                                       played, prep, sizeof prep / sizeof prep[0], &n_prep, &job, blocks, sizeof blocks / sizeof blocks[0], &n_blocks)
+            : ohp_flywheel_plan(&sp, &sv, training, generated, played, prep, &n_prep, &job, blocks,
+                                sizeof blocks / sizeof blocks[0], &n_blocks);
         if (rc == OHP_E_INVALID_ARG || rc == OHP_E_INVALID_DESC) continue; // plays nothing / not planned / the reference ASSERTs
         if (rc != OHP_OK) return rc;
         const uint64_t frame_bytes = (uint64_t)sp.channels * (sp.bit_depth / 8u);

@@ -606,3 +606,44 @@ def test_recent_audio_plans_on_random_element_schedules(ref, port, seed):
                 except capi.OhpError:
                     pass  # (a change of attenuation inside the block: the PCM-only plan declines)
     assert compared >= 20
+
+
+def test_a_batch_planned_from_the_recent_audio(ref, port):
+    """ohp_flywheel_plan_batch_recent over a whole batch of random element schedules, silence under the starvations and all:
+    three calls over the batch, and at out_off[k] what the k-th planned starving element of the reference played.  It plans
+    everything the PCM-only batch plans, and more."""
+    w = workloads.elements(51, n_streams=60)
+    inp = port.fill_pcm(w.in_bytes, w.seed)
+    sched = capi.schedule_build(w.streams, w.events)
+    sv = sched.starvations
+    b = capi.flywheel_plan_batch(w.streams, sv, recent=sched.recent, recent_begin=sched.recent_begin)
+    plain = capi.flywheel_plan_batch(w.streams, sv)
+    assert set(int(k) for k in plain.planned) < set(int(k) for k in b.planned)
+    assert capi.validate(b.prep, w.in_bytes, b.training_bytes) == (abi.OK, 0)
+    assert capi.flywheel_validate(b.jobs, b.training_bytes, b.generated_bytes) == (abi.OK, 0)
+    rc, training = port.process_chunks(b.prep, inp, b.training_bytes)
+    assert rc == 0
+    rc, generated = port.flywheel(b.jobs, training, b.generated_bytes)
+    assert rc == 0
+    rc, out = port.process_chunks(b.blocks, generated, b.out_bytes)
+    assert rc == 0
+    at = {int(k): i for i, k in enumerate(b.planned)}
+    playing = np.nonzero(sv["plays"] == 1)[0]
+    compared = silent = 0
+    for s in range(len(w.streams)):
+        mine = [int(k) for k in playing if int(sv["stream"][k]) == s]
+        if not mine:
+            continue
+        st, ev = one_stream(w, s)
+        rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+        if rc == -3:
+            continue
+        assert rc == 0 and len(ramps) == len(mine)
+        per = audio.size // len(mine)
+        for j, k in enumerate(mine):
+            if k in at:
+                i = at[k]
+                assert np.array_equal(out[int(b.out_off[i]):int(b.out_off[i]) + per], audio[j * per:(j + 1) * per]), (s, k)
+                compared += 1
+                silent += int((sched.recent_of(k)["silence"] != 0).any())
+    assert compared >= 40 and silent >= 1
