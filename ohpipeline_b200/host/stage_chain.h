@@ -145,6 +145,17 @@ public:
             frame += frames;
             srcJiffies += (uint64_t)frames * iJps;
         }
+        // A reservoir that runs dry exactly where the stream ends still starves its StarvationRamper (there is no message left
+        // for the event to be applied ahead of, and nothing of the stream's own audio for it to change): recorded
+        for (unsigned i = 0; i < OHP_MAX_STAGES && iErr == 0 && iStarvationLog != nullptr; i++) {
+            Stage& s = iStages[i];
+            uint32_t ei;
+            while (s.elem == ElemStarvation && NextStageEvent(i, ei) && iEvents[ei].at_jiffies <= s.pos) {
+                NoteStarvation(s, ei);
+                (void)ApplyElementEvent(s, iEvents[ei]); // OHP_EV_HALT / OHP_EV_STARVATION: state only
+                s.nextEv = ei + 1;
+            }
+        }
         return iErr;
     }
 
