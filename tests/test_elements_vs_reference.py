@@ -647,3 +647,23 @@ def test_a_batch_planned_from_the_recent_audio(ref, port):
                 compared += 1
                 silent += int((sched.recent_of(k)["silence"] != 0).any())
     assert compared >= 40 and silent >= 1
+
+
+def test_a_reservoir_dry_exactly_where_the_stream_ends(ref, port):
+    """The last message has passed and the reservoir is empty: the element starves there as anywhere (found by the campaign,
+    seed 200924).  The stream's own playables are what they were; the starvation is recorded and its flywheel ramp planned."""
+    w = workloads.config5(n_streams=1, seconds=0.1)
+    st = w.streams.copy()
+    inp = port.fill_pcm(w.in_bytes, 9)
+    end = int(st[0]["total_frames"]) * abi.jiffies_per_sample(96000)
+    ev = workloads._events([(end, 1, abi.EV_STARVATION, 50 * MS)])
+    st[0]["first_event"], st[0]["num_events"] = 0, 1
+    sched = capi.schedule_build(st, ev)
+    sv = sched.starvations
+    assert len(sv) == 1 and int(sv["plays"][0]) == 1 and int(sv["pcm_jiffies"][0]) == end
+    rc, audio, ramps = ref.elements_generated_audio(st, ev, inp)
+    assert rc == 0 and len(ramps) == 1 and int(ramps[0]) == int(sv["ramp"][0])
+    assert np.array_equal(_flywheel_on_cpu(port, st, sv[0:1], inp), audio)
+    assert np.array_equal(_flywheel_from_recent_on_cpu(port, st, sv[0:1], sched.recent_of(0), inp)[0], audio)
+    # the walk the GPU compiles produces the same playables (it keeps no starvation records)
+    assert np.array_equal(capi.schedule_build(st, ev, walk=True).chunks, sched.chunks)
